@@ -1,0 +1,173 @@
+// geom.cuh -- curve flattening shared by the flatten kernel (device) and the
+// host front end (is_point_in_path needs a synchronous flattening, reference
+// src/canvas_ity.hpp:3101-3132).
+//
+// Behavioural spec (reference "hpp" = src/canvas_ity.hpp):
+//   flatten_cubic      == add_bezier        hpp:1398-1487
+//   subdivide_piece    == add_tessellation  hpp:1331-1387 (recursion -> explicit stack)
+//   stroke_angular     == path_to_lines     hpp:1498-1500
+// Every float operation keeps the reference's association order and this file
+// must be compiled without FMA contraction (-fmad=false / -ffp-contract=off):
+// the flatness, angle and cut tests are discontinuous decisions.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#else
+#define CB_HD inline
+#endif
+
+namespace cb200 {
+
+struct vec2 { float x, y; };
+
+CB_HD vec2 v2(float x, float y) { vec2 r; r.x = x; r.y = y; return r; }
+CB_HD vec2 operator+(vec2 a, vec2 b) { return v2(a.x + b.x, a.y + b.y); }
+CB_HD vec2 operator-(vec2 a, vec2 b) { return v2(a.x - b.x, a.y - b.y); }
+CB_HD vec2 operator*(float s, vec2 a) { return v2(a.x * s, a.y * s); }
+CB_HD float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+CB_HD vec2 perp(vec2 a) { return v2(-a.y, a.x); }
+CB_HD vec2 mix(vec2 a, vec2 b, float t) { return a + t * (b - a); }
+CB_HD float vlen(vec2 a) { return sqrtf(dot(a, a)); }
+CB_HD vec2 unit(vec2 a) { return (1.0f / fmaxf(1.0e-6f, vlen(a))) * a; }
+CB_HD float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+struct affine { float a, b, c, d, e, f; };
+CB_HD vec2 apply(const affine &m, vec2 p) {
+    return v2(m.a * p.x + m.c * p.y + m.e, m.b * p.x + m.d * p.y + m.f);
+}
+
+// Cosine of the largest turn a stroked curve piece may keep (hpp:1498-1500);
+// fills use -1 which also switches the emission rule (end points only).
+CB_HD float stroke_angular(float line_width) {
+    const float tolerance = 0.125f;
+    float ratio = tolerance / fmaxf(0.5f * line_width, tolerance);
+    return (ratio - 2.0f) * ratio * 2.0f + 1.0f;
+}
+
+// One monotone piece: halve until both inner control points sit within 1/8 px
+// of the chord and (strokes) the turn stays under the angular limit; depth cap
+// 20.  Left halves first so points come out in curve order.  `Sink::put(vec2)`.
+template <class Sink>
+CB_HD void subdivide_piece(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink)
+{
+    const bool stroking = angular > -1.0f;
+    // pending right halves; their start point is wherever the left subtree ends
+    vec2 stack_c1[21], stack_c2[21], stack_p3[21];
+    int stack_budget[21];
+    int depth = 0;
+    int budget = 20;
+    for (;;) {
+        vec2 e1 = c1 - p0, e2 = c2 - c1, e3 = p3 - c2, chord = p3 - p0;
+        float q1 = dot(e1, e1), q2 = dot(e2, e2), q3 = dot(e3, e3);
+        float chord2 = fmaxf(1.0e-4f, dot(chord, chord));
+        float t1 = clamp01(dot(e1, chord) / chord2);
+        float t2 = clamp01(dot(e3, chord) / chord2);
+        vec2 off1 = p0 + t1 * chord - c1;
+        vec2 off2 = p3 - t2 * chord - c2;
+        float cosine = 1.0f;
+        if (stroking) {
+            if (q1 * q3 != 0.0f) cosine = dot(e1, e3) / sqrtf(q1 * q3);
+            else if (q1 * q2 != 0.0f) cosine = dot(e1, e2) / sqrtf(q1 * q2);
+            else if (q2 * q3 != 0.0f) cosine = dot(e2, e3) / sqrtf(q2 * q3);
+        }
+        const float flat2 = 0.125f * 0.125f;
+        bool done = (dot(off1, off1) <= flat2 && dot(off2, off2) <= flat2 &&
+                     cosine >= angular) || budget == 0;
+        if (done) {
+            // strokes also get the control points so joins see true tangents
+            if (stroking && q1 != 0.0f) sink.put(c1);
+            if (stroking && q2 != 0.0f) sink.put(c2);
+            if (angular == -1.0f || q3 != 0.0f) sink.put(p3);
+            if (depth == 0) return;
+            --depth;
+            p0 = p3;                       // right half starts where we stopped
+            c1 = stack_c1[depth]; c2 = stack_c2[depth]; p3 = stack_p3[depth];
+            budget = stack_budget[depth];
+            continue;
+        }
+        vec2 l1 = mix(p0, c1, 0.5f);
+        vec2 mid = mix(c1, c2, 0.5f);
+        vec2 r2 = mix(c2, p3, 0.5f);
+        vec2 l2 = mix(l1, mid, 0.5f);
+        vec2 r1 = mix(mid, r2, 0.5f);
+        vec2 split = mix(l2, r1, 0.5f);
+        --budget;
+        stack_c1[depth] = r1; stack_c2[depth] = r2; stack_p3[depth] = p3;
+        stack_budget[depth] = budget;
+        ++depth;
+        c1 = l1; c2 = l2; p3 = split;
+    }
+}
+
+// Roots of the derivative's quadratic a t^2 + b t + c on one axis, in the
+// cancellation-free form (hpp:1420-1434).  Appends to cut[n...].
+CB_HD int axis_extrema(float a, float b, float c, float *cut, int n)
+{
+    const float eps = 1.0e-4f;
+    if (fabsf(a) > eps) {
+        float disc = b * b - 4.0f * a * c;
+        if (disc >= 0.0f) {
+            float sgn = b > 0.0f ? 1.0f : -1.0f;
+            float q = -b - sgn * sqrtf(disc);
+            float r = q / (2.0f * a);
+            cut[n++] = r;
+            cut[n++] = c / (a * r);
+        }
+    } else if (fabsf(b) > eps)
+        cut[n++] = -c / b;
+    return n;
+}
+
+// A whole cubic: cut at x/y extrema and at the curvature extremum so every
+// piece is monotone and turns < 90 degrees, then subdivide each piece.
+template <class Sink>
+CB_HD void flatten_cubic(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink)
+{
+    vec2 e1 = c1 - p0, e2 = c2 - c1, e3 = p3 - c2;
+    if (dot(e1, e1) == 0.0f && dot(e3, e3) == 0.0f) {   // a line (or a point)
+        sink.put(p3);
+        return;
+    }
+    float cut[7];
+    cut[0] = 0.0f; cut[1] = 1.0f;
+    int n = 2;
+    vec2 qa = -9.0f * e2 + 3.0f * (p3 - p0);
+    vec2 qb = 6.0f * (p0 + c2) - 12.0f * c1;
+    vec2 qc = 3.0f * e1;
+    n = axis_extrema(qa.x, qb.x, qc.x, cut, n);
+    n = axis_extrema(qa.y, qb.y, qc.y, cut, n);
+    float d12 = dot(perp(e1), e2), d13 = dot(perp(e1), e3), d23 = dot(perp(e2), e3);
+    float ka = d12 - d13 + d23;
+    float kb = -2.0f * d12 + d13;
+    if (fabsf(ka) > 1.0e-4f && fabsf(kb) > 1.0e-4f)
+        cut[n++] = -0.5f * kb / ka;
+    for (int i = 1; i < n; ++i) {          // tiny insertion sort, NaNs stay put
+        float v = cut[i];
+        int j = i - 1;
+        for (; j >= 0 && v < cut[j]; --j) cut[j + 1] = cut[j];
+        cut[j + 1] = v;
+    }
+    vec2 from = p0;
+    for (int i = 0; i + 1 < n; ++i) {
+        float lo = cut[i], hi = cut[i + 1];
+        if (!(0.0f <= lo && hi <= 1.0f && lo != hi)) continue;
+        // blossom [lo,hi]: de Casteljau at hi, then again at lo/hi from the left
+        float rel = lo / hi;
+        vec2 a1 = mix(p0, c1, hi), a2 = mix(c1, c2, hi), a3 = mix(c2, p3, hi);
+        vec2 b1 = mix(a1, a2, hi), b2 = mix(a2, a3, hi);
+        vec2 g = mix(a1, b1, rel);
+        vec2 to = mix(b1, b2, hi);
+        vec2 k2 = mix(b1, to, rel);
+        vec2 k1 = mix(g, k2, rel);
+        subdivide_piece(from, k1, k2, to, angular, sink);
+        from = to;
+    }
+}
+
+struct count_sink { int n; CB_HD void put(vec2) { ++n; } };
+struct write_sink { vec2 *out; int n; CB_HD void put(vec2 p) { out[n++] = p; } };
+
+} // namespace cb200

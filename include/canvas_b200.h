@@ -1,0 +1,189 @@
+/* canvas_b200.h -- C ABI of the B200 rasterise + composite back end.
+ *
+ * This is the drop-in boundary for canvas_ity's data-parallel hot path.  The
+ * reference (src/canvas_ity.hpp, "hpp" below) has no FFI of its own: its seam is
+ * the private call chain behind the draw entry points
+ *     fill()            hpp:3044   path_to_lines + render_main
+ *     stroke()          hpp:3050   path_to_lines + stroke_lines + render_main
+ *     clip()            hpp:3057   path_to_lines + lines_to_runs + mask product
+ *     fill_rectangle()  hpp:3155 / stroke_rectangle() hpp:3174 / draw_image() hpp:3313
+ *     fill_text()       hpp:3276 / stroke_text() hpp:3286
+ *     get_image_data()  hpp:3348 / put_image_data()  hpp:3383
+ * Host C++ keeps recording state and device-space cubic paths exactly as the
+ * reference does (hpp:2866-3042) and lowers every draw call to one cb200_draw
+ * record; cb200_submit() replaces everything the reference does below those
+ * entry points (hpp:1331-2605) with sm_100a kernels.
+ *
+ * Plain C: pointers + sizes only, no C++/torch types.  Every function returns
+ * 0 on success or a negative cb200_status; nothing throws across this ABI.
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * CB200_ERR_NO_DEVICE.
+ */
+#ifndef CANVAS_B200_H
+#define CANVAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_ABI_VERSION 1
+
+typedef enum cb200_status {
+    CB200_OK = 0,
+    CB200_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: there is no CPU path */
+    CB200_ERR_BAD_ARG = -2,
+    CB200_ERR_CUDA = -3,        /* see cb200_last_error() */
+    CB200_ERR_OOM = -4,
+    CB200_ERR_OVERFLOW = -5     /* a device work queue overflowed even after regrowth */
+} cb200_status;
+
+/* ---- lowered draw records (the data contract, hpp:159-175) ---------------- */
+
+/* cb200_draw.kind */
+enum { CB200_FILL = 0, CB200_STROKE = 1, CB200_CLIP = 2 };
+/* cb200_brush.type == paint_brush::types, hpp:162 */
+enum { CB200_BRUSH_COLOR = 0, CB200_BRUSH_LINEAR = 1, CB200_BRUSH_RADIAL = 2,
+       CB200_BRUSH_PATTERN = 3 };
+/* cb200_brush.flags */
+enum { CB200_BRUSH_CLAMP = 1 };   /* draw_image addressing, hpp:2306/2319 */
+
+/* One subpath: a start point followed by n_cubics * 3 control points, all in
+ * device space (hpp:2878-2882).  Lines are degenerate cubics (hpp:2913-2916). */
+typedef struct cb200_subpath {
+    uint32_t first_point;   /* index into cb200_frame.points (xy pairs) */
+    uint32_t n_cubics;      /* subpath owns 1 + 3 * n_cubics points */
+    uint32_t closed;        /* subpath_data.closed, hpp:169 */
+    uint32_t reserved;
+} cb200_subpath;
+
+/* paint_brush (hpp:162-165) flattened.  Colours: solid = 1 premultiplied
+ * linear rgba; gradients = n_colors unpremultiplied linear stops (hpp:2834);
+ * pattern = an entry of cb200_frame.images. */
+typedef struct cb200_brush {
+    uint32_t type;
+    uint32_t flags;
+    uint32_t first_color;   /* index into colors[] (rgba quads) and stops[] */
+    uint32_t n_colors;
+    float    start[2], end[2];
+    float    start_radius, end_radius;
+    uint32_t image;         /* pattern: index into images[] */
+    uint32_t repetition;    /* repetition_style bit set, hpp:153 / 2278-2282 */
+} cb200_brush;
+
+/* A straight-alpha sRGB RGBA8 image (what set_pattern/draw_image receive,
+ * hpp:2839/3313); converted on the device to premultiplied linear float. */
+typedef struct cb200_image {
+    uint64_t texel_offset;  /* byte offset into cb200_frame.texels, tightly packed rows */
+    int32_t  width, height;
+} cb200_image;
+
+/* State snapshot of one fill/stroke/clip (everything render_main, render_shadow,
+ * stroke_lines and dash_lines read, hpp:1858-2605). */
+typedef struct cb200_draw {
+    uint32_t kind;
+    uint32_t op;            /* composite_operation value = 4-bit mix program, hpp:146-149 */
+    uint32_t first_subpath, n_subpaths;
+    uint32_t brush;
+    uint32_t mask_src;      /* clip-mask slot that gates this draw; 0 = whole canvas */
+    uint32_t mask_dst;      /* CB200_CLIP: slot that receives coverage * mask_src */
+    uint32_t cap, join;     /* cap_style / join_style, hpp:150-151 */
+    uint32_t first_dash, n_dash;
+    float    dash_offset;
+    float    global_alpha;
+    float    line_width, miter_limit;
+    float    forward[6], inverse[6];   /* affine_matrix a..f, hpp:161 */
+    float    shadow_color[4];          /* premultiplied linear, hpp:2726 */
+    float    shadow_offset_x, shadow_offset_y, shadow_blur;
+    uint32_t reserved;
+} cb200_draw;
+
+typedef struct cb200_frame {
+    const cb200_draw    *draws;     uint32_t n_draws;
+    const cb200_subpath *subpaths;  uint32_t n_subpaths;
+    const float         *points;    uint32_t n_points;    /* xy pairs */
+    const cb200_brush   *brushes;   uint32_t n_brushes;
+    const float         *colors;    /* rgba quads */
+    const float         *stops;     uint32_t n_colors;
+    const float         *dashes;    uint32_t n_dashes;
+    const cb200_image   *images;    uint32_t n_images;
+    const uint8_t       *texels;    uint64_t texel_bytes;
+} cb200_frame;
+
+/* ---- canvases --------------------------------------------------------------- */
+
+typedef struct cb200_canvas cb200_canvas;
+
+/* New canvas, all pixels transparent black, mask slot 0 = everything visible
+ * (ctor, hpp:2607-2644).  `device` is a CUDA ordinal. */
+int cb200_canvas_create(int width, int height, int device, cb200_canvas **out);
+
+/* A canvas that owns only scanlines [band_y0, band_y0 + band_rows) of a
+ * width x height image; geometry stays in full-image coordinates. */
+int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows,
+                             int device, cb200_canvas **out);
+
+void cb200_canvas_destroy(cb200_canvas *canvas);
+
+/* Run `frame` (draws in order) on the canvas' stream.  Asynchronous: returns
+ * once the frame is copied to pinned staging and the kernels are enqueued. */
+int cb200_submit(cb200_canvas *canvas, const cb200_frame *frame);
+
+/* Upload a frame once, then replay it with no host<->device traffic
+ * (device-resident timing; the framebuffer is cleared first when `clear`). */
+int cb200_frame_upload(cb200_canvas *canvas, const cb200_frame *frame);
+int cb200_frame_replay(cb200_canvas *canvas, int clear);
+
+/* Wait for everything enqueued on the canvas' stream. */
+int cb200_sync(cb200_canvas *canvas);
+
+/* get_image_data (hpp:3348): sRGB + 4x4 ordered dither to straight-alpha RGBA8.
+ * (x, y) is the canvas-space origin of the destination; out-of-canvas = 0. */
+int cb200_read_rgba8(cb200_canvas *canvas, uint8_t *dst, int width, int height,
+                     int stride, int x, int y);
+/* put_image_data (hpp:3383). */
+int cb200_write_rgba8(cb200_canvas *canvas, const uint8_t *src, int width,
+                      int height, int stride, int x, int y);
+/* Linear premultiplied float RGBA framebuffer, band_rows * width * 4 floats. */
+int cb200_read_f32(cb200_canvas *canvas, float *dst);
+/* Clip-mask slot as dense visibility, band_rows * width floats. */
+int cb200_read_mask(cb200_canvas *canvas, uint32_t slot, float *dst);
+/* Clear to transparent black and forget all mask slots. */
+int cb200_clear(cb200_canvas *canvas);
+/* Copy mask slot `src` to `dst` is never needed: slots are immutable once
+ * written.  The host may recycle a slot id after the frame that last used it. */
+
+/* Readback without the host copy: runs the sRGB/dither kernel into a device
+ * buffer owned by the canvas and returns its device pointer (for NCCL gathers
+ * and device-resident timing). */
+int cb200_read_rgba8_device(cb200_canvas *canvas, void **device_ptr);
+
+/* ---- introspection / measurement ------------------------------------------- */
+
+typedef struct cb200_stats {
+    uint64_t draws, cubics, line_points, edges, raw_runs, tile_entries,
+             composited_pixels, shadow_pixels, kernel_launches;
+    float    last_frame_ms;        /* CUDA events on the canvas stream */
+    float    composite_ms;         /* the tile compositor only */
+    float    raster_ms, sort_ms, geometry_ms, readback_ms;
+} cb200_stats;
+
+int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);
+
+/* Debug taps used by the parity tests: intermediate buffers of the last frame.
+ * Each returns the element count (>= 0) and copies at most `capacity`. */
+int64_t cb200_debug_lines(cb200_canvas *canvas, float *xy_pairs, uint32_t *job_of_edge,
+                          int64_t capacity);       /* edges: 4 floats each */
+int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative,
+                         int64_t capacity);        /* sorted (job,y,x) runs */
+
+const char *cb200_last_error(void);
+int cb200_abi_version(void);
+int cb200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANVAS_B200_H */

@@ -1,0 +1,82 @@
+// ref_api.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// The unmodified reference (REFERENCE_HPP = /root/reference/src/canvas_ity.hpp,
+// compiled from where it lies; never copied into this repo) behind the flat C
+// API of include/canvas_b200_api.h.  Built by oracle/Makefile into
+// oracle/_ref/libcanvas_ref.so with -ffp-contract=off (bit-identical to -O0,
+// SURVEY 7.4) and -fno-access-control so cv_read_f32 can reach the private float
+// `bitmap` (reference :1171).  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load the result.
+#define CANVAS_ITY_IMPLEMENTATION
+#include REFERENCE_HPP
+
+#include "../canvas_ity_b200/csrc/host/script.hpp"
+#include "../include/canvas_b200_api.h"
+
+#include <cstring>
+#include <string>
+
+namespace {
+struct ns_tag {
+    typedef canvas_ity::composite_operation composite_operation;
+    typedef canvas_ity::cap_style cap_style;
+    typedef canvas_ity::join_style join_style;
+    typedef canvas_ity::brush_type brush_type;
+    typedef canvas_ity::repetition_style repetition_style;
+    typedef canvas_ity::align_style align_style;
+    typedef canvas_ity::baseline_style baseline_style;
+};
+canvas_ity::canvas *ref(cv_canvas *c) { return reinterpret_cast<canvas_ity::canvas *>(c); }
+}
+
+extern "C" {
+
+cv_canvas *cv_create(int width, int height)
+{
+    return reinterpret_cast<cv_canvas *>(new canvas_ity::canvas(width, height));
+}
+cv_canvas *cv_create_band(int, int, int, int, int) { return nullptr; }
+cv_canvas *cv_create_tapped(int, int, cv_frame_fn, cv_read_fn, cv_write_fn, void *) { return nullptr; }
+void cv_destroy(cv_canvas *c) { delete ref(c); }
+
+long cv_run_script(cv_canvas *canvas, const uint8_t *script, size_t bytes, uint32_t *queries,
+                   int query_capacity, int *n_queries)
+{
+    std::vector<cb200_script::query_result> q;
+    long n = cb200_script::run_script<canvas_ity::canvas, ns_tag>(*ref(canvas), script, bytes, &q);
+    if (n_queries) *n_queries = int(q.size());
+    for (int i = 0; queries && i < query_capacity && i < int(q.size()); ++i) {
+        queries[i * 4 + 0] = q[size_t(i)].code;
+        queries[i * 4 + 1] = q[size_t(i)].got_bits;
+        queries[i * 4 + 2] = q[size_t(i)].recorded_bits;
+        queries[i * 4 + 3] = 0;
+    }
+    return n;
+}
+
+int cv_get_image_data(cv_canvas *c, uint8_t *image, int w, int h, int stride, int x, int y)
+{
+    ref(c)->get_image_data(image, w, h, stride, x, y);
+    return 0;
+}
+int cv_put_image_data(cv_canvas *c, const uint8_t *image, int w, int h, int stride, int x, int y)
+{
+    ref(c)->put_image_data(image, w, h, stride, x, y);
+    return 0;
+}
+int cv_is_point_in_path(cv_canvas *c, float x, float y) { return ref(c)->is_point_in_path(x, y); }
+float cv_measure_text(cv_canvas *c, const char *text) { return ref(c)->measure_text(text); }
+int cv_flush(cv_canvas *) { return 0; }
+
+int cv_read_f32(cv_canvas *c, float *dst)
+{
+    canvas_ity::canvas *r = ref(c);
+    memcpy(dst, r->bitmap, sizeof(float) * 4 * size_t(r->size_x) * size_t(r->size_y));
+    return 0;
+}
+
+cb200_canvas *cv_device(cv_canvas *) { return nullptr; }
+const char *cv_last_error(void) { return ""; }
+const char *cv_backend_name(void) { return "reference"; }
+
+}  // extern "C"
