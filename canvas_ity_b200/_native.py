@@ -1,0 +1,97 @@
+"""ctypes loader for libcanvas_b200.so (the product) -- fails loudly, never falls back.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` /
+``make -C canvas_ity_b200/csrc``.  Signatures mirror include/canvas_b200.h and
+include/canvas_b200_api.h one to one.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcanvas_b200.so")
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("draws", "cubics", "line_points", "edges", "raw_runs", "tile_entries",
+                                           "composited_pixels", "shadow_pixels", "kernel_launches")] + \
+               [(n, C.c_float) for n in ("last_frame_ms", "composite_ms", "raster_ms", "sort_ms", "geometry_ms",
+                                         "readback_ms")]
+
+
+class Frame(C.Structure):          # cb200_frame
+    _fields_ = [("draws", C.c_void_p), ("n_draws", C.c_uint32),
+                ("subpaths", C.c_void_p), ("n_subpaths", C.c_uint32),
+                ("points", C.c_void_p), ("n_points", C.c_uint32),
+                ("brushes", C.c_void_p), ("n_brushes", C.c_uint32),
+                ("colors", C.c_void_p), ("stops", C.c_void_p), ("n_colors", C.c_uint32),
+                ("dashes", C.c_void_p), ("n_dashes", C.c_uint32),
+                ("images", C.c_void_p), ("n_images", C.c_uint32),
+                ("texels", C.c_void_p), ("texel_bytes", C.c_uint64)]
+
+
+FRAME_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Frame))
+
+# name -> (restype, argtypes); every symbol the two headers declare
+SIGNATURES = {
+    # include/canvas_b200.h
+    "cb200_canvas_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cb200_canvas_create_band": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_void_p)]),
+    "cb200_canvas_destroy": (None, [C.c_void_p]),
+    "cb200_submit": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
+    "cb200_frame_upload": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
+    "cb200_frame_replay": (C.c_int, [C.c_void_p, C.c_int]),
+    "cb200_sync": (C.c_int, [C.c_void_p]),
+    "cb200_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
+    "cb200_write_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
+    "cb200_read_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cb200_read_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cb200_clear": (C.c_int, [C.c_void_p]),
+    "cb200_masks_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cb200_read_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "cb200_debug_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "cb200_debug_runs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "cb200_last_error": (C.c_char_p, []),
+    "cb200_abi_version": (C.c_int, []),
+    "cb200_device_count": (C.c_int, []),
+    # include/canvas_b200_api.h
+    "cv_create": (C.c_void_p, [C.c_int, C.c_int]),
+    "cv_create_band": (C.c_void_p, [C.c_int] * 5),
+    "cv_create_tapped": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cv_destroy": (None, [C.c_void_p]),
+    "cv_run_script": (C.c_long, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "cv_get_image_data": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
+    "cv_put_image_data": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
+    "cv_is_point_in_path": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "cv_measure_text": (C.c_float, [C.c_void_p, C.c_char_p]),
+    "cv_flush": (C.c_int, [C.c_void_p]),
+    "cv_read_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cv_device": (C.c_void_p, [C.c_void_p]),
+    "cv_last_error": (C.c_char_p, []),
+    "cv_backend_name": (C.c_char_p, []),
+}
+
+
+def bind(lib, names=None):
+    for name, (res, args) in SIGNATURES.items():
+        if names is not None and name not in names:
+            continue
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing: loud on purpose
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA back end.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "canvas_ity_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib

@@ -1,0 +1,880 @@
+// backend.cu -- the C ABI of include/canvas_b200.h: device canvases, frame
+// translation/upload and the fixed per-frame launch sequence.
+//
+// A submitted cb200_frame is translated on the host into device records
+// (draw_rec, subpath_rec, flatten units, raster jobs, ...), packed into ONE pinned
+// staging blob, copied with ONE cudaMemcpyAsync and processed by a fixed sequence
+// of frame-level kernels on the canvas' stream (see device/common.cuh).  Every
+// data-dependent size stays on the device; capacities are checked by the kernels
+// themselves (frame_header::overflow) and, if one was too small, the frame is
+// re-run with larger buffers before its result is ever observed -- the
+// compositor does not touch the framebuffer of an overflowed frame.
+//
+// There is no CPU fallback here: without a CUDA device cb200_canvas_create fails.
+#include "device/frame.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace cb200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &what)
+{
+    g_error = what;
+    return code;
+}
+
+#define CK(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? CB200_ERR_OOM : CB200_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+template <class T>
+struct dev_buf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host-side image of everything uploaded for one frame.
+struct staged_frame {
+    std::vector<draw_rec> draws;
+    std::vector<subpath_rec> subpaths;
+    std::vector<unit_rec> units;
+    std::vector<float> points;
+    std::vector<brush_rec> brushes;
+    std::vector<float> colors, stops, dashes;
+    std::vector<dash_item> dash_items;
+    std::vector<uint2> draw_src;
+    std::vector<stroke_src> sources;
+    std::vector<job_rec> jobs;
+    std::vector<uint32_t> shadow_jobs;
+    std::vector<uint8_t> texels_u8;
+    std::vector<float *> mask_table;
+    uint64_t n_texels = 0;
+    int key_bits = 0, bits_x = 0, bits_y = 0;
+    uint32_t n_dash_subpath_cap = 0;
+    bool valid = false;
+};
+
+int bits_for(uint32_t max_value)
+{
+    int b = 1;
+    while ((uint64_t(1) << b) <= max_value) ++b;
+    return b;
+}
+
+}  // namespace
+
+struct cb200_canvas {
+    int device = 0, width = 0, height = 0, band_y0 = 0, band_rows = 0;
+    cudaStream_t stream = nullptr;
+    float4 *fb = nullptr;
+    std::map<uint32_t, float *> masks;
+
+    // input blob (device + pinned host mirror)
+    dev_buf<uint8_t> blob;
+    uint8_t *pinned = nullptr;
+    size_t pinned_cap = 0;
+    frame_header *pinned_hdr = nullptr;       // readback of the header after a frame
+
+    // device work buffers
+    dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
+        half_count, half_offset, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
+        te_first, partials, sort_hist;
+    dev_buf<float2> pts;
+    dev_buf<loop_span> loops;
+    dev_buf<stroke_src> sources;
+    dev_buf<float4> pieces, texels;
+    dev_buf<uint64_t> keys0, keys1;
+    dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
+    dev_buf<uint8_t> rgba8;
+    uint8_t *pinned_rgba8 = nullptr;
+    size_t pinned_rgba8_cap = 0;
+
+    uint32_t cap_pts = 0, cap_items = 0, cap_rows = 0, cap_runs = 0, cap_tiles = 0, cap_sources = 0,
+             cap_dash_subpaths = 0;
+    uint64_t cap_planes = 0;
+
+    staged_frame staged;
+    device_frame df;
+    canvas_target target;
+    bool pending = false;                     // a frame was launched and not yet verified
+    bool resident = false;                    // staged frame came from cb200_frame_upload
+    size_t hdr_offset = 0, hdr_pristine_offset = 0;
+    cudaEvent_t ev[8];
+    cb200_stats stats;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------- staging ----
+
+// Extended-box blur parameters of one draw, hpp:2402-2405, 2453-2459.
+void blur_params(float blur, int &radius, int &border, float &w1, float &w2)
+{
+    float sigma2 = 0.25f * blur * blur;
+    size_t r = static_cast<size_t>(0.5f * sqrtf(4.0f * sigma2 + 1.0f) - 0.5f);
+    radius = int(r);
+    border = 3 * (radius + 1);
+    float alpha = static_cast<float>(2 * r + 1) * (static_cast<float>(r * (r + 1)) - sigma2) /
+                  (2.0f * sigma2 - static_cast<float>(6 * (r + 1) * (r + 1)));
+    float div = 2.0f * (alpha + static_cast<float>(r)) + 1.0f;
+    w1 = alpha / div;
+    w2 = (1.0f - alpha) / div;
+}
+
+affine to_affine(const float *m) { affine a = { m[0], m[1], m[2], m[3], m[4], m[5] }; return a; }
+
+int stage_frame(cb200_canvas *cv, const cb200_frame *in, staged_frame &sf)
+{
+    sf = staged_frame();
+    if (in->n_draws && !in->draws) return fail(CB200_ERR_BAD_ARG, "frame.draws is null");
+    sf.draws.resize(in->n_draws);
+    sf.subpaths.resize(in->n_subpaths);
+    sf.draw_src.assign(in->n_draws, make_uint2(0, 0));
+    for (uint32_t s = 0; s < in->n_subpaths; ++s) {
+        const cb200_subpath &sp = in->subpaths[s];
+        if (uint64_t(sp.first_point) + 1 + 3ull * sp.n_cubics > in->n_points)
+            return fail(CB200_ERR_BAD_ARG, "subpath points out of range");
+        subpath_rec r = { sp.first_point, sp.n_cubics, sp.closed, 0xffffffffu, 0 };
+        sf.subpaths[s] = r;
+    }
+    int max_pad = 0;
+    for (uint32_t i = 0; i < in->n_draws; ++i) {
+        const cb200_draw &d = in->draws[i];
+        if (uint64_t(d.first_subpath) + d.n_subpaths > in->n_subpaths)
+            return fail(CB200_ERR_BAD_ARG, "draw subpaths out of range");
+        if (d.kind != CB200_CLIP && d.brush >= in->n_brushes) return fail(CB200_ERR_BAD_ARG, "draw brush out of range");
+        if (uint64_t(d.first_dash) + d.n_dash > in->n_dashes) return fail(CB200_ERR_BAD_ARG, "draw dashes out of range");
+        draw_rec r;
+        memset(&r, 0, sizeof r);
+        r.kind = d.kind; r.op = d.op;
+        r.first_subpath = d.first_subpath; r.n_subpaths = d.n_subpaths;
+        r.brush = d.brush; r.mask_src = d.mask_src; r.mask_dst = d.mask_dst;
+        r.cap = d.cap; r.join = d.join;
+        r.first_dash = d.first_dash; r.n_dash = d.kind == CB200_STROKE ? d.n_dash : 0;
+        r.dash_offset = d.dash_offset; r.global_alpha = d.global_alpha;
+        r.line_width = d.line_width; r.miter_limit = d.miter_limit;
+        r.forward = to_affine(d.forward); r.inverse = to_affine(d.inverse);
+        memcpy(r.shadow_color, d.shadow_color, sizeof r.shadow_color);
+        r.shadow_dx = d.shadow_offset_x; r.shadow_dy = d.shadow_offset_y; r.shadow_blur = d.shadow_blur;
+        r.angular = d.kind == CB200_STROKE ? stroke_angular(d.line_width) : -1.0f;
+        r.first_unit = uint32_t(sf.units.size());
+        for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+            subpath_rec &sp = sf.subpaths[d.first_subpath + s];
+            if (sp.draw != 0xffffffffu) return fail(CB200_ERR_BAD_ARG, "subpath shared by two draws");
+            sp.draw = i;
+            sp.first_unit = uint32_t(sf.units.size());
+            for (uint32_t k = 0; k <= sp.n_cubics; ++k) {
+                unit_rec u = { d.first_subpath + s, k };
+                sf.units.push_back(u);
+            }
+        }
+        r.n_units = uint32_t(sf.units.size()) - r.first_unit;
+        // stroke sources: un-dashed strokes list their subpaths now, dashed ones are
+        // appended on the device by K2
+        if (d.kind == CB200_STROKE) {
+            if (r.n_dash) {
+                for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+                    dash_item it = { d.first_subpath + s, (s == 0 ? 1u : 0u) | (s + 1 == d.n_subpaths ? 2u : 0u) };
+                    sf.dash_items.push_back(it);
+                }
+            }
+        }
+        sf.draws[i] = r;
+        // jobs in composite order: shadow (if any) before the draw itself
+        bool shadow = d.kind != CB200_CLIP && d.shadow_color[3] != 0.0f &&
+                      (d.shadow_blur != 0.0f || d.shadow_offset_x != 0.0f || d.shadow_offset_y != 0.0f);
+        if (shadow) {
+            job_rec j;
+            memset(&j, 0, sizeof j);
+            j.draw = i; j.kind = JOB_SHADOW;
+            blur_params(d.shadow_blur, j.radius, j.border, j.w1, j.w2);
+            j.off_x = static_cast<float>(j.border) + d.shadow_offset_x;
+            j.off_y = static_cast<float>(j.border) + d.shadow_offset_y;
+            j.pad = 2 * j.border;
+            max_pad = std::max(max_pad, j.pad);
+            sf.shadow_jobs.push_back(uint32_t(sf.jobs.size()));
+            sf.jobs.push_back(j);
+        }
+        job_rec j;
+        memset(&j, 0, sizeof j);
+        j.draw = i;
+        j.kind = d.kind == CB200_CLIP ? JOB_CLIP : JOB_MAIN;
+        sf.jobs.push_back(j);
+    }
+    // static stroke sources, grouped by draw (keeps every draw's K3 output contiguous)
+    for (uint32_t i = 0; i < in->n_draws; ++i) {
+        const cb200_draw &d = in->draws[i];
+        if (d.kind != CB200_STROKE || sf.draws[i].n_dash) continue;
+        sf.draw_src[i].x = uint32_t(sf.sources.size());
+        for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+            stroke_src src = { d.first_subpath + s, i | (in->subpaths[d.first_subpath + s].closed ? 0x80000000u : 0u) };
+            sf.sources.push_back(src);
+        }
+        sf.draw_src[i].y = uint32_t(sf.sources.size());
+    }
+    sf.points.assign(in->points, in->points + 2 * size_t(in->n_points));
+    sf.colors.assign(in->colors, in->colors + 4 * size_t(in->n_colors));
+    sf.stops.assign(in->stops, in->stops + in->n_colors);
+    sf.dashes.assign(in->dashes, in->dashes + in->n_dashes);
+    // brushes; pattern images are converted to float4 texels on the device
+    std::vector<uint64_t> image_texel_base(in->n_images);
+    for (uint32_t k = 0; k < in->n_images; ++k) {
+        const cb200_image &im = in->images[k];
+        if (im.width <= 0 || im.height <= 0 ||
+            im.texel_offset + 4ull * uint64_t(im.width) * uint64_t(im.height) > in->texel_bytes)
+            return fail(CB200_ERR_BAD_ARG, "image out of range");
+        image_texel_base[k] = sf.n_texels;
+        size_t bytes = 4 * size_t(im.width) * size_t(im.height);
+        sf.texels_u8.insert(sf.texels_u8.end(), in->texels + im.texel_offset, in->texels + im.texel_offset + bytes);
+        sf.n_texels += uint64_t(im.width) * uint64_t(im.height);
+    }
+    sf.brushes.resize(in->n_brushes);
+    for (uint32_t k = 0; k < in->n_brushes; ++k) {
+        const cb200_brush &b = in->brushes[k];
+        brush_rec r;
+        memset(&r, 0, sizeof r);
+        r.type = b.type; r.flags = b.flags; r.first_color = b.first_color; r.n_colors = b.n_colors;
+        r.sx = b.start[0]; r.sy = b.start[1]; r.ex = b.end[0]; r.ey = b.end[1];
+        r.r0 = b.start_radius; r.r1 = b.end_radius; r.repetition = b.repetition;
+        if (b.type == CB200_BRUSH_PATTERN) {
+            if (b.image >= in->n_images) return fail(CB200_ERR_BAD_ARG, "brush image out of range");
+            r.width = in->images[b.image].width;
+            r.height = in->images[b.image].height;
+            r.texel_offset = image_texel_base[b.image];
+            r.n_colors = 1;
+        } else if (uint64_t(b.first_color) + b.n_colors > in->n_colors)
+            return fail(CB200_ERR_BAD_ARG, "brush colours out of range");
+        sf.brushes[k] = r;
+    }
+    // sort key layout: job | y | x
+    sf.bits_x = bits_for(uint32_t(cv->width + max_pad + 1));
+    sf.bits_y = bits_for(uint32_t(cv->height + max_pad + 1));
+    sf.key_bits = sf.bits_x + sf.bits_y + bits_for(uint32_t(sf.jobs.size()));
+    if (sf.key_bits > 64) return fail(CB200_ERR_BAD_ARG, "too many jobs for the sort key");
+    sf.valid = true;
+    return CB200_OK;
+}
+
+// ------------------------------------------------------------ capacities ----
+
+int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header *seen)
+{
+    // first guesses scale with the input; after an overflow the header tells the truth
+    uint32_t n_units = uint32_t(sf.units.size());
+    uint32_t want_pts = std::max<uint32_t>(1u << 18, n_units * 192u);
+    uint32_t want_sources = uint32_t(sf.sources.size()) + std::max<uint32_t>(4096u, uint32_t(sf.dash_items.size()) * 64u);
+    uint32_t want_dash_sub = sf.dash_items.empty() ? 0u : std::max<uint32_t>(4096u, uint32_t(sf.dash_items.size()) * 64u);
+    uint32_t want_items = want_pts * 2, want_rows = 1u << 22, want_runs = 1u << 23, want_tiles = 1u << 17;
+    uint64_t want_planes = sf.shadow_jobs.empty() ? 0 : uint64_t(cv->width + 64) * uint64_t(cv->height + 64) * 2;
+    if (seen) {
+        uint32_t total_pts = seen->n_line_points + seen->n_dash_points + seen->n_stroke_points;
+        want_pts = std::max(want_pts, total_pts + total_pts / 4 + 1024);
+        want_sources = std::max(want_sources, seen->n_sources + seen->n_sources / 4 + 64);
+        want_dash_sub = std::max(want_dash_sub, seen->n_dash_subpaths + seen->n_dash_subpaths / 4 + 64);
+        want_items = std::max(want_items, seen->n_items + seen->n_items / 4 + 1024);
+        want_rows = std::max(want_rows, seen->n_row_items + seen->n_row_items / 4 + 1024);
+        want_runs = std::max(want_runs, seen->n_runs + seen->n_runs / 4 + 1024);
+        want_tiles = std::max(want_tiles, seen->n_tile_entries + seen->n_tile_entries / 4 + 1024);
+        want_planes = std::max<uint64_t>(want_planes, seen->plane_floats + seen->plane_floats / 4 + 1024);
+        if (seen->overflow & (OVF_POINTS | OVF_DASH)) want_pts = std::max(want_pts, cv->cap_pts * 2);
+        if (seen->overflow & OVF_DASH) {
+            want_sources = std::max(want_sources, cv->cap_sources * 2);
+            want_dash_sub = std::max(want_dash_sub, cv->cap_dash_subpaths * 2);
+        }
+    }
+    want_pts = std::max(want_pts, cv->cap_pts);
+    want_sources = std::max(want_sources, cv->cap_sources);
+    want_dash_sub = std::max(want_dash_sub, cv->cap_dash_subpaths);
+    want_items = std::max(want_items, std::max(cv->cap_items, want_pts * 2));
+    want_rows = std::max(want_rows, cv->cap_rows);
+    want_runs = std::max(want_runs, cv->cap_runs);
+    want_tiles = std::max(want_tiles, cv->cap_tiles);
+    want_planes = std::max(want_planes, cv->cap_planes);
+
+    CK(cv->unit_count.reserve(n_units + 1));
+    CK(cv->unit_offset.reserve(n_units + 2));
+    CK(cv->pts.reserve(want_pts));
+    CK(cv->pt_loop.reserve(want_pts));
+    CK(cv->dash_pts_count.reserve(sf.dash_items.size() + 1));
+    CK(cv->dash_sub_count.reserve(sf.dash_items.size() + 1));
+    CK(cv->dash_tail.reserve(sf.dash_items.size() + 1));
+    CK(cv->sources.reserve(want_sources));
+    CK(cv->half_count.reserve(2 * size_t(want_sources) + 2));
+    CK(cv->half_offset.reserve(2 * size_t(want_sources) + 2));
+    CK(cv->loops.reserve(sf.subpaths.size() + want_dash_sub + 2 * size_t(want_sources) + 2));
+    CK(cv->pieces.reserve(3 * size_t(want_items)));
+    CK(cv->piece_job.reserve(3 * size_t(want_items)));
+    CK(cv->piece_rows.reserve(3 * size_t(want_items)));
+    CK(cv->piece_rlo.reserve(3 * size_t(want_items)));
+    CK(cv->piece_row_off.reserve(3 * size_t(want_items)));
+    CK(cv->row_runs.reserve(want_rows));
+    CK(cv->keys0.reserve(want_runs));
+    CK(cv->keys1.reserve(want_runs));
+    CK(cv->vals0.reserve(want_runs));
+    CK(cv->vals1.reserve(want_runs));
+    CK(cv->cumulative.reserve(want_runs));
+    CK(cv->te_flags.reserve(want_tiles));
+    CK(cv->te_backdrop.reserve(size_t(want_tiles) * kTile));
+    CK(cv->te_first.reserve(size_t(want_tiles) * kTile));
+    CK(cv->planes.reserve(want_planes));
+    CK(cv->planes_tmp.reserve(want_planes));
+    CK(cv->partials.reserve(8 * kGrid));
+    CK(cv->sort_hist.reserve(256 * kGrid));
+    CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
+    cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
+    cv->cap_items = want_items; cv->cap_rows = want_rows; cv->cap_runs = want_runs;
+    cv->cap_tiles = want_tiles; cv->cap_planes = want_planes;
+    return CB200_OK;
+}
+
+// Pack the staged frame into the pinned blob, upload it and point device_frame
+// at the pieces.  Layout: [header][pristine header][arrays...], 256 B aligned.
+template <class T>
+size_t place(std::vector<std::pair<size_t, std::pair<const void *, size_t> > > &plan, size_t &at,
+             const std::vector<T> &v)
+{
+    size_t off = at;
+    plan.push_back(std::make_pair(off, std::make_pair(static_cast<const void *>(v.data()), v.size() * sizeof(T))));
+    at = align_up(at + std::max<size_t>(v.size() * sizeof(T), 16), 256);
+    return off;
+}
+
+int upload_frame(cb200_canvas *cv)
+{
+    staged_frame &sf = cv->staged;
+    // clip masks written by this frame need planes before the table is built
+    uint32_t max_slot = 0;
+    for (const draw_rec &d : sf.draws) {
+        max_slot = std::max(max_slot, std::max(d.mask_src, d.mask_dst));
+        if (d.kind == CB200_CLIP && !cv->masks.count(d.mask_dst)) {
+            float *p = nullptr;
+            CK(cudaMalloc(&p, sizeof(float) * size_t(cv->width) * size_t(cv->band_rows)));
+            cv->masks[d.mask_dst] = p;
+        }
+    }
+    sf.mask_table.assign(size_t(max_slot) + 1, nullptr);
+    for (auto &kv : cv->masks)
+        if (kv.first <= max_slot) sf.mask_table[kv.first] = kv.second;
+    for (const draw_rec &d : sf.draws)
+        if (d.mask_src && !sf.mask_table[d.mask_src])
+            return fail(CB200_ERR_BAD_ARG, "draw reads a clip-mask slot that was never written");
+
+    std::vector<std::pair<size_t, std::pair<const void *, size_t> > > plan;
+    size_t at = 0;
+    std::vector<frame_header> hdr(1);
+    memset(&hdr[0], 0, sizeof(frame_header));
+    hdr[0].n_draws = uint32_t(sf.draws.size());
+    hdr[0].n_subpaths = uint32_t(sf.subpaths.size());
+    hdr[0].n_units = uint32_t(sf.units.size());
+    hdr[0].n_jobs = uint32_t(sf.jobs.size());
+    hdr[0].width = cv->width; hdr[0].height = cv->height;
+    hdr[0].band_y0 = cv->band_y0; hdr[0].band_rows = cv->band_rows;
+    hdr[0].n_sources = uint32_t(sf.sources.size());
+    hdr[0].sort_bits_x = uint32_t(sf.bits_x); hdr[0].sort_bits_y = uint32_t(sf.bits_y);
+    hdr[0].sort_bits = uint32_t(sf.key_bits);
+    cv->hdr_offset = place(plan, at, hdr);
+    cv->hdr_pristine_offset = place(plan, at, hdr);
+    size_t o_draws = place(plan, at, sf.draws), o_sub = place(plan, at, sf.subpaths);
+    size_t o_units = place(plan, at, sf.units), o_points = place(plan, at, sf.points);
+    size_t o_brushes = place(plan, at, sf.brushes), o_colors = place(plan, at, sf.colors);
+    size_t o_stops = place(plan, at, sf.stops), o_dashes = place(plan, at, sf.dashes);
+    size_t o_ditems = place(plan, at, sf.dash_items), o_dsrc = place(plan, at, sf.draw_src);
+    size_t o_jobs = place(plan, at, sf.jobs), o_sjobs = place(plan, at, sf.shadow_jobs);
+    size_t o_masks = place(plan, at, sf.mask_table), o_tex = place(plan, at, sf.texels_u8);
+    size_t o_src = place(plan, at, sf.sources);
+
+    if (at > cv->pinned_cap) {
+        if (cv->pinned) cudaFreeHost(cv->pinned);
+        cv->pinned = nullptr;
+        cv->pinned_cap = 0;
+        size_t want = align_up(at + at / 2, 1 << 16);
+        CK(cudaMallocHost(&cv->pinned, want));
+        cv->pinned_cap = want;
+    }
+    CK(cv->blob.reserve(cv->pinned_cap));
+    for (auto &pl : plan)
+        if (pl.second.second) memcpy(cv->pinned + pl.first, pl.second.first, pl.second.second);
+    CK(cudaMemcpyAsync(cv->blob.p, cv->pinned, at, cudaMemcpyHostToDevice, cv->stream));
+    // static stroke sources live in the growable device array K2 appends to
+    if (!sf.sources.empty())
+        CK(cudaMemcpyAsync(cv->sources.p, cv->blob.p + o_src, sf.sources.size() * sizeof(stroke_src),
+                           cudaMemcpyDeviceToDevice, cv->stream));
+
+    device_frame &f = cv->df;
+    memset(&f, 0, sizeof f);
+    uint8_t *b = cv->blob.p;
+    f.hdr = reinterpret_cast<frame_header *>(b + cv->hdr_offset);
+    f.draws = reinterpret_cast<draw_rec *>(b + o_draws);
+    f.subpaths = reinterpret_cast<subpath_rec *>(b + o_sub);
+    f.units = reinterpret_cast<unit_rec *>(b + o_units);
+    f.in_points = reinterpret_cast<float2 *>(b + o_points);
+    f.brushes = reinterpret_cast<brush_rec *>(b + o_brushes);
+    f.colors = reinterpret_cast<float4 *>(b + o_colors);
+    f.stops = reinterpret_cast<float *>(b + o_stops);
+    f.dashes = reinterpret_cast<float *>(b + o_dashes);
+    f.dash_items = reinterpret_cast<dash_item *>(b + o_ditems);
+    f.n_dash_items = uint32_t(sf.dash_items.size());
+    f.draw_src = reinterpret_cast<uint2 *>(b + o_dsrc);
+    f.sources = cv->sources.p;
+    f.n_static_sources = uint32_t(sf.sources.size());
+    f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
+    f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
+    f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
+    f.texels = cv->texels.p;
+    f.unit_count = cv->unit_count.p; f.unit_offset = cv->unit_offset.p;
+    f.pts = cv->pts.p; f.cap_pts = cv->cap_pts; f.pt_loop = cv->pt_loop.p;
+    f.loops = cv->loops.p; f.cap_loops = uint32_t(cv->loops.cap);
+    f.dash_pts_count = cv->dash_pts_count.p; f.dash_sub_count = cv->dash_sub_count.p; f.dash_tail = cv->dash_tail.p;
+    f.half_count = cv->half_count.p; f.half_offset = cv->half_offset.p;
+    f.cap_sources = cv->cap_sources;
+    f.stroke_loop_base = uint32_t(sf.subpaths.size()) + cv->cap_dash_subpaths;
+    f.pieces = cv->pieces.p; f.piece_job = cv->piece_job.p; f.piece_rows = cv->piece_rows.p;
+    f.piece_rlo = cv->piece_rlo.p; f.piece_row_off = cv->piece_row_off.p;
+    f.cap_items = cv->cap_items;
+    f.row_runs = cv->row_runs.p; f.cap_rows = cv->cap_rows;
+    f.keys[0] = cv->keys0.p; f.keys[1] = cv->keys1.p; f.vals[0] = cv->vals0.p; f.vals[1] = cv->vals1.p;
+    f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p;
+    f.te_flags = cv->te_flags.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
+    f.cap_tiles = cv->cap_tiles;
+    f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
+    f.partials = cv->partials.p; f.sort_hist = cv->sort_hist.p;
+
+    canvas_target &t = cv->target;
+    t.fb = cv->fb; t.width = cv->width; t.height = cv->height;
+    t.band_y0 = cv->band_y0; t.band_rows = cv->band_rows;
+    t.mask_planes = reinterpret_cast<float **>(b + o_masks);
+    t.n_masks = uint32_t(sf.mask_table.size());
+
+    if (sf.n_texels) {
+        launch_texel_convert(b + o_tex, cv->texels.p, sf.n_texels, cv->stream);
+        ++cv->launches;
+    }
+    return CB200_OK;
+}
+
+// The fixed launch sequence of one frame.
+int run_frame(cb200_canvas *cv)
+{
+    staged_frame &sf = cv->staged;
+    device_frame &f = cv->df;
+    cudaStream_t s = cv->stream;
+    CK(cudaMemsetAsync(cv->partials.p, 0, sizeof(uint32_t) * 8 * kGrid, s));
+    CK(cudaEventRecord(cv->ev[0], s));
+    launch_flatten(f, uint32_t(sf.units.size()), s);
+    launch_dash(f, s);
+    launch_stroke(f, s);
+    CK(cudaEventRecord(cv->ev[1], s));
+    launch_raster(f, cv->target, s);
+    CK(cudaEventRecord(cv->ev[2], s));
+    int sorted = 0;
+    launch_sort(f, s, sf.key_bits, &sorted);
+    CK(cudaEventRecord(cv->ev[3], s));
+    launch_rows(f, cv->target, sorted, s);
+    launch_shadow(f, cv->target, sorted, s);
+    CK(cudaEventRecord(cv->ev[4], s));
+    launch_composite(f, cv->target, sorted, s);
+    CK(cudaEventRecord(cv->ev[5], s));
+    CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(cv->ev[6], s));
+    cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
+                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 2) + 7 + 2 * ((sf.key_bits + 7) / 8) + 1 +
+                    (sf.shadow_jobs.empty() ? 0 : 7) + 1;
+    cv->pending = true;
+    CK(cudaGetLastError());
+    return CB200_OK;
+}
+
+// Wait for the launched frame, and if a device queue overflowed re-run it with
+// larger buffers (the framebuffer was not touched by the failed attempt).
+int finish_pending(cb200_canvas *cv)
+{
+    if (!cv->pending) return CB200_OK;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        CK(cudaEventSynchronize(cv->ev[6]));
+        CK(cudaGetLastError());
+        frame_header seen = *cv->pinned_hdr;
+        if (!seen.overflow) {
+            float ms = 0.0f;
+            cb200_stats &st = cv->stats;
+            cudaEventElapsedTime(&ms, cv->ev[0], cv->ev[5]); st.last_frame_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[0], cv->ev[1]); st.geometry_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[1], cv->ev[2]); st.raster_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[2], cv->ev[3]); st.sort_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[4], cv->ev[5]); st.composite_ms = ms;
+            st.draws = seen.n_draws;
+            st.cubics = seen.n_units - seen.n_subpaths;
+            st.line_points = seen.n_line_points + seen.n_dash_points + seen.n_stroke_points;
+            st.edges = seen.n_items;
+            st.raw_runs = seen.n_runs;
+            st.tile_entries = seen.n_tile_entries;
+            st.composited_pixels = seen.composited_pixels;
+            st.shadow_pixels = seen.plane_floats;
+            st.kernel_launches = cv->launches;
+            cv->pending = false;
+            return CB200_OK;
+        }
+        int rc = ensure_capacity(cv, cv->staged, &seen);
+        if (rc != CB200_OK) return rc;
+        // pointers/capacities changed: rebuild the device frame from the staged copy
+        rc = upload_frame(cv);
+        if (rc != CB200_OK) return rc;
+        rc = run_frame(cv);
+        if (rc != CB200_OK) return rc;
+    }
+    cv->pending = false;
+    return fail(CB200_ERR_OVERFLOW, "device work queues still overflow after regrowth");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------- C ABI ----
+
+extern "C" {
+
+int cb200_abi_version(void) { return CB200_ABI_VERSION; }
+
+int cb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *cb200_last_error(void) { return g_error.c_str(); }
+
+int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, int device, cb200_canvas **out)
+{
+    if (!out) return fail(CB200_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (width < 1 || height < 1 || width > 32768 || height > 32768)
+        return fail(CB200_ERR_BAD_ARG, "canvas size must be 1..32768");
+    if (band_y0 < 0 || band_rows < 1 || band_y0 + band_rows > height)
+        return fail(CB200_ERR_BAD_ARG, "band outside the canvas");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CB200_ERR_NO_DEVICE, "no CUDA device available (this back end has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(CB200_ERR_BAD_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cb200_canvas *cv = new cb200_canvas;
+    cv->device = device; cv->width = width; cv->height = height;
+    cv->band_y0 = band_y0; cv->band_rows = band_rows;
+    memset(&cv->stats, 0, sizeof cv->stats);
+    cudaError_t err = cudaStreamCreateWithFlags(&cv->stream, cudaStreamNonBlocking);
+    size_t px = size_t(width) * size_t(band_rows);
+    if (err == cudaSuccess) err = cudaMalloc(&cv->fb, px * sizeof(float4));
+    if (err == cudaSuccess) err = cudaMemsetAsync(cv->fb, 0, px * sizeof(float4), cv->stream);
+    if (err == cudaSuccess) err = cudaMallocHost(&cv->pinned_hdr, sizeof(frame_header));
+    for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->ev[i]);
+    if (err != cudaSuccess) {
+        std::string why = cudaGetErrorString(err);
+        cb200_canvas_destroy(cv);
+        return fail(err == cudaErrorMemoryAllocation ? CB200_ERR_OOM : CB200_ERR_CUDA, "canvas create: " + why);
+    }
+    *out = cv;
+    return CB200_OK;
+}
+
+int cb200_canvas_create(int width, int height, int device, cb200_canvas **out)
+{
+    return cb200_canvas_create_band(width, height, 0, height, device, out);
+}
+
+void cb200_canvas_destroy(cb200_canvas *cv)
+{
+    if (!cv) return;
+    cudaSetDevice(cv->device);
+    if (cv->stream) cudaStreamSynchronize(cv->stream);
+    if (cv->fb) cudaFree(cv->fb);
+    for (auto &kv : cv->masks) cudaFree(kv.second);
+    cv->blob.release();
+    if (cv->pinned) cudaFreeHost(cv->pinned);
+    if (cv->pinned_hdr) cudaFreeHost(cv->pinned_hdr);
+    if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
+    cv->unit_count.release(); cv->unit_offset.release(); cv->pt_loop.release();
+    cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
+    cv->half_count.release(); cv->half_offset.release(); cv->piece_job.release();
+    cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
+    cv->row_runs.release(); cv->te_flags.release(); cv->te_first.release(); cv->partials.release();
+    cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
+    cv->pieces.release(); cv->texels.release(); cv->keys0.release(); cv->keys1.release();
+    cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->te_backdrop.release();
+    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
+    for (int i = 0; i < 8; ++i)
+        if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
+    if (cv->stream) cudaStreamDestroy(cv->stream);
+    delete cv;
+}
+
+int cb200_submit(cb200_canvas *cv, const cb200_frame *frame)
+{
+    if (!cv || !frame) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);                 // the previous frame owns the staging until verified
+    if (rc != CB200_OK) return rc;
+    if (frame->n_draws == 0) return CB200_OK;
+    rc = stage_frame(cv, frame, cv->staged);
+    if (rc != CB200_OK) return rc;
+    cv->resident = false;
+    rc = ensure_capacity(cv, cv->staged, nullptr);
+    if (rc != CB200_OK) return rc;
+    rc = upload_frame(cv);
+    if (rc != CB200_OK) return rc;
+    return run_frame(cv);
+}
+
+int cb200_frame_upload(cb200_canvas *cv, const cb200_frame *frame)
+{
+    if (!cv || !frame) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    rc = stage_frame(cv, frame, cv->staged);
+    if (rc != CB200_OK) return rc;
+    rc = ensure_capacity(cv, cv->staged, nullptr);
+    if (rc != CB200_OK) return rc;
+    rc = upload_frame(cv);
+    if (rc != CB200_OK) return rc;
+    cv->resident = true;
+    return CB200_OK;
+}
+
+int cb200_frame_replay(cb200_canvas *cv, int clear)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (!cv->resident || !cv->staged.valid) return fail(CB200_ERR_BAD_ARG, "no frame uploaded");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    if (clear)
+        CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows), cv->stream));
+    // the header is consumed by a run: restore it from its pristine twin (device to device)
+    CK(cudaMemcpyAsync(cv->blob.p + cv->hdr_offset, cv->blob.p + cv->hdr_pristine_offset, sizeof(frame_header),
+                       cudaMemcpyDeviceToDevice, cv->stream));
+    return run_frame(cv);
+}
+
+int cb200_sync(cb200_canvas *cv)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaStreamSynchronize(cv->stream));
+    return CB200_OK;
+}
+
+static int readback_to_device(cb200_canvas *cv, int width, int height, int x, int y)
+{
+    size_t bytes = 4 * size_t(width) * size_t(height);
+    CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
+    CK(cudaEventRecord(cv->ev[7], cv->stream));
+    launch_readback(cv->fb, cv->width, cv->band_y0, cv->band_rows, cv->rgba8.p, width, height, x, y, cv->stream);
+    ++cv->launches;
+    return CB200_OK;
+}
+
+int cb200_read_rgba8(cb200_canvas *cv, uint8_t *dst, int width, int height, int stride, int x, int y)
+{
+    if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (width <= 0 || height <= 0) return CB200_OK;
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    rc = readback_to_device(cv, width, height, x, y);
+    if (rc != CB200_OK) return rc;
+    size_t bytes = 4 * size_t(width) * size_t(height);
+    if (bytes > cv->pinned_rgba8_cap) {
+        if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
+        cv->pinned_rgba8 = nullptr;
+        cv->pinned_rgba8_cap = 0;
+        CK(cudaMallocHost(&cv->pinned_rgba8, bytes));
+        cv->pinned_rgba8_cap = bytes;
+    }
+    CK(cudaMemcpyAsync(cv->pinned_rgba8, cv->rgba8.p, bytes, cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaEventRecord(cv->ev[6], cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, cv->ev[7], cv->ev[6]);
+    cv->stats.readback_ms = ms;
+    if (stride == 4 * width) memcpy(dst, cv->pinned_rgba8, bytes);
+    else
+        for (int row = 0; row < height; ++row)
+            memcpy(dst + ptrdiff_t(row) * stride, cv->pinned_rgba8 + size_t(row) * size_t(width) * 4, size_t(width) * 4);
+    return CB200_OK;
+}
+
+int cb200_read_rgba8_device(cb200_canvas *cv, void **device_ptr)
+{
+    if (!cv || !device_ptr) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    rc = readback_to_device(cv, cv->width, cv->band_rows, 0, cv->band_y0);
+    if (rc != CB200_OK) return rc;
+    *device_ptr = cv->rgba8.p;
+    return CB200_OK;
+}
+
+int cb200_write_rgba8(cb200_canvas *cv, const uint8_t *src, int width, int height, int stride, int x, int y)
+{
+    if (!cv || !src) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (width <= 0 || height <= 0) return CB200_OK;
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    size_t bytes = 4 * size_t(width) * size_t(height);
+    if (bytes > cv->pinned_rgba8_cap) {
+        if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
+        cv->pinned_rgba8 = nullptr;
+        cv->pinned_rgba8_cap = 0;
+        CK(cudaMallocHost(&cv->pinned_rgba8, bytes));
+        cv->pinned_rgba8_cap = bytes;
+    }
+    for (int row = 0; row < height; ++row)
+        memcpy(cv->pinned_rgba8 + size_t(row) * size_t(width) * 4, src + ptrdiff_t(row) * stride, size_t(width) * 4);
+    CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
+    CK(cudaMemcpyAsync(cv->rgba8.p, cv->pinned_rgba8, bytes, cudaMemcpyHostToDevice, cv->stream));
+    launch_upload(cv->fb, cv->width, cv->band_y0, cv->band_rows, cv->rgba8.p, width, height, x, y, cv->stream);
+    ++cv->launches;
+    CK(cudaStreamSynchronize(cv->stream));       // pinned staging is reused by the next call
+    return CB200_OK;
+}
+
+int cb200_read_f32(cb200_canvas *cv, float *dst)
+{
+    if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaMemcpyAsync(dst, cv->fb, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows),
+                       cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
+    return CB200_OK;
+}
+
+int cb200_read_mask(cb200_canvas *cv, uint32_t slot, float *dst)
+{
+    if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    size_t n = size_t(cv->width) * size_t(cv->band_rows);
+    if (slot == 0) { for (size_t i = 0; i < n; ++i) dst[i] = 1.0f; return CB200_OK; }
+    if (!cv->masks.count(slot)) return fail(CB200_ERR_BAD_ARG, "no such mask slot");
+    CK(cudaMemcpyAsync(dst, cv->masks[slot], sizeof(float) * n, cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
+    return CB200_OK;
+}
+
+int cb200_masks_keep(cb200_canvas *cv, const uint32_t *slots, uint32_t n)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaStreamSynchronize(cv->stream));
+    for (auto it = cv->masks.begin(); it != cv->masks.end();) {
+        bool keep = false;
+        for (uint32_t i = 0; i < n; ++i) keep = keep || slots[i] == it->first;
+        if (keep) ++it;
+        else { cudaFree(it->second); it = cv->masks.erase(it); }
+    }
+    return CB200_OK;
+}
+
+int cb200_clear(cb200_canvas *cv)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows), cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
+    for (auto &kv : cv->masks) cudaFree(kv.second);
+    cv->masks.clear();
+    return CB200_OK;
+}
+
+int cb200_get_stats(cb200_canvas *cv, cb200_stats *out)
+{
+    if (!cv || !out) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    cv->stats.kernel_launches = cv->launches;
+    *out = cv->stats;
+    return CB200_OK;
+}
+
+int64_t cb200_debug_lines(cb200_canvas *cv, float *edges, uint32_t *job_of_edge, int64_t capacity)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (cudaSetDevice(cv->device) != cudaSuccess) return CB200_ERR_CUDA;
+    if (finish_pending(cv) != CB200_OK) return CB200_ERR_CUDA;
+    cudaStreamSynchronize(cv->stream);
+    frame_header h = *cv->pinned_hdr;
+    int64_t n = int64_t(h.n_items) * 3, got = 0;
+    std::vector<float4> pieces(static_cast<size_t>(n));
+    std::vector<uint32_t> jobs(static_cast<size_t>(n)), rows(static_cast<size_t>(n));
+    if (n) {
+        cudaMemcpy(pieces.data(), cv->pieces.p, sizeof(float4) * size_t(n), cudaMemcpyDeviceToHost);
+        cudaMemcpy(jobs.data(), cv->piece_job.p, sizeof(uint32_t) * size_t(n), cudaMemcpyDeviceToHost);
+        cudaMemcpy(rows.data(), cv->piece_rows.p, sizeof(uint32_t) * size_t(n), cudaMemcpyDeviceToHost);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        if (!rows[size_t(i)]) continue;
+        if (got < capacity && edges) {
+            memcpy(edges + got * 4, &pieces[size_t(i)], sizeof(float4));
+            if (job_of_edge) job_of_edge[got] = jobs[size_t(i)];
+        }
+        ++got;
+    }
+    return got;
+}
+
+int64_t cb200_debug_runs(cb200_canvas *cv, uint64_t *keys, float *cumulative, int64_t capacity)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (cudaSetDevice(cv->device) != cudaSuccess) return CB200_ERR_CUDA;
+    if (finish_pending(cv) != CB200_OK) return CB200_ERR_CUDA;
+    cudaStreamSynchronize(cv->stream);
+    frame_header h = *cv->pinned_hdr;
+    int64_t n = std::min<int64_t>(h.n_runs, capacity);
+    int sorted = ((cv->staged.key_bits + 7) / 8) & 1;
+    if (n && keys) cudaMemcpy(keys, sorted ? cv->keys1.p : cv->keys0.p, sizeof(uint64_t) * size_t(n), cudaMemcpyDeviceToHost);
+    if (n && cumulative) cudaMemcpy(cumulative, cv->cumulative.p, sizeof(float) * size_t(n), cudaMemcpyDeviceToHost);
+    return h.n_runs;
+}
+
+}  // extern "C"

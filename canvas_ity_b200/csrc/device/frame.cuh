@@ -1,0 +1,90 @@
+// frame.cuh -- device buffers of one frame in flight and the launcher
+// prototypes of every pipeline stage (definitions in the .cu files next to it).
+#pragma once
+
+#include "common.cuh"
+
+namespace cb200 {
+
+// A polyline/polygon in the shared point pool.  Loop ids are global:
+//   [0, n_subpaths)                        K1 output, one per input subpath
+//   [n_subpaths, +n_dash_subpaths)         K2 output (dashed strokes only)
+//   [stroke_loop_base, +2 * n_sources)     K3 output (two per stroke source)
+struct loop_span { uint32_t first, count; };
+
+// A polyline that K3 expands: static ones (un-dashed strokes, loop = subpath id)
+// are listed by the host, dashed ones are appended by K2.
+struct stroke_src { uint32_t loop, draw_closed; };   // draw | closed << 31
+struct dash_item { uint32_t subpath, flags; };       // flags: 1 first of its draw, 2 last of its draw
+
+struct device_frame {
+    frame_header *hdr;            // device
+    // inputs (uploaded once per frame)
+    draw_rec *draws;
+    subpath_rec *subpaths;
+    unit_rec *units;
+    float2 *in_points;
+    brush_rec *brushes;
+    float4 *colors;  float *stops;
+    float *dashes;
+    dash_item *dash_items; uint32_t n_dash_items;      // subpaths of dashed strokes, draw order
+    uint2 *draw_src;                                   // per draw: first stroke source, count
+    stroke_src *sources;   uint32_t n_static_sources;
+    job_rec *jobs;
+    float4 *texels;
+    // geometry
+    uint32_t *unit_count, *unit_offset;               // n_units + 1
+    float2 *pts;           uint32_t cap_pts;
+    uint32_t *pt_loop;
+    loop_span *loops;      uint32_t cap_loops;
+    uint32_t *dash_pts_count, *dash_sub_count, *dash_tail, *dash_pts_off, *dash_sub_off;
+    uint32_t *half_count, *half_offset;               // 2 per stroke source (+1)
+    uint32_t cap_sources;
+    uint32_t stroke_loop_base;
+    // raster
+    float4 *pieces;        uint32_t *piece_job;  uint32_t *piece_rows;   // 3 per item
+    uint32_t *piece_rlo, *piece_row_off;
+    uint32_t cap_items;
+    uint32_t *row_runs;    uint32_t cap_rows;          // per (piece,row)
+    uint64_t *keys[2];     float *vals[2];            uint32_t cap_runs;
+    float *cumulative;
+    // tiles
+    uint32_t *te_flags;    float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
+    float *planes, *planes_tmp;  uint64_t cap_planes;
+    uint32_t *shadow_jobs; uint32_t n_shadow_jobs;     // job indices with kind JOB_SHADOW
+    // scratch
+    uint32_t *partials;                                // several kGrid-sized slices
+    uint32_t *sort_hist;
+};
+
+struct canvas_target {
+    float4 *fb;            // band_rows x width, linear premultiplied
+    int width, height, band_y0, band_rows;
+    float **mask_planes;   // device array of plane pointers indexed by slot (slot 0 unused)
+    uint32_t n_masks;
+};
+
+// geometry.cu
+void launch_flatten(const device_frame &f, uint32_t n_units, cudaStream_t s);
+void launch_dash(const device_frame &f, cudaStream_t s);
+void launch_stroke(const device_frame &f, cudaStream_t s);
+// raster.cu
+void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s);
+// sort.cu
+void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer);
+// coverage.cu
+void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
+// composite.cu
+void launch_composite(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
+// shadow.cu
+void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
+// pixels.cu
+// dst / src are tightly packed RGBA8 device buffers of dst_w x dst_h pixels
+void launch_readback(const float4 *fb, int width, int band_y0, int band_rows, uint8_t *dst, int dst_w,
+                     int dst_h, int x, int y, cudaStream_t s);
+void launch_upload(float4 *fb, int width, int band_y0, int band_rows, const uint8_t *src, int src_w,
+                   int src_h, int x, int y, cudaStream_t s);
+void launch_texel_convert(const uint8_t *src, float4 *dst, uint64_t n_texels, cudaStream_t s);
+void launch_fill_f32(float *dst, float value, uint64_t n, cudaStream_t s);
+
+}  // namespace cb200

@@ -1,0 +1,119 @@
+// pixels.cu -- K10 readback (get_image_data, hpp:3348-3381), K11 upload
+// (put_image_data hpp:3383-3408 and the texel conversion of set_pattern
+// hpp:2852-2860).  Pure streaming kernels: 16 B in / 4 B out per pixel (or the
+// reverse), one thread per pixel, consecutive threads on consecutive pixels.
+#include "frame.cuh"
+
+namespace cb200 {
+
+namespace {
+
+__device__ __forceinline__ float to_srgb(float v)     // delinearized, hpp:1282-1284
+{
+    return v < 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+
+__device__ __forceinline__ float to_linear(float v)   // linearized, hpp:1273-1275
+{
+    return v < 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+}
+
+// 4x4 ordered-dither thresholds (k + 0.5) / 16 of the classic Bayer matrix, hpp:3358-3362
+__constant__ float c_bayer[16] = {
+    0.5f / 16, 8.5f / 16, 2.5f / 16, 10.5f / 16, 12.5f / 16, 4.5f / 16, 14.5f / 16, 6.5f / 16,
+    3.5f / 16, 11.5f / 16, 1.5f / 16, 9.5f / 16, 15.5f / 16, 7.5f / 16, 13.5f / 16, 5.5f / 16 };
+
+__global__ void __launch_bounds__(kBlock) k_readback(const float4 *fb, int width, int band_y0, int band_rows,
+                                                      uchar4 *dst, int dst_w, int dst_h, int ox, int oy)
+{
+    size_t n = size_t(dst_w) * size_t(dst_h);
+    size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int ix = int(i % size_t(dst_w)), iy = int(i / size_t(dst_w));
+        int cx = ox + ix, cy = oy + iy;
+        float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (cx >= 0 && cx < width && cy >= band_y0 && cy < band_y0 + band_rows)
+            c = fb[size_t(cy - band_y0) * size_t(width) + size_t(cx)];
+        if (c.w < kThreshold) c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // unpremultiplied()
+        else { float k = 1.0f / c.w; c.x = k * c.x; c.y = k * c.y; c.z = k * c.z; }
+        float th = c_bayer[(cy & 3) * 4 + (cx & 3)];
+        uchar4 o;
+        o.x = static_cast<unsigned char>(th + 255.0f * to_srgb(clamp01(c.x)));
+        o.y = static_cast<unsigned char>(th + 255.0f * to_srgb(clamp01(c.y)));
+        o.z = static_cast<unsigned char>(th + 255.0f * to_srgb(clamp01(c.z)));
+        o.w = static_cast<unsigned char>(th + 255.0f * clamp01(c.w));
+        dst[i] = o;
+    }
+}
+
+__device__ __forceinline__ float4 decode(uchar4 t)
+{
+    float a = t.w / 255.0f;
+    return make_float4(to_linear(t.x / 255.0f) * a, to_linear(t.y / 255.0f) * a,
+                       to_linear(t.z / 255.0f) * a, a);
+}
+
+__global__ void __launch_bounds__(kBlock) k_upload(float4 *fb, int width, int band_y0, int band_rows,
+                                                    const uchar4 *src, int src_w, int src_h, int ox, int oy)
+{
+    size_t n = size_t(src_w) * size_t(src_h);
+    size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int cx = ox + int(i % size_t(src_w)), cy = oy + int(i / size_t(src_w));
+        if (cx < 0 || cx >= width || cy < band_y0 || cy >= band_y0 + band_rows) continue;
+        fb[size_t(cy - band_y0) * size_t(width) + size_t(cx)] = decode(src[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_texels(const uchar4 *src, float4 *dst, uint64_t n)
+{
+    uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = decode(src[i]);
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill(float *dst, float value, uint64_t n)
+{
+    uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
+}
+
+inline int grid_for(uint64_t n)
+{
+    uint64_t blocks = (n + kBlock - 1) / kBlock;
+    uint64_t cap = uint64_t(148) * 16;
+    return int(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+void launch_readback(const float4 *fb, int width, int band_y0, int band_rows, uint8_t *dst, int dst_w,
+                     int dst_h, int x, int y, cudaStream_t s)
+{
+    uint64_t n = uint64_t(dst_w) * uint64_t(dst_h);
+    if (!n) return;
+    k_readback<<<grid_for(n), kBlock, 0, s>>>(fb, width, band_y0, band_rows, reinterpret_cast<uchar4 *>(dst),
+                                              dst_w, dst_h, x, y);
+}
+
+void launch_upload(float4 *fb, int width, int band_y0, int band_rows, const uint8_t *src, int src_w,
+                   int src_h, int x, int y, cudaStream_t s)
+{
+    uint64_t n = uint64_t(src_w) * uint64_t(src_h);
+    if (!n) return;
+    k_upload<<<grid_for(n), kBlock, 0, s>>>(fb, width, band_y0, band_rows, reinterpret_cast<const uchar4 *>(src),
+                                            src_w, src_h, x, y);
+}
+
+void launch_texel_convert(const uint8_t *src, float4 *dst, uint64_t n_texels, cudaStream_t s)
+{
+    if (!n_texels) return;
+    k_texels<<<grid_for(n_texels), kBlock, 0, s>>>(reinterpret_cast<const uchar4 *>(src), dst, n_texels);
+}
+
+void launch_fill_f32(float *dst, float value, uint64_t n, cudaStream_t s)
+{
+    if (!n) return;
+    k_fill<<<grid_for(n), kBlock, 0, s>>>(dst, value, n);
+}
+
+}  // namespace cb200

@@ -1,0 +1,442 @@
+// raster.cu -- K4: scan conversion of every loop edge of every job into
+// signed-area pixel runs (reference add_runs hpp:2109-2170 and the clip/clamp
+// part of lines_to_runs hpp:2193-2240).  sm_100a, compiled with -fmad=false.
+//
+// Decomposition (all counts stay on the device):
+//   k_job_items   one CTA: K4 work items per job = loop points of its draw
+//   k_edges       one thread per (job, loop point): edge prev->point, offset,
+//                 clipped per edge against the padded canvas (per-edge
+//                 clipping == Sutherland-Hodgman for area accumulation) into <= 3
+//                 pieces; counts the scanlines each piece touches inside the band
+//   k_scan_rows   piece scanline counts -> exclusive offsets
+//   k_row_count   one thread per (piece, scanline): closed-form run count
+//   k_row_emit    same items: walks the pixels of one scanline exactly like the
+//                 reference DDA (its per-row / per-column positions are evaluated
+//                 directly from the edge's `from`, so any row can start cold) and
+//                 writes (key = job|y|x, delta) pairs
+//   k_job_tiles   one CTA: bounding boxes -> tile rectangles, tile-entry bases,
+//                 shadow working rectangles and plane storage (hpp:2409-2428)
+#include "frame.cuh"
+
+namespace cb200 {
+
+namespace {
+
+struct edge_walk {
+    vec2 from, to;
+    float sign, ystep, dxdy, dydx, fx0, fy0;
+    bool vertical, down;
+    int rows;                  // scanlines the reference loop would visit
+};
+
+__device__ __forceinline__ edge_walk edge_setup(float4 pc)
+{
+    edge_walk e;
+    vec2 a = v2(pc.x, pc.y), b = v2(pc.z, pc.w);
+    e.sign = b.y > a.y ? 1.0f : -1.0f;
+    if (a.x > b.x) { vec2 t = a; a = b; b = t; }          // always walk left to right
+    e.from = a; e.to = b;
+    e.down = b.y > a.y;
+    e.ystep = e.down ? 1.0f : -1.0f;
+    e.dxdy = (b.x - a.x) / (b.y - a.y);
+    e.dydx = (b.y - a.y) / (b.x - a.x);
+    e.vertical = b.x - a.x < 2.0e-5f;
+    e.fx0 = floorf(a.x);
+    e.fy0 = floorf(a.y);
+    e.rows = e.down ? int(ceilf(b.y) - e.fy0) : int(e.fy0 - floorf(b.y)) + 1;
+    return e;
+}
+
+struct row_walk {
+    vec2 now, stop;            // entry / exit of the edge in this scanline
+    float px, py;              // first pixel touched
+    int inner;                 // pixels crossed before the last one
+};
+
+__device__ __forceinline__ float edge_x_at(const edge_walk &e, float y) { return (y - e.from.y) * e.dxdy + e.from.x; }
+__device__ __forceinline__ float edge_y_at(const edge_walk &e, float x) { return (x - e.from.x) * e.dydx + e.from.y; }
+
+__device__ __forceinline__ row_walk row_setup(const edge_walk &e, int r)
+{
+    row_walk w;
+    float fr = float(r);
+    if (e.down) {
+        w.py = e.fy0 + fr;
+        float y_in = e.fy0 + fr, y_out = e.fy0 + fr + 1.0f;
+        w.now = r == 0 ? e.from : v2(edge_x_at(e, y_in), y_in);
+        w.stop = e.to.y < y_out ? e.to : v2(edge_x_at(e, y_out), y_out);
+    } else {
+        w.py = e.fy0 - fr;
+        float y_in = e.fy0 - fr + 1.0f, y_out = e.fy0 - fr;
+        w.now = r == 0 ? e.from : v2(edge_x_at(e, y_in), y_in);
+        w.stop = e.to.y > y_out ? e.to : v2(edge_x_at(e, y_out), y_out);
+    }
+    w.px = (r == 0 || e.vertical) ? e.fx0 : fmaxf(e.fx0, ceilf(w.now.x) - 1.0f);
+    float crossed = e.vertical ? 0.0f : ceilf(w.stop.x) - 1.0f - w.px;
+    w.inner = crossed > 0.0f ? int(crossed) : 0;
+    return w;
+}
+
+// ------------------------------------------------------------- job items ----
+
+__global__ void __launch_bounds__(kBlock) k_job_items(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *h = f.hdr;
+    uint32_t n = h->n_jobs, carry = 0;
+    uint32_t stroke_base = h->n_line_points + h->n_dash_points;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t j = base + threadIdx.x, count = 0, first_point = 0;
+        if (j < n && !h->overflow) {
+            const draw_rec &d = f.draws[f.jobs[j].draw];
+            if (d.kind == CB200_STROKE) {
+                uint2 src = f.draw_src[f.jobs[j].draw];
+                if (src.y > src.x) {
+                    uint32_t a = f.half_offset[2 * src.x], b = f.half_offset[2 * src.y];
+                    first_point = stroke_base + a;
+                    count = b - a;
+                }
+            } else if (d.n_units) {
+                uint32_t a = f.unit_offset[d.first_unit], b = f.unit_offset[d.first_unit + d.n_units];
+                first_point = a;
+                count = b - a;
+            }
+        }
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(count, sm, total);
+        if (j < n) {
+            job_rec &jr = f.jobs[j];
+            jr.first_point = first_point;
+            jr.first_item = carry + ex;
+            jr.n_items = count;
+            jr.min_x = jr.min_y = 0x7fffffff;
+            jr.max_x = jr.max_y = -1;
+            jr.run_min_x = jr.run_min_y = 0x7fffffff;
+            jr.run_max_x = jr.run_max_y = -1;
+            jr.first_key = 0xffffffffu;
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        h->n_items = carry;
+        if (carry > f.cap_items) atomicOr(&h->overflow, OVF_ITEMS);
+    }
+}
+
+// ------------------------------------------------------------------ edges ----
+
+// Parameter at which a->b crosses the line `side == 0`, the same ratio
+// Sutherland-Hodgman uses (hpp:2220-2222); only meaningful when sa * sb < 0.
+__device__ __forceinline__ float cross_at(float sa, float sb) { return sa / (sa - sb); }
+
+__global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target t)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *h = f.hdr;
+    uint32_t n = h->overflow ? 0 : h->n_items, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    uint32_t j = 0;
+    if (first < end) {                                   // job of my first item
+        uint32_t lo = 0, hi = h->n_jobs;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (f.jobs[mid].first_item <= first) lo = mid; else hi = mid;
+        }
+        j = lo;
+    }
+    for (uint32_t k = 0; k < ipt; ++k) {
+        uint32_t it = first + k;
+        if (it >= end) break;
+        while (it >= f.jobs[j].first_item + f.jobs[j].n_items) ++j;
+        const job_rec &job = f.jobs[j];
+        uint32_t p = job.first_point + (it - job.first_item);
+        loop_span loop = f.loops[f.pt_loop[p]];
+        uint32_t q = p == loop.first ? loop.first + loop.count - 1 : p - 1;
+        float2 pa = f.pts[q], pb = f.pts[p];
+        vec2 a = v2(job.off_x + pa.x, job.off_y + pa.y), b = v2(job.off_x + pb.x, job.off_y + pb.y);
+        float w = float(t.width + job.pad), hgt = float(t.height + job.pad);
+        // crossing parameters with the four clip lines, in increasing order
+        float cut[6];
+        int nc = 0;
+        cut[nc++] = 0.0f;
+        if (a.x * b.x < 0.0f) cut[nc++] = cross_at(a.x, b.x);
+        if (a.y * b.y < 0.0f) cut[nc++] = cross_at(a.y, b.y);
+        if ((w - a.x) * (w - b.x) < 0.0f) cut[nc++] = cross_at(w - a.x, w - b.x);
+        if ((hgt - a.y) * (hgt - b.y) < 0.0f) cut[nc++] = cross_at(hgt - a.y, hgt - b.y);
+        for (int i = 2; i < nc; ++i) {
+            float v = cut[i];
+            int m = i - 1;
+            for (; m >= 1 && v < cut[m]; --m) cut[m + 1] = cut[m];
+            cut[m + 1] = v;
+        }
+        cut[nc++] = 1.0f;
+        int row0 = job.kind == JOB_SHADOW ? 0 : t.band_y0;
+        int row1 = job.kind == JOB_SHADOW ? t.height + job.pad : t.band_y0 + t.band_rows;
+        int made = 0;
+        for (int i = 0; i + 1 < nc; ++i) {
+            float t0 = cut[i], t1 = cut[i + 1];
+            if (!(t0 < t1)) continue;
+            vec2 p0 = t0 == 0.0f ? a : mix(a, b, t0), p1 = t1 == 1.0f ? b : mix(a, b, t1);
+            vec2 mid = 0.5f * (p0 + p1);
+            if (!(mid.y >= 0.0f && mid.y <= hgt)) continue;          // above / below: no area
+            // left / right of the canvas: project onto the boundary (clamp); inside: keep
+            float4 pc = make_float4(fminf(fmaxf(p0.x, 0.0f), w), fminf(fmaxf(p0.y, 0.0f), hgt),
+                                    fminf(fmaxf(p1.x, 0.0f), w), fminf(fmaxf(p1.y, 0.0f), hgt));
+            uint32_t rows = 0, rlo = 0;
+            if (!(fabsf(pc.w - pc.y) < 2.0e-5f) && made < 3) {
+                edge_walk e = edge_setup(pc);
+                // scanlines inside [row0, row1)
+                int r_first, r_last;                       // inclusive range of r
+                if (e.down) { r_first = row0 - int(e.fy0); r_last = row1 - 1 - int(e.fy0); }
+                else { r_first = int(e.fy0) - (row1 - 1); r_last = int(e.fy0) - row0; }
+                if (r_first < 0) r_first = 0;
+                if (r_last > e.rows - 1) r_last = e.rows - 1;
+                if (r_last >= r_first) {
+                    rows = uint32_t(r_last - r_first + 1);
+                    rlo = uint32_t(r_first);
+                    int y_lo = e.down ? int(e.fy0) + r_first : int(e.fy0) - r_last;
+                    int y_hi = e.down ? int(e.fy0) + r_last : int(e.fy0) - r_first;
+                    int x_lo = int(e.fx0), x_hi = int(floorf(e.to.x)) + 1;
+                    atomicMin(&f.jobs[j].min_x, x_lo); atomicMax(&f.jobs[j].max_x, x_hi);
+                    atomicMin(&f.jobs[j].min_y, y_lo); atomicMax(&f.jobs[j].max_y, y_hi);
+                }
+            }
+            if (made < 3) {
+                uint32_t slot = it * 3 + made;
+                f.pieces[slot] = pc;
+                f.piece_job[slot] = j;
+                f.piece_rows[slot] = rows;
+                f.piece_rlo[slot] = rlo;
+                sum += rows;
+                ++made;
+            }
+        }
+        for (; made < 3; ++made) f.piece_rows[it * 3 + made] = 0;
+    }
+    uint32_t total;
+    block_exclusive_scan(sum, sm, total);
+    if (threadIdx.x == 0) f.partials[4 * kGrid + blockIdx.x] = total;
+    finish_partials(f.partials + 4 * kGrid, &h->tickets[4], &h->n_row_items, sm);
+}
+
+// piece_rows (counts) -> piece_row_off (exclusive offsets), same slice mapping
+__global__ void __launch_bounds__(kBlock) k_scan_rows(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *h = f.hdr;
+    uint32_t n = h->overflow ? 0 : h->n_items, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
+        uint32_t s = (first + k) * 3;
+        sum += f.piece_rows[s] + f.piece_rows[s + 1] + f.piece_rows[s + 2];
+    }
+    uint32_t total;
+    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[4 * kGrid + blockIdx.x];
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
+        uint32_t s = (first + k) * 3;
+        for (int m = 0; m < 3; ++m) { f.piece_row_off[s + m] = at; at += f.piece_rows[s + m]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && h->n_row_items > f.cap_rows) atomicOr(&h->overflow, OVF_ROWS);
+}
+
+// Largest piece slot whose offset is <= item (slots with zero rows share offsets;
+// the walk below skips them).
+__device__ __forceinline__ uint32_t find_piece(const uint32_t *off, uint32_t n_slots, uint32_t item)
+{
+    uint32_t lo = 0, hi = n_slots;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *h = f.hdr;
+    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    uint32_t n_slots = h->n_items * 3;
+    uint32_t slot = first < end ? find_piece(f.piece_row_off, n_slots, first) : 0;
+    for (uint32_t k = 0; k < ipt; ++k) {
+        uint32_t it = first + k;
+        if (it >= end) break;
+        while (it >= f.piece_row_off[slot] + f.piece_rows[slot]) ++slot;
+        edge_walk e = edge_setup(f.pieces[slot]);
+        row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
+        uint32_t runs = uint32_t(w.inner) + 2;
+        f.row_runs[it] = runs;
+        sum += runs;
+    }
+    uint32_t total;
+    block_exclusive_scan(sum, sm, total);
+    if (threadIdx.x == 0) f.partials[5 * kGrid + blockIdx.x] = total;
+    finish_partials(f.partials + 5 * kGrid, &h->tickets[5], &h->n_runs, sm);
+}
+
+__global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *h = f.hdr;
+    if (h->n_runs > f.cap_runs) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&h->overflow, OVF_RUNS);
+        return;
+    }
+    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.row_runs[first + k];
+    uint32_t total;
+    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[5 * kGrid + blockIdx.x];
+    uint32_t n_slots = h->n_items * 3;
+    uint32_t slot = first < end ? find_piece(f.piece_row_off, n_slots, first) : 0;
+    const uint32_t bx = h->sort_bits_x, by = h->sort_bits_y;
+    uint64_t *keys = f.keys[0];
+    float *vals = f.vals[0];
+    for (uint32_t k = 0; k < ipt; ++k) {
+        uint32_t it = first + k;
+        if (it >= end) break;
+        while (it >= f.piece_row_off[slot] + f.piece_rows[slot]) ++slot;
+        uint32_t j = f.piece_job[slot];
+        edge_walk e = edge_setup(f.pieces[slot]);
+        row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
+        uint64_t row_key = ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx;
+        bool shadow = f.jobs[j].kind == JOB_SHADOW;
+        int lo_x = 0x7fffffff, hi_x = -1;
+        vec2 cur = w.now;
+        float px = w.px, carry = 0.0f;
+        for (int c = 0; c < w.inner; ++c) {
+            float gx = px + 1.0f;
+            vec2 nx = v2(gx, edge_y_at(e, gx));
+            float strip = clamp01((nx.y - cur.y) * e.ystep);
+            float mid = (nx.x + cur.x) * 0.5f;
+            float area = (mid - px) * strip;
+            float delta = (carry + strip - area) * e.sign;
+            keys[at] = row_key | uint64_t(uint32_t(px));
+            vals[at] = delta;
+            ++at;
+            if (delta != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
+            carry = area;
+            cur = nx;
+            px = gx;
+        }
+        float strip = clamp01((w.stop.y - cur.y) * e.ystep);
+        float mid = (w.stop.x + cur.x) * 0.5f;
+        float area = (mid - px) * strip;
+        float d0 = (carry + strip - area) * e.sign, d1 = area * e.sign;
+        keys[at] = row_key | uint64_t(uint32_t(px));         vals[at] = d0; ++at;
+        keys[at] = row_key | uint64_t(uint32_t(px + 1.0f));  vals[at] = d1; ++at;
+        if (shadow) {
+            // exact bounds of the runs the reference keeps (non-zero deltas) plus the
+            // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252)
+            if (d0 != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
+            if (d1 != 0.0f) { lo_x = min(lo_x, int(px) + 1); hi_x = max(hi_x, int(px) + 1); }
+            job_rec &jr = f.jobs[j];
+            if (hi_x >= 0) {
+                atomicMin(&jr.run_min_x, lo_x); atomicMax(&jr.run_max_x, hi_x);
+                atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py));
+            }
+            atomicMin(&jr.first_key, (uint32_t(w.py) << 16) | uint32_t(w.px));
+        }
+    }
+}
+
+// ------------------------------------------------------------- job tiles ----
+
+__global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_target t)
+{
+    __shared__ uint32_t sm[33];
+    __shared__ unsigned long long plane_carry;
+    frame_header *h = f.hdr;
+    if (threadIdx.x == 0) plane_carry = 0;
+    __syncthreads();
+    uint32_t n = h->n_jobs, carry = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t j = base + threadIdx.x, tiles = 0;
+        unsigned long long plane = 0;
+        if (j < n && !h->overflow) {
+            job_rec &jr = f.jobs[j];
+            const draw_rec &d = f.draws[jr.draw];
+            int x0, y0, x1, y1;                                  // raster-space pixel rectangle
+            bool everywhere = jr.kind == JOB_CLIP || (jr.kind == JOB_MAIN && (~d.op & 8u));
+            if (jr.kind == JOB_SHADOW) {
+                // working rectangle of render_shadow, hpp:2409-2425
+                int b = jr.border, full_w = t.width + 2 * b, full_h = t.height + 2 * b;
+                int lx = jr.run_min_x, hx = jr.run_max_x, ly = jr.run_min_y, hy = jr.run_max_y;
+                if (jr.first_key != 0xffffffffu) {
+                    int fy = int(jr.first_key >> 16), fx = int(jr.first_key & 0xffffu);
+                    lx = min(lx, fx); hx = max(hx, fx); ly = min(ly, fy); hy = max(hy, fy);
+                } else { lx = full_w; hx = 0; ly = full_h; hy = 0; }
+                int left = max(lx - b, 0), right = min(hx + b, full_w) + 1;
+                int top = max(ly - b, 0), bottom = min(hy + b, full_h);
+                jr.left = left; jr.top = top;
+                jr.bw = max(right - left, 0); jr.bh = max(bottom - top, 0);
+                plane = (unsigned long long)jr.bw * (unsigned long long)jr.bh;
+                x0 = left; y0 = top; x1 = left + jr.bw; y1 = top + jr.bh;
+                // where the blurred plane lands on the canvas, hpp:2512-2514, 2535
+                jr.cx0 = max(left - b, 0); jr.cx1 = min(right - b, t.width);
+                jr.cy0 = max(top - b, t.band_y0); jr.cy1 = min(bottom - b, t.band_y0 + t.band_rows);
+                if (plane == 0) { jr.cx1 = jr.cx0; jr.cy1 = jr.cy0; }
+            } else {
+                if (everywhere) { x0 = 0; y0 = t.band_y0; x1 = t.width; y1 = t.band_y0 + t.band_rows; }
+                else {
+                    x0 = max(jr.min_x, 0); x1 = min(jr.max_x + 1, t.width);
+                    y0 = max(jr.min_y, t.band_y0); y1 = min(jr.max_y + 1, t.band_y0 + t.band_rows);
+                }
+                jr.cx0 = x0; jr.cy0 = y0; jr.cx1 = x1; jr.cy1 = y1;
+            }
+            if (x1 > x0 && y1 > y0) {
+                jr.tx0 = x0 / kTile; jr.ty0 = y0 / kTile;
+                jr.tw = (x1 - 1) / kTile - jr.tx0 + 1;
+                jr.th = (y1 - 1) / kTile - jr.ty0 + 1;
+                tiles = uint32_t(jr.tw) * uint32_t(jr.th);
+            } else { jr.tx0 = jr.ty0 = 0; jr.tw = jr.th = 0; }
+        }
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(tiles, sm, total);
+        if (j < n) f.jobs[j].te_base = carry + ex;
+        carry += total;
+        // plane storage: order of allocation does not matter, only disjointness
+        if (plane) f.jobs[j].plane_offset = atomicAdd(&plane_carry, plane);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        h->n_tile_entries = carry;
+        h->plane_floats = plane_carry;
+        if (carry > f.cap_tiles) atomicOr(&h->overflow, OVF_TILES);
+        if (plane_carry > f.cap_planes) atomicOr(&h->overflow, OVF_PLANES);
+    }
+}
+
+// zero the per-(tile entry, row) coverage bookkeeping
+__global__ void k_clear_tiles(device_frame f)
+{
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    uint64_t n = uint64_t(h->n_tile_entries) * kTile;
+    uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        f.te_backdrop[i] = 0.0f;
+        f.te_first[i] = kNoRun;
+        if (i < h->n_tile_entries) f.te_flags[i] = 0;
+    }
+}
+
+}  // namespace
+
+void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s)
+{
+    k_job_items<<<1, kBlock, 0, s>>>(f);
+    k_edges<<<kGrid, kBlock, 0, s>>>(f, t);
+    k_scan_rows<<<kGrid, kBlock, 0, s>>>(f);
+    k_row_count<<<kGrid, kBlock, 0, s>>>(f);
+    k_row_emit<<<kGrid, kBlock, 0, s>>>(f);
+    k_job_tiles<<<1, kBlock, 0, s>>>(f, t);
+    k_clear_tiles<<<kGrid, kBlock, 0, s>>>(f);
+}
+
+}  // namespace cb200

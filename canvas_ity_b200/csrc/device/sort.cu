@@ -1,0 +1,130 @@
+// sort.cu -- K5: stable LSD radix sort of the pixel runs by key = job|y|x
+// (replaces the std::sort of reference lines_to_runs, hpp:2243; the tie order
+// among runs on the same pixel is irrelevant to the summed coverage).
+//
+// 8-bit digits; only ceil(key_bits / 8) passes run, the host knows key_bits from
+// the canvas size and the job count.  Per pass, two launches with fixed grids
+// (the run count lives on the device):
+//   k_sort_hist     per-CTA digit histogram of its slice; the last CTA to finish
+//                   turns the kGrid x 256 table into global bases (digit-major)
+//   k_sort_scatter  each CTA re-reads its slice in order, 256 keys per step;
+//                   ranks are made stable with warp match + per-warp digit counts
+#include "frame.cuh"
+
+namespace cb200 {
+
+namespace {
+
+constexpr int kRadix = 256;
+
+__device__ __forceinline__ void sort_slice(uint32_t n, uint32_t &begin, uint32_t &end)
+{
+    uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + kBlock - 1) / kBlock * kBlock;
+    uint64_t b = uint64_t(per) * blockIdx.x;
+    begin = b < n ? uint32_t(b) : n;
+    end = b + per < n ? uint32_t(b + per) : n;
+}
+
+__global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, int shift)
+{
+    __shared__ uint32_t bins[kRadix];
+    __shared__ uint32_t sm[33];
+    __shared__ bool last;
+    frame_header *h = f.hdr;
+    uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
+    sort_slice(n, begin, end);
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t *keys = f.keys[src];
+    for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock)
+        atomicAdd(&bins[uint32_t(keys[i] >> shift) & 0xffu], 1u);
+    __syncthreads();
+    f.sort_hist[threadIdx.x * kGrid + blockIdx.x] = bins[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&h->tickets[6], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // exclusive scan of the digit-major table: digit 0 of every CTA, digit 1, ...
+    const uint32_t total_entries = kRadix * kGrid;
+    const uint32_t per = (total_entries + kBlock - 1) / kBlock;
+    uint32_t lo = threadIdx.x * per, hi = min(lo + per, total_entries), sum = 0;
+    volatile uint32_t *tab = f.sort_hist;
+    for (uint32_t i = lo; i < hi; ++i) sum += tab[i];
+    uint32_t tot;
+    uint32_t at = block_exclusive_scan(sum, sm, tot);
+    for (uint32_t i = lo; i < hi; ++i) { uint32_t v = tab[i]; tab[i] = at; at += v; }
+    if (threadIdx.x == 0) h->tickets[6] = 0;
+}
+
+__global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift)
+{
+    __shared__ uint32_t base[kRadix];              // next free global slot per digit for this CTA
+    __shared__ uint32_t warp_count[kBlock / 32][kRadix];
+    frame_header *h = f.hdr;
+    uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
+    sort_slice(n, begin, end);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = f.sort_hist[threadIdx.x * kGrid + blockIdx.x];
+    for (int w = 0; w < kBlock / 32; ++w) warp_count[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t *kin = f.keys[src];
+    const float *vin = f.vals[src];
+    uint64_t *kout = f.keys[src ^ 1];
+    float *vout = f.vals[src ^ 1];
+    for (uint32_t tile = begin; tile < end; tile += kBlock) {
+        uint32_t i = tile + threadIdx.x;
+        bool valid = i < end;
+        uint64_t key = valid ? kin[i] : 0;
+        float val = valid ? vin[i] : 0.0f;
+        uint32_t digit = valid ? uint32_t(key >> shift) & 0xffu : 0x100u + uint32_t(lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warp_count[warp][digit] = __popc(peers);
+        __syncthreads();
+        {   // thread d owns digit d: prefix over the warps, then advance the CTA base
+            uint32_t d = threadIdx.x, run = base[d];
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) {
+                uint32_t c = warp_count[w][d];
+                warp_count[w][d] = run;
+                run += c;
+            }
+            base[d] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            uint32_t dst = warp_count[warp][digit] + rank;
+            kout[dst] = key;
+            vout[dst] = val;
+        }
+        __syncthreads();
+        // prefixes (also of digits absent from a warp) must not leak into the next step
+        {
+            uint32_t d = threadIdx.x;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) warp_count[w][d] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// Sorts keys[0]/vals[0]; *result_buffer receives which of the two buffers holds
+// the sorted data.
+void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer)
+{
+    int passes = (key_bits + 7) / 8;
+    int src = 0;
+    for (int p = 0; p < passes; ++p) {
+        k_sort_hist<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
+        k_sort_scatter<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
+        src ^= 1;
+    }
+    *result_buffer = src;
+}
+
+}  // namespace cb200

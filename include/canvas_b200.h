@@ -152,8 +152,10 @@ int cb200_read_f32(cb200_canvas *canvas, float *dst);
 int cb200_read_mask(cb200_canvas *canvas, uint32_t slot, float *dst);
 /* Clear to transparent black and forget all mask slots. */
 int cb200_clear(cb200_canvas *canvas);
-/* Copy mask slot `src` to `dst` is never needed: slots are immutable once
- * written.  The host may recycle a slot id after the frame that last used it. */
+/* Clip-mask slots are immutable once written (clip() always writes a fresh
+ * slot).  The host tells the back end which slots are still reachable (current
+ * mask + save stack); every other plane is freed. */
+int cb200_masks_keep(cb200_canvas *canvas, const uint32_t *slots, uint32_t n);
 
 /* Readback without the host copy: runs the sRGB/dither kernel into a device
  * buffer owned by the canvas and returns its device pointer (for NCCL gathers
