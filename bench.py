@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Ghostscript tiger (305 draws, 2222 cubics) at 4096 x 4096.
+
+Contract (see the round brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+
+  step     one whole frame: clear + flatten/stroke + scan conversion + sort + coverage + tile
+           compositing of all 305 draws (the reference demo's timed region, tiger.cpp:104-4323:
+           draw calls only, fresh canvas each frame; its readback is outside the timed region).
+  value    frames/s with the lowered frame already resident in HBM (cb200_frame_upload once,
+           cb200_frame_replay per step), CUDA events on the canvas stream, max over ranks.
+  e2e      frames/s through the public drop-in API with HOST buffers every step: canvas-script
+           replay (host path building + lowering) -> pinned H2D -> kernels -> get_image_data
+           (sRGB/dither kernel + D2H of the RGBA8 image).
+  roofline the tile compositor (k_composite): algorithmic bytes = 32 B per composited pixel
+            / its CUDA-event time, against the measured HBM peak.
+  cpu_baseline  the unmodified reference (oracle/_ref/libcanvas_ref_fast.so, -O3 -march=native
+           -ffp-contract=off) rendering the same call stream on the box's host cores, bounded sample.
+
+N > 1 (torchrun): frames are independent canvases, every rank renders whole frames (weak scaling,
+no data-path collective); `--mode bands` instead shards ONE frame by scanline bands and gathers
+the RGBA8 bands with NCCL all_gather (strong scaling).
+
+`--impl reference` times the reference's own CPU implementation with all host threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tiger_4096_frames_per_s"
+UNIT = "frames/s"
+SIZE = 4096
+ALGO_BYTES_PER_COMPOSITED_PIXEL = 32.0     # 16 B load + 16 B store of the float4 texel
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe's line)."""
+
+    def __init__(self, index):
+        self.rows, self.stop = [], threading.Event()
+        self.cmd = ["nvidia-smi", "-i", str(index),
+                    "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                    "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                    "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"]
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm ----
+
+def run_reference(args, rank, world):
+    """The reference's own CPU renderer on the same call stream, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    from tests import harness as H
+    lib = H.reference_library(fast=True) or H.reference_library()
+    if lib is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
+        return
+    script = H.tiger_script(SIZE, SIZE)
+    threads = os.cpu_count() or 1
+
+    def frames(count, out, slot):
+        t0 = time.perf_counter()
+        for _ in range(count):
+            h = lib.cv_create(SIZE, SIZE)           # fresh canvas per frame, as tiger.cpp does
+            lib.cv_run_script(h, script, len(script), None, 0, None)
+            lib.cv_destroy(h)
+        out[slot] = time.perf_counter() - t0
+
+    def step(per_thread):
+        out = [0.0] * threads
+        ts = [threading.Thread(target=frames, args=(per_thread, out, i)) for i in range(threads)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return time.perf_counter() - t0
+
+    # one step = one frame per host thread (ctypes releases the GIL): a bounded sample of the workload
+    for _ in range(min(args.warmup, 1)):
+        step(1)
+    steps = max(1, min(args.steps, 4))
+    t = sum(step(1) for _ in range(steps))
+    fps = steps * threads / t
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "tiger_4096 (demos/tiger call stream fit to 4096x4096, source_over, no shadow)",
+                       "frames_per_step": threads},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": "%d steps x %d concurrent frames (one per host thread), draw calls only" % (steps, threads)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(script, budget_s=20.0):
+    """Single-thread reference frames for about `budget_s` seconds (what one frame costs the reference)."""
+    from tests import harness as H
+    lib = H.reference_library(fast=True) or H.reference_library()
+    kind = "reference"
+    if lib is None:
+        return None
+    n, t0 = 0, time.perf_counter()
+    best = 1e30
+    while True:
+        t1 = time.perf_counter()
+        h = lib.cv_create(SIZE, SIZE)
+        lib.cv_run_script(h, script, len(script), None, 0, None)
+        lib.cv_destroy(h)
+        best = min(best, time.perf_counter() - t1)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 24:
+            break
+    return {"value": 1.0 / best, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d whole 4096x4096 tiger frames on one host thread (the reference is single-threaded), best-of" % n}
+
+
+# ------------------------------------------------------------------------ our arm ----
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
+    ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from tests import harness as H
+    from canvas_ity_b200 import _native
+    lib = _native.load()
+    if lib.cb200_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; this back end has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = args.size
+    bands = args.mode == "bands" and world > 1
+    y0, rows = (rank * size // world, (rank + 1) * size // world - rank * size // world) if bands else (0, size)
+
+    script = H.tiger_script(size, size)
+    frame = H.lower_script(script, size, size)[0]
+    cv = C.c_void_p()
+    rc = lib.cb200_canvas_create_band(size, size, y0, rows, local, C.byref(cv))
+    if rc:
+        raise SystemExit("cb200_canvas_create: " + lib.cb200_last_error().decode())
+
+    def check(rc):
+        if rc:
+            raise RuntimeError(lib.cb200_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: `value` ----
+    check(lib.cb200_frame_upload(cv, C.byref(frame.frame)))
+    stats = _native.Stats()
+    for _ in range(args.warmup):
+        check(lib.cb200_frame_replay(cv, 1))
+    check(lib.cb200_sync(cv))
+    check(lib.cb200_get_stats(cv, C.byref(stats)))
+    launches_before = stats.kernel_launches
+    gathered = torch.empty((size, size, 4), dtype=torch.uint8, device="cuda") if bands else None
+    band = torch.empty((rows, size, 4), dtype=torch.uint8, device="cuda") if bands else None
+    frame_ms, comp_ms = [], []
+    barrier()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            check(lib.cb200_frame_replay(cv, 1))
+            if bands:        # one image out of N bands: sRGB/dither on device, NCCL all_gather of RGBA8 rows
+                check(lib.cb200_read_rgba8_into(cv, C.c_void_p(band.data_ptr()), size, rows, 0, y0))
+                check(lib.cb200_sync(cv))
+                dist.all_gather_into_tensor(gathered.view(-1), band.view(-1))
+            check(lib.cb200_get_stats(cv, C.byref(stats)))      # waits for the frame; CUDA-event times
+            frame_ms.append(stats.last_frame_ms)
+            comp_ms.append(stats.composite_ms)
+        barrier()
+        wall = time.perf_counter() - t0
+    device_s = sum(frame_ms) / 1e3 if not bands else wall
+    check(lib.cb200_get_stats(cv, C.byref(stats)))
+    launches = int(stats.kernel_launches - launches_before)
+    composited = int(stats.composited_pixels)
+
+    # ---- end-to-end arm through the public API with host buffers: `e2e` ----
+    e2e = None
+    if not bands:
+        h = lib.cv_create_band(size, size, local, 0, size)
+        out = np.zeros((size, size, 4), np.uint8)
+        clear = b""
+
+        def one_frame():
+            # fresh-canvas semantics: destination_out-free clear through the API = put nothing; we
+            # re-create nothing: cb200_clear is the cheap equivalent of constructing a new canvas
+            check(lib.cb200_clear(lib.cv_device(h)))
+            lib.cv_run_script(h, script, len(script), None, 0, None)
+            lib.cv_get_image_data(h, out.ctypes.data, size, size, 4 * size, 0, 0)
+        for _ in range(args.warmup):
+            one_frame()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_frame()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        lib.cv_destroy(h)
+        e2e = {"seconds": e2e_s, "h2d": frame.upload_bytes, "d2h": size * size * 4}
+
+    # ---- max over ranks, aggregate ----
+    t_dev = torch.tensor([device_s, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    device_s, e2e_s = float(t_dev[0]), float(t_dev[1])
+    frames_total = args.steps * (1 if bands else world)
+    value = frames_total / device_s
+    peak, peak_src = measured_hbm_peak()
+    comp_avg_s = float(np.mean(comp_ms)) / 1e3
+    achieved = composited * ALGO_BYTES_PER_COMPOSITED_PIXEL / comp_avg_s / 1e9
+    lib.cb200_canvas_destroy(cv)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * device_s / args.steps, "higher_is_better": True,
+            "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "tiger_%d (demos/tiger call stream, 305 draws / 2222 cubics, fit to %dx%d, source_over, "
+                                   "no shadow; fresh canvas per frame)" % (size, size, size),
+                       "canvas": [size, size], "parallelism": ("bands%d+allgather" % world) if bands else ("frames x%d" % world),
+                       "l2": "268 MB float framebuffer per frame > 126 MB L2 (inputs larger than L2, no explicit flush)",
+                       "composited_pixels_per_frame": composited,
+                       "composited_mpix_per_s": composited * value / 1e6 / (1 if bands else world) * (1 if bands else world),
+                       "canvas_mpix_per_s": size * size * value / 1e6},
+            "roofline": {"bound": "hbm", "kernel": "k_composite", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": composited * ALGO_BYTES_PER_COMPOSITED_PIXEL,
+                         "kernel_ms": comp_avg_s * 1e3,
+                         "note": "algorithmic = 32 B x composited pixels (3.05x overdraw); the tile compositor keeps "
+                                 "overlapping draws in registers, so DRAM traffic is about 1/3 of this and frac may exceed 1"},
+            "stages_ms": {"geometry": stats.geometry_ms, "raster": stats.raster_ms, "sort": stats.sort_ms,
+                          "composite": stats.composite_ms, "frame": stats.last_frame_ms},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+        }
+        if e2e:
+            line["e2e"] = {"value": args.steps * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                           "d2h_bytes_per_step": e2e["d2h"]}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(script)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,30 @@ class Frame(C.Structure):          # cb200_frame
 
 
 FRAME_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Frame))
+SIZEOF_DRAW, SIZEOF_SUBPATH, SIZEOF_BRUSH, SIZEOF_IMAGE = 140, 16, 48, 16
+
+
+class OwnedFrame:
+    """Deep copy of a cb200_frame (the pointers handed to a frame tap die with the callback)."""
+
+    def __init__(self, f):
+        def grab(ptr, nbytes):
+            return C.create_string_buffer(C.string_at(ptr, nbytes), nbytes) if ptr and nbytes else C.create_string_buffer(1)
+        self.parts = {
+            "draws": grab(f.draws, f.n_draws * SIZEOF_DRAW), "subpaths": grab(f.subpaths, f.n_subpaths * SIZEOF_SUBPATH),
+            "points": grab(f.points, f.n_points * 8), "brushes": grab(f.brushes, f.n_brushes * SIZEOF_BRUSH),
+            "colors": grab(f.colors, f.n_colors * 16), "stops": grab(f.stops, f.n_colors * 4),
+            "dashes": grab(f.dashes, f.n_dashes * 4), "images": grab(f.images, f.n_images * SIZEOF_IMAGE),
+            "texels": grab(f.texels, f.texel_bytes)}
+        self.frame = Frame()
+        for name, _ in Frame._fields_:
+            if name in self.parts:
+                setattr(self.frame, name, C.cast(self.parts[name], C.c_void_p))
+            else:
+                setattr(self.frame, name, getattr(f, name))
+        self.n_draws = f.n_draws
+        self.n_points = f.n_points
+        self.upload_bytes = sum(len(p) for p in self.parts.values())
 
 # name -> (restype, argtypes); every symbol the two headers declare
 SIGNATURES = {
@@ -48,12 +72,14 @@ SIGNATURES = {
     "cb200_clear": (C.c_int, [C.c_void_p]),
     "cb200_masks_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "cb200_read_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cb200_read_rgba8_into": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4),
     "cb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cb200_debug_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_debug_runs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_abi_version": (C.c_int, []),
     "cb200_device_count": (C.c_int, []),
+    "cb200_struct_size": (C.c_int, [C.c_int]),
     # include/canvas_b200_api.h
     "cv_create": (C.c_void_p, [C.c_int, C.c_int]),
     "cv_create_band": (C.c_void_p, [C.c_int] * 5),

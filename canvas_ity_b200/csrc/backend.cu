@@ -561,6 +561,18 @@ extern "C" {
 
 int cb200_abi_version(void) { return CB200_ABI_VERSION; }
 
+int cb200_struct_size(int which)
+{
+    switch (which) {
+    case 0: return int(sizeof(cb200_draw));
+    case 1: return int(sizeof(cb200_subpath));
+    case 2: return int(sizeof(cb200_brush));
+    case 3: return int(sizeof(cb200_image));
+    case 4: return int(sizeof(cb200_frame));
+    default: return -1;
+    }
+}
+
 int cb200_device_count(void)
 {
     int n = 0;
@@ -743,6 +755,20 @@ int cb200_read_rgba8_device(cb200_canvas *cv, void **device_ptr)
     rc = readback_to_device(cv, cv->width, cv->band_rows, 0, cv->band_y0);
     if (rc != CB200_OK) return rc;
     *device_ptr = cv->rgba8.p;
+    return CB200_OK;
+}
+
+int cb200_read_rgba8_into(cb200_canvas *cv, void *device_dst, int width, int height, int x, int y)
+{
+    if (!cv || !device_dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (width <= 0 || height <= 0) return CB200_OK;
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    launch_readback(cv->fb, cv->width, cv->band_y0, cv->band_rows, static_cast<uint8_t *>(device_dst), width, height,
+                    x, y, cv->stream);
+    ++cv->launches;
+    CK(cudaGetLastError());
     return CB200_OK;
 }
 

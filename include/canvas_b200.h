@@ -161,6 +161,10 @@ int cb200_masks_keep(cb200_canvas *canvas, const uint32_t *slots, uint32_t n);
  * buffer owned by the canvas and returns its device pointer (for NCCL gathers
  * and device-resident timing). */
 int cb200_read_rgba8_device(cb200_canvas *canvas, void **device_ptr);
+/* Same kernel, but into a caller-owned DEVICE buffer of width*height*4 bytes (a
+ * torch tensor, an NCCL send buffer): asynchronous on the canvas stream, follow
+ * with cb200_sync() before handing the buffer to another stream. */
+int cb200_read_rgba8_into(cb200_canvas *canvas, void *device_dst, int width, int height, int x, int y);
 
 /* ---- introspection / measurement ------------------------------------------- */
 
@@ -183,6 +187,8 @@ int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative
 
 const char *cb200_last_error(void);
 int cb200_abi_version(void);
+/* sizeof of the ABI records, for bindings that mirror them: 0 draw, 1 subpath, 2 brush, 3 image, 4 frame */
+int cb200_struct_size(int which);
 int cb200_device_count(void);
 
 #ifdef __cplusplus

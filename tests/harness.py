@@ -168,6 +168,25 @@ def render_oracle(script, width, height):
         orc.oracle_canvas_destroy(o)
 
 
+def lower_script(script, width, height):
+    """Run `script` through the front end only and return the lowered frames it would submit
+    (deep copies), plus the upload size.  No device is touched."""
+    prod = product_library()
+    frames = []
+
+    @_native.FRAME_FN
+    def on_frame(user, frame):
+        frames.append(_native.OwnedFrame(frame.contents))
+
+    h = prod.cv_create_tapped(width, height, C.cast(on_frame, C.c_void_p), None, None, None)
+    try:
+        _run(prod, h, script)
+        prod.cv_flush(h)
+    finally:
+        prod.cv_destroy(h)
+    return frames
+
+
 # ------------------------------------------------------------------ comparison ----
 
 def float_mismatch(got, want, tol=FLOAT_TOL):
