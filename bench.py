@@ -241,13 +241,15 @@ def main():
     if not bands:
         h = lib.cv_create_band(size, size, local, 0, size)
         out = np.zeros((size, size, 4), np.uint8)
-        clear = b""
+        # every frame starts from the constructor's state like the demo's fresh canvas: save/restore
+        # brackets the call stream (transform, styles), cb200_clear resets pixels and clip masks
+        e2e_script = bytes([H.OP["SAVE"]]) + script + bytes([H.OP["RESTORE"]])
 
         def one_frame():
             # fresh-canvas semantics: destination_out-free clear through the API = put nothing; we
             # re-create nothing: cb200_clear is the cheap equivalent of constructing a new canvas
             check(lib.cb200_clear(lib.cv_device(h)))
-            lib.cv_run_script(h, script, len(script), None, 0, None)
+            lib.cv_run_script(h, e2e_script, len(e2e_script), None, 0, None)
             lib.cv_get_image_data(h, out.ctypes.data, size, size, 4 * size, 0, 0)
         for _ in range(args.warmup):
             one_frame()

@@ -104,12 +104,13 @@ struct cb200_canvas {
 
     // device work buffers
     dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
-        half_count, half_offset, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
+        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
         te_first, partials, sort_hist;
     dev_buf<float2> pts;
     dev_buf<loop_span> loops;
     dev_buf<stroke_src> sources;
     dev_buf<float4> pieces, texels;
+    dev_buf<comp_rec> comp;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8;
@@ -227,6 +228,14 @@ int stage_frame(cb200_canvas *cv, const cb200_frame *in, staged_frame &sf)
         memset(&j, 0, sizeof j);
         j.draw = i;
         j.kind = d.kind == CB200_CLIP ? JOB_CLIP : JOB_MAIN;
+        // occlusion-culling candidate: where its coverage is exactly 1 this draw REPLACES the pixel
+        // (hpp:2583-2591 with cov = vis = 1): solid colour, unclipped, and either source_copy or
+        // source_over with global_alpha == colour alpha == 1
+        if (j.kind == JOB_MAIN && d.mask_src == 0 && in->brushes[d.brush].type == CB200_BRUSH_COLOR &&
+            in->brushes[d.brush].n_colors == 1) {
+            float a = in->colors[4 * size_t(in->brushes[d.brush].first_color) + 3];
+            if (d.op == 2u || (d.op == 14u && d.global_alpha == 1.0f && a == 1.0f)) j.opaque = 1;
+        }
         sf.jobs.push_back(j);
     }
     // static stroke sources, grouped by draw (keeps every draw's K3 output contiguous)
@@ -328,7 +337,10 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->dash_tail.reserve(sf.dash_items.size() + 1));
     CK(cv->sources.reserve(want_sources));
     CK(cv->half_count.reserve(2 * size_t(want_sources) + 2));
-    CK(cv->half_offset.reserve(2 * size_t(want_sources) + 2));
+    CK(cv->half_offset.reserve(2 * size_t(want_sources) + 4));
+    CK(cv->half_unit_off.reserve(2 * size_t(want_sources) + 4));
+    CK(cv->half_dirty.reserve(2 * size_t(want_sources) + 4));
+    CK(cv->stroke_unit_pts.reserve(size_t(want_pts) + 2 * size_t(want_sources) + 4));
     CK(cv->loops.reserve(sf.subpaths.size() + want_dash_sub + 2 * size_t(want_sources) + 2));
     CK(cv->pieces.reserve(3 * size_t(want_items)));
     CK(cv->piece_job.reserve(3 * size_t(want_items)));
@@ -347,7 +359,8 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->planes.reserve(want_planes));
     CK(cv->planes_tmp.reserve(want_planes));
     CK(cv->partials.reserve(8 * kGrid));
-    CK(cv->sort_hist.reserve(256 * kGrid));
+    CK(cv->comp.reserve(sf.jobs.size() + 1));
+    CK(cv->sort_hist.reserve(256 * kGrid + 256));
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
     cv->cap_items = want_items; cv->cap_rows = want_rows; cv->cap_runs = want_runs;
@@ -446,6 +459,7 @@ int upload_frame(cb200_canvas *cv)
     f.sources = cv->sources.p;
     f.n_static_sources = uint32_t(sf.sources.size());
     f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
+    f.comp = cv->comp.p;
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
     f.texels = cv->texels.p;
@@ -454,6 +468,8 @@ int upload_frame(cb200_canvas *cv)
     f.loops = cv->loops.p; f.cap_loops = uint32_t(cv->loops.cap);
     f.dash_pts_count = cv->dash_pts_count.p; f.dash_sub_count = cv->dash_sub_count.p; f.dash_tail = cv->dash_tail.p;
     f.half_count = cv->half_count.p; f.half_offset = cv->half_offset.p;
+    f.half_unit_off = cv->half_unit_off.p; f.half_dirty = cv->half_dirty.p; f.stroke_unit_pts = cv->stroke_unit_pts.p;
+    f.cap_stroke_units = uint32_t(cv->stroke_unit_pts.cap);
     f.cap_sources = cv->cap_sources;
     f.stroke_loop_base = uint32_t(sf.subpaths.size()) + cv->cap_dash_subpaths;
     f.pieces = cv->pieces.p; f.piece_job = cv->piece_job.p; f.piece_rows = cv->piece_rows.p;
@@ -505,7 +521,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
-                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 2) + 7 + 2 * ((sf.key_bits + 7) / 8) + 1 +
+                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 7) + 7 + 3 * ((sf.key_bits + 7) / 8) + 2 +
                     (sf.shadow_jobs.empty() ? 0 : 7) + 1;
     cv->pending = true;
     CK(cudaGetLastError());
@@ -635,11 +651,11 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
     cv->unit_count.release(); cv->unit_offset.release(); cv->pt_loop.release();
     cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
-    cv->half_count.release(); cv->half_offset.release(); cv->piece_job.release();
+    cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->piece_job.release();
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->te_flags.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
-    cv->pieces.release(); cv->texels.release(); cv->keys0.release(); cv->keys1.release();
+    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 8; ++i)

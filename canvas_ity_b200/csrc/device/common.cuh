@@ -90,10 +90,23 @@ struct job_rec {
     int32_t left, top, bw, bh;
     uint64_t plane_offset;
     float w1, w2; int32_t radius;
+    uint32_t opaque;                       // host: solid, alpha 1, source_over/copy, unclipped
 };
 
-// Output loops of the geometry stage: closed polygons in device space.
-struct loop_rec { uint32_t first_point, n_points, draw; };
+// Everything the tile compositor needs to know about one job, packed into one
+// 128-byte line so a warp fetches it with a single coalesced load.
+struct comp_rec {
+    uint32_t kind, op, flags, mask_src, mask_dst, brush, draw, te_base;
+    int32_t tx0, ty0, tw, th, cx0, cy0, cx1, cy1;
+    float alpha;                       // global_alpha
+    float color[4];                    // solid colour, or the shadow tint
+    int32_t border, left, top, bw;     // shadow plane placement
+    uint32_t plane_lo, plane_hi;       // plane offset (floats), 64 bit
+    uint32_t brush_type, pad[4];
+};
+static_assert(sizeof(comp_rec) == 128, "comp_rec must be one 128 B line");
+enum { COMP_EVERYWHERE = 1, COMP_OPAQUE = 2 };   // comp_rec.flags
+enum { TE_NONEMPTY = 1, TE_COVERED = 2 };        // te_flags
 
 struct frame_header {
     // inputs
@@ -104,6 +117,7 @@ struct frame_header {
     uint32_t n_dash_points, n_dash_subpaths;
     uint32_t n_sources;                    // stroke sources: static + dashed
     uint32_t n_stroke_points;              // K3 output
+    uint32_t n_stroke_units;               // K3 work items (joins + caps)
     uint32_t n_items;                      // K4 work items (job x loop point)
     uint32_t n_row_items;                  // (piece, scanline) pairs
     uint32_t n_runs;

@@ -28,8 +28,13 @@ __device__ __forceinline__ float keys_weight(float t)
     return t < 1.0f ? (1.5f * t - 2.5f) * t * t + 1.0f : ((-0.5f * t + 2.5f) * t - 4.0f) * t + 2.0f;
 }
 
+struct paint_tables {
+    const float4 *colors; const float *stops; const float4 *texels;
+    const brush_rec *brushes; const draw_rec *draws;
+};
+
 // paint_pixel, hpp:2265-2377.  `at` is the device-space pixel centre.
-__device__ rgba paint_at(const device_frame &f, const brush_rec &b, const affine &inv, vec2 at)
+__device__ rgba paint_at(const paint_tables &f, const brush_rec &b, const affine &inv, vec2 at)
 {
     if (b.n_colors == 0) return mk(0.0f, 0.0f, 0.0f, 0.0f);
     if (b.type == CB200_BRUSH_COLOR) {
@@ -122,12 +127,56 @@ __device__ __forceinline__ void blend(float4 &back, rgba fore, uint32_t op, floa
 }
 
 constexpr int kRowsPerThread = kTile * kTile / kBlock;      // 4
+constexpr int kBatch = kBlock / 32;                         // jobs staged in shared memory at a time
 
-__global__ void __launch_bounds__(kBlock) k_composite(device_frame f, canvas_target t, int sb,
-                                                       int tiles_x, int tile_y0)
+// Coverage of one tile row from staged row info (see tile_cov.cuh for the global
+// memory variant used by the shadow rasteriser).
+__device__ __forceinline__ float staged_row_sum(const cov_source &c, float backdrop, uint32_t first, uint32_t job,
+                                                int y, int x0, float *row_buf)
+{
+    if (first == kNoRun) return backdrop;
+    const int lane = threadIdx.x & 31;
+    const uint64_t row_key = (uint64_t(job) << c.by) | uint64_t(uint32_t(y));
+    const uint64_t xmask = (1ull << c.bx) - 1;
+    row_buf[lane] = __int_as_float(0x7fc00000);
+    __syncwarp();
+    for (uint32_t k = first;; k += 32) {
+        uint32_t idx = k + uint32_t(lane);
+        bool ok = idx < c.n_runs;
+        uint64_t key = ok ? c.keys[idx] : ~0ull;
+        int col = int(key & xmask) - x0;
+        ok = ok && (key >> c.bx) == row_key && col < kTile;
+        if (ok) {
+            float v = c.cumulative[idx];
+            if (v == v) row_buf[col] = v;
+        }
+        if (!__all_sync(0xffffffffu, ok)) break;
+    }
+    __syncwarp();
+    float mine = row_buf[lane];
+    uint32_t have = __ballot_sync(0xffffffffu, mine == mine);
+    uint32_t upto = have & (0xffffffffu >> (31 - lane));
+    int src = upto ? 31 - __clz(upto) : 0;
+    float got = __shfl_sync(0xffffffffu, mine, src);
+    __syncwarp();
+    return upto ? got : backdrop;
+}
+
+// Non-solid brushes: kept out of line so the solid path stays small.
+__device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t draw, float x, float y)
+{
+    return paint_at(f, f.brushes[brush], f.draws[draw].inverse, v2(x, y));
+}
+
+__global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_target t, int sb,
+                                                          int tiles_x, int tile_y0)
 {
     __shared__ uint32_t sm[33];
-    __shared__ uint32_t job_list[kBlock];
+    __shared__ uint32_t s_job[kBlock], s_te[kBlock];
+    __shared__ int s_start;
+    __shared__ __align__(16) comp_rec s_rec[kBatch];
+    __shared__ float s_back[kBatch][kTile];
+    __shared__ uint32_t s_first[kBatch][kTile];
     __shared__ float row_buf[kBlock / 32][kTile];
     frame_header *h = f.hdr;
     if (h->overflow) return;
@@ -136,6 +185,27 @@ __global__ void __launch_bounds__(kBlock) k_composite(device_frame f, canvas_tar
     const int x = tx * kTile + lane;
     const int band_y1 = t.band_y0 + t.band_rows;
     const bool x_in = x < t.width;
+    const int tile_x0 = tx * kTile, tile_y0p = ty * kTile;
+    const uint32_t n_jobs = h->n_jobs;
+
+    // Pass 1 -- occlusion culling: the last job that paints this whole tile with an
+    // opaque solid colour (covered tile entry, source_over/copy, alpha 1, unclipped)
+    // makes every earlier job, and the old framebuffer content, irrelevant.
+    if (threadIdx.x == 0) s_start = -1;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_jobs; base += kBlock) {
+        uint32_t j = base + threadIdx.x;
+        if (j < n_jobs) {
+            const comp_rec &c = f.comp[j];
+            if ((c.flags & COMP_OPAQUE) && c.cx0 < tile_x0 + kTile && c.cx1 > tile_x0 &&
+                c.cy0 < tile_y0p + kTile && c.cy1 > tile_y0p) {
+                uint32_t te = c.te_base + uint32_t(ty - c.ty0) * uint32_t(c.tw) + uint32_t(tx - c.tx0);
+                if (f.te_flags[te] & TE_COVERED) atomicMax(&s_start, int(j));
+            }
+        }
+    }
+    __syncthreads();
+    const int start_job = s_start;
 
     float4 px[kRowsPerThread];
     int py[kRowsPerThread];
@@ -144,74 +214,89 @@ __global__ void __launch_bounds__(kBlock) k_composite(device_frame f, canvas_tar
     for (int k = 0; k < kRowsPerThread; ++k) {
         py[k] = ty * kTile + warp + k * (kBlock / 32);
         live[k] = x_in && py[k] >= t.band_y0 && py[k] < band_y1;
-        px[k] = live[k] ? t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]
-                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        px[k] = (live[k] && start_job < 0) ? t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]
+                                            : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     const cov_source cs = make_cov_source(f, sb);
-    const int tile_x0 = tx * kTile, tile_y0p = ty * kTile;
-    const uint32_t n_jobs = h->n_jobs;
+    const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
     unsigned long long painted = 0;
 
-    for (uint32_t base = 0; base < n_jobs; base += kBlock) {
+    // Pass 2 -- replay the surviving jobs in submission order.
+    const uint32_t first_job = start_job < 0 ? 0u : uint32_t(start_job);
+    for (uint32_t base = first_job - first_job % kBlock; base < n_jobs; base += kBlock) {
         // which of these 256 jobs touch this tile?  (ordered compaction)
-        uint32_t j = base + threadIdx.x, hit = 0;
-        if (j < n_jobs) {
-            const job_rec &jr = f.jobs[j];
-            if (jr.cx0 < tile_x0 + kTile && jr.cx1 > tile_x0 && jr.cy0 < tile_y0p + kTile &&
-                jr.cy1 > tile_y0p) {
-                if (jr.kind == JOB_SHADOW) hit = 1;
+        uint32_t j = base + threadIdx.x, hit = 0, te = 0;
+        if (j < n_jobs && j >= first_job) {
+            const comp_rec &c = f.comp[j];
+            if (c.cx0 < tile_x0 + kTile && c.cx1 > tile_x0 && c.cy0 < tile_y0p + kTile && c.cy1 > tile_y0p) {
+                if (c.kind == JOB_SHADOW) hit = 1;
                 else {
-                    uint32_t te = jr.te_base + uint32_t(ty - jr.ty0) * uint32_t(jr.tw) + uint32_t(tx - jr.tx0);
-                    bool everywhere = jr.kind == JOB_CLIP || (~f.draws[jr.draw].op & 8u);
-                    hit = (everywhere || f.te_flags[te]) ? 1 : 0;
+                    te = c.te_base + uint32_t(ty - c.ty0) * uint32_t(c.tw) + uint32_t(tx - c.tx0);
+                    hit = ((c.flags & COMP_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY)) ? 1 : 0;
                 }
             }
         }
         uint32_t n_hit;
         uint32_t slot = block_exclusive_scan(hit, sm, n_hit);
-        if (hit) job_list[slot] = j;
+        if (hit) { s_job[slot] = j; s_te[slot] = te; }
         __syncthreads();
 
-        for (uint32_t q = 0; q < n_hit; ++q) {
-            const uint32_t jj = job_list[q];
-            const job_rec &jr = f.jobs[jj];
-            const draw_rec &d = f.draws[jr.draw];
-            const float *mask = d.mask_src ? t.mask_planes[d.mask_src] : nullptr;
-            if (jr.kind == JOB_SHADOW) {
-                const float *plane = f.planes + jr.plane_offset;
-                const rgba tint = mk(d.shadow_color[0], d.shadow_color[1], d.shadow_color[2], d.shadow_color[3]);
+        for (uint32_t b0 = 0; b0 < n_hit; b0 += kBatch) {
+            // stage up to kBatch jobs: one warp per job fetches its record and the 32
+            // (backdrop, first run) pairs of this tile entry -- all loads in flight at once
+            if (b0 + warp < n_hit) {
+                uint32_t jj = s_job[b0 + warp], tte = s_te[b0 + warp];
+                reinterpret_cast<uint32_t *>(&s_rec[warp])[lane] = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
+                bool has_rows = f.comp[jj].kind != JOB_SHADOW;
+                s_back[warp][lane] = has_rows ? f.te_backdrop[tte * kTile + lane] : 0.0f;
+                s_first[warp][lane] = has_rows ? f.te_first[tte * kTile + lane] : kNoRun;
+            }
+            __syncthreads();
+            const uint32_t n_here = min(uint32_t(kBatch), n_hit - b0);
+            for (uint32_t q = 0; q < n_here; ++q) {
+                const comp_rec &c = s_rec[q];
+                const uint32_t jj = s_job[b0 + q];
+                const float *mask = c.mask_src ? t.mask_planes[c.mask_src] : nullptr;
+                const uint32_t op = c.op;
+                if (c.kind == JOB_SHADOW) {
+                    const float *plane = f.planes + (uint64_t(c.plane_hi) << 32 | c.plane_lo);
+                    const rgba tint = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
+#pragma unroll
+                    for (int k = 0; k < kRowsPerThread; ++k) {
+                        if (!live[k] || x < c.cx0 || x >= c.cx1 || py[k] < c.cy0 || py[k] >= c.cy1) continue;
+                        float vis = mask ? fminf(fabsf(mask[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
+                        if (vis < kThreshold) continue;
+                        float s = plane[size_t(py[k] + c.border - c.top) * size_t(c.bw) + size_t(x + c.border - c.left)];
+                        blend(px[k], scale(c.alpha * s, tint), op, vis);
+                        ++painted;
+                    }
+                    continue;
+                }
+                const bool everywhere = (~op & 8u) != 0;
+                const bool solid = c.brush_type == CB200_BRUSH_COLOR;
+                const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
+                const float alpha = c.alpha;
+                float *mask_out = c.kind == JOB_CLIP ? t.mask_planes[c.mask_dst] : nullptr;
 #pragma unroll
                 for (int k = 0; k < kRowsPerThread; ++k) {
-                    if (!live[k] || x < jr.cx0 || x >= jr.cx1 || py[k] < jr.cy0 || py[k] >= jr.cy1) continue;
-                    float vis = mask ? fminf(fabsf(mask[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
-                    if (vis < kThreshold) continue;
-                    float s = plane[size_t(py[k] + jr.border - jr.top) * size_t(jr.bw) + size_t(x + jr.border - jr.left)];
-                    blend(px[k], scale(d.global_alpha * s, tint), d.op, vis);
+                    const int ly = warp + k * (kBlock / 32);
+                    // warp-uniform: every lane of the warp shares the row
+                    float sum = staged_row_sum(cs, s_back[q][ly], s_first[q][ly], jj, py[k], tile_x0, row_buf[warp]);
+                    float cov = fminf(fabsf(sum), 1.0f);
+                    if (!live[k]) continue;
+                    size_t at = size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x);
+                    float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
+                    if (mask_out) { mask_out[at] = cov * vis; continue; }
+                    if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
+                    rgba paint = solid ? flat
+                                       : (c.brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
+                                                                : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(py[k]) + 0.5f));
+                    blend(px[k], scale(cov * alpha, paint), op, vis);
                     ++painted;
                 }
-                continue;
             }
-            const uint32_t te = jr.te_base + uint32_t(ty - jr.ty0) * uint32_t(jr.tw) + uint32_t(tx - jr.tx0);
-            const brush_rec *br = jr.kind == JOB_CLIP ? nullptr : &f.brushes[d.brush];
-            const bool everywhere = (~d.op & 8u) != 0;
-            float *mask_out = jr.kind == JOB_CLIP ? t.mask_planes[d.mask_dst] : nullptr;
-#pragma unroll
-            for (int k = 0; k < kRowsPerThread; ++k) {
-                const int ly = warp + k * (kBlock / 32);
-                // warp-uniform: every lane of the warp shares the row
-                float sum = tile_row_sum(cs, te, ly, jj, py[k], tile_x0, row_buf[warp]);
-                float cov = fminf(fabsf(sum), 1.0f);
-                if (!live[k]) continue;
-                size_t at = size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x);
-                float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
-                if (mask_out) { mask_out[at] = cov * vis; continue; }
-                if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
-                rgba paint = paint_at(f, *br, d.inverse, v2(float(x) + 0.5f, float(py[k]) + 0.5f));
-                blend(px[k], scale(cov * d.global_alpha, paint), d.op, vis);
-                ++painted;
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int k = 0; k < kRowsPerThread; ++k)

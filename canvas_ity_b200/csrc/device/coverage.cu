@@ -83,12 +83,45 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
     }
 }
 
+// A tile entry is "covered" when every scanline of the tile that lies on the canvas
+// has full coverage carried in from the left and no run inside the tile: the draw
+// paints all of it with coverage exactly 1.  The compositor uses this for occlusion
+// culling (an opaque covered draw makes everything beneath it irrelevant).
+__global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_target t)
+{
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    const uint32_t n_jobs = h->n_jobs;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n = h->n_tile_entries;
+    // one warp per tile entry, one lane per scanline; entry -> job by binary search on te_base
+    for (uint32_t te = warp; te < n; te += n_warps) {
+        uint32_t flags = f.te_flags[te];
+        if (!(flags & TE_NONEMPTY)) continue;
+        uint32_t lo = 0, hi = n_jobs;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (f.jobs[mid].te_base <= te) lo = mid; else hi = mid;
+        }
+        while (lo + 1 < n_jobs && f.jobs[lo].tw * f.jobs[lo].th == 0) ++lo;      // skip empty jobs sharing the base
+        const job_rec &jr = f.jobs[lo];
+        if (jr.kind != JOB_MAIN || !jr.opaque) continue;
+        uint32_t local = te - jr.te_base;
+        int ty = jr.ty0 + int(local / uint32_t(jr.tw));
+        int y = ty * kTile + lane;
+        bool on_canvas = y >= t.band_y0 && y < t.band_y0 + t.band_rows;
+        bool full = !on_canvas || (f.te_first[te * kTile + lane] == kNoRun && fabsf(f.te_backdrop[te * kTile + lane]) >= 1.0f);
+        if (__all_sync(0xffffffffu, full) && lane == 0) f.te_flags[te] = flags | TE_COVERED;
+    }
+}
+
 }  // namespace
 
 void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
 {
-    (void)t;
     k_rows<<<kGrid, kBlock, 0, s>>>(f, sorted_buffer);
+    k_tile_flags<<<kGrid, kBlock, 0, s>>>(f, t);
 }
 
 }  // namespace cb200

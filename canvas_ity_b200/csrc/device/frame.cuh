@@ -31,6 +31,7 @@ struct device_frame {
     uint2 *draw_src;                                   // per draw: first stroke source, count
     stroke_src *sources;   uint32_t n_static_sources;
     job_rec *jobs;
+    comp_rec *comp;                                    // per job, built by k_job_tiles
     float4 *texels;
     // geometry
     uint32_t *unit_count, *unit_offset;               // n_units + 1
@@ -39,6 +40,7 @@ struct device_frame {
     loop_span *loops;      uint32_t cap_loops;
     uint32_t *dash_pts_count, *dash_sub_count, *dash_tail, *dash_pts_off, *dash_sub_off;
     uint32_t *half_count, *half_offset;               // 2 per stroke source (+1)
+    uint32_t *half_unit_off, *half_dirty, *stroke_unit_pts;  uint32_t cap_stroke_units;
     uint32_t cap_sources;
     uint32_t stroke_loop_base;
     // raster

@@ -9,9 +9,11 @@
 //   K2  one thread per dashed source subpath: the dash phase walk is a serial
 //       recurrence in the reference (hpp:1858-1934) and is kept serial per subpath;
 //       subpaths run in parallel.
-//   K3  one thread per half stroke (source polyline x direction), same
-//       count/emit structure (add_half_stroke / stroke_lines, hpp:1949-2100).
-//       Round joins and caps call the K1 device routine for their arcs.
+//   K3  one thread per stroke unit (one join or one cap of one half stroke), same
+//       count/emit structure (add_half_stroke / stroke_lines, hpp:1949-2100); the
+//       reference's serial recurrence is only replayed (by one warp) for polylines
+//       that contain a segment shorter than 1e-4.  Round joins and caps call the K1
+//       device routine for their arcs.
 #include "frame.cuh"
 
 namespace cb200 {
@@ -273,63 +275,67 @@ __device__ __forceinline__ stroke_style style_of(const draw_rec &d)
     return st;
 }
 
-// One side of a polyline, walked from index `first` to `last` (either
-// direction) in user space; emits device-space outline points.
+// State carried along a half-stroke walk (hpp:1956-1958, 2019-2024): the last
+// accepted point (user space), the unit tangent and length of the segment that
+// arrived there.
+struct walk_state { vec2 pivot, tin; float lin; };
+
+// One step of the walk: the join at `ws.pivot` between the incoming segment and
+// pivot->nxt (hpp:1963-2024).  Returns true when a join was emitted.
 template <class Sink>
-__device__ void walk_half(const float2 *pts, uint32_t first, uint32_t last, bool closed,
-                          const stroke_style &st, Sink &sink)
+__device__ __forceinline__ bool join_step(walk_state &ws, vec2 nxt, const stroke_style &st, Sink &sink)
 {
     const float eps = 1.0e-4f;
-    vec2 tin = v2(0.0f, 0.0f);
-    float lin = 0.0f;
-    vec2 pivot = apply(st.inv, ld(pts, first));
-    uint32_t finish = first, i = first;
-    do {
-        vec2 nxt = apply(st.inv, ld(pts, i));
-        vec2 tout = unit(nxt - pivot);
-        float lout = vlen(nxt - pivot);
-        if (lin != 0.0f && lout >= eps) {
-            if (closed && finish == first) finish = i;
-            vec2 a = pivot + st.half * perp(tin);
-            vec2 b = pivot + st.half * perp(tout);
-            float turn = dot(perp(tin), tout);
-            if (fabsf(turn) < eps) turn = 0.0f;
-            vec2 tip = turn == 0.0f ? v2(0.0f, 0.0f) : (st.half / turn) * (tout - tin);
-            bool tight = dot(tip, tin) < -lin && dot(tip, tout) > lout;
-            bool wrap = turn > 0.0f && tight;        // inner join tighter than the segments
-            if (wrap) {
-                vec2 t = a; a = b; b = t;
-                t = tin; tin = tout; tout = t;
-                sink.put(apply(st.fwd, b));
-                sink.put(apply(st.fwd, pivot));
-                sink.put(apply(st.fwd, a));
-            }
-            if ((turn > 0.0f && !tight) ||
-                (turn != 0.0f && st.join == 0 && dot(tip, tip) <= st.miter2))
-                sink.put(apply(st.fwd, pivot + tip));
-            else if (st.join == 2) {
-                float cosine = dot(tin, tout);
-                float angle = acosf(fminf(fmaxf(cosine, -1.0f), 1.0f));
-                float k = 4.0f / 3.0f * tanf(0.25f * angle);
-                sink.put(apply(st.fwd, a));
-                flatten_cubic(apply(st.fwd, a), apply(st.fwd, a + (k * st.half) * tin),
-                              apply(st.fwd, b - (k * st.half) * tout), apply(st.fwd, b), -1.0f, sink);
-            } else {
-                sink.put(apply(st.fwd, a));
-                sink.put(apply(st.fwd, b));
-            }
-            if (wrap) {
-                sink.put(apply(st.fwd, b));
-                sink.put(apply(st.fwd, pivot));
-                sink.put(apply(st.fwd, a));
-                vec2 t = tin; tin = tout; tout = t;
-            }
+    vec2 tin = ws.tin, pivot = ws.pivot;
+    vec2 tout = unit(nxt - pivot);
+    float lout = vlen(nxt - pivot);
+    bool joined = false;
+    if (ws.lin != 0.0f && lout >= eps) {
+        joined = true;
+        vec2 a = pivot + st.half * perp(tin);
+        vec2 b = pivot + st.half * perp(tout);
+        float turn = dot(perp(tin), tout);
+        if (fabsf(turn) < eps) turn = 0.0f;
+        vec2 tip = turn == 0.0f ? v2(0.0f, 0.0f) : (st.half / turn) * (tout - tin);
+        bool tight = dot(tip, tin) < -ws.lin && dot(tip, tout) > lout;
+        bool wrap = turn > 0.0f && tight;            // inner join tighter than the segments
+        vec2 jin = tin, jout = tout;
+        if (wrap) {
+            vec2 t = a; a = b; b = t;
+            jin = tout; jout = tin;
+            sink.put(apply(st.fwd, b));
+            sink.put(apply(st.fwd, pivot));
+            sink.put(apply(st.fwd, a));
         }
-        if (lout >= eps) { tin = tout; lin = lout; pivot = nxt; }
-        i = i == last ? first : (last > first ? i + 1 : i - 1);
-    } while (i != finish);
-    if (closed || lin == 0.0f) return;
-    vec2 ahead = st.half * tin;
+        if ((turn > 0.0f && !tight) || (turn != 0.0f && st.join == 0 && dot(tip, tip) <= st.miter2))
+            sink.put(apply(st.fwd, pivot + tip));
+        else if (st.join == 2) {
+            float cosine = dot(jin, jout);
+            float angle = acosf(fminf(fmaxf(cosine, -1.0f), 1.0f));
+            float k = 4.0f / 3.0f * tanf(0.25f * angle);
+            sink.put(apply(st.fwd, a));
+            flatten_cubic(apply(st.fwd, a), apply(st.fwd, a + (k * st.half) * jin),
+                          apply(st.fwd, b - (k * st.half) * jout), apply(st.fwd, b), -1.0f, sink);
+        } else {
+            sink.put(apply(st.fwd, a));
+            sink.put(apply(st.fwd, b));
+        }
+        if (wrap) {
+            sink.put(apply(st.fwd, b));
+            sink.put(apply(st.fwd, pivot));
+            sink.put(apply(st.fwd, a));
+        }
+    }
+    if (lout >= eps) { ws.tin = tout; ws.lin = lout; ws.pivot = nxt; }
+    return joined;
+}
+
+// Line cap at the end of an open half (hpp:2029-2057).
+template <class Sink>
+__device__ __forceinline__ void cap_end(const walk_state &ws, const stroke_style &st, Sink &sink)
+{
+    vec2 pivot = ws.pivot;
+    vec2 ahead = st.half * ws.tin;
     vec2 side = perp(ahead);
     if (st.cap == 0) {                                   // butt
         sink.put(apply(st.fwd, pivot + side));
@@ -347,75 +353,372 @@ __device__ void walk_half(const float2 *pts, uint32_t first, uint32_t last, bool
     }
 }
 
-template <class Sink>
-__device__ __forceinline__ void stroke_half(const device_frame &f, uint32_t h, Sink &sink)
+// One half stroke by one WARP.  The reference walks the polyline serially, but
+// the state it carries is a pure function of the two preceding points whenever no
+// segment shorter than 1e-4 is skipped -- the overwhelmingly common case.  So 32
+// consecutive steps are evaluated by 32 lanes, each rebuilding its own state from
+// the points, and a warp scan orders their output; a chunk that does contain a
+// skipped (degenerate) segment is replayed serially by lane 0 with the exact
+// reference recurrence.  EMIT selects count-only or write mode.
+template <bool EMIT>
+__device__ uint32_t warp_half(const device_frame &f, uint32_t h, uint32_t out_base, uint32_t loop_id)
 {
+    const int lane = threadIdx.x & 31;
     stroke_src src = f.sources[h >> 1];
     loop_span l = f.loops[src.loop];
-    if (l.count < 2) return;
+    if (l.count < 2) return 0;
     const draw_rec &d = f.draws[src.draw_closed & 0x7fffffffu];
-    bool closed = (src.draw_closed >> 31) != 0;
-    stroke_style st = style_of(d);
-    if (h & 1) walk_half(f.pts, l.first + l.count - 1, l.first, closed, st, sink);
-    else walk_half(f.pts, l.first, l.first + l.count - 1, closed, st, sink);
+    const bool closed = (src.draw_closed >> 31) != 0;
+    const stroke_style st = style_of(d);
+    const bool backwards = (h & 1) != 0;
+    const uint32_t origin = backwards ? l.first + l.count - 1 : l.first;
+    const uint32_t count = l.count;
+    const float eps = 1.0e-4f;
+    auto point_at = [&](uint32_t step) -> vec2 {       // user-space point visited at `step`
+        uint32_t k = step % count;
+        return apply(st.inv, ld(f.pts, backwards ? origin - k : origin + k));
+    };
+    walk_state ws;
+    ws.pivot = point_at(0);
+    ws.tin = v2(0.0f, 0.0f);
+    ws.lin = 0.0f;
+    uint32_t total_steps = count;                        // grows by `sf` once a closed walk finds its first join
+    uint32_t first_join = 0xffffffffu;
+    uint32_t emitted = 0;
+    uint32_t base = 1;                                   // step 0 revisits the start point: a no-op
+    while (base < total_steps) {
+        const uint32_t limit = total_steps;              // steps known when this chunk starts
+        const uint32_t chunk = min(32u, limit - base);
+        uint32_t s = base + uint32_t(lane);
+        bool valid = s < limit;
+        vec2 q = valid ? point_at(s) : v2(0.0f, 0.0f);
+        vec2 prev = v2(__shfl_up_sync(0xffffffffu, q.x, 1), __shfl_up_sync(0xffffffffu, q.y, 1));
+        vec2 prev2 = v2(__shfl_up_sync(0xffffffffu, q.x, 2), __shfl_up_sync(0xffffffffu, q.y, 2));
+        if (lane == 0) prev = ws.pivot;
+        if (lane == 1) prev2 = ws.pivot;
+        bool accepted = !valid || vlen(q - prev) >= eps;
+        bool fast = __all_sync(0xffffffffu, accepted);
+        if (fast) {
+            walk_state mine;
+            mine.pivot = prev;
+            if (lane == 0) { mine.tin = ws.tin; mine.lin = ws.lin; }
+            else { mine.tin = unit(prev - prev2); mine.lin = vlen(prev - prev2); }
+            uint32_t n = 0;
+            bool joined = false;
+            if (valid) {
+                count_sink cs = { 0 };
+                walk_state probe = mine;
+                joined = join_step(probe, q, st, cs);
+                n = uint32_t(cs.n);
+            }
+            uint32_t incl = warp_inclusive_scan(n);
+            if (EMIT && valid && n) {
+                point_sink ps = { f.pts, f.pt_loop, out_base + emitted + incl - n, loop_id };
+                walk_state again = mine;
+                join_step(again, q, st, ps);
+            }
+            emitted += __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t jm = __ballot_sync(0xffffffffu, joined);
+            if (closed && first_join == 0xffffffffu && jm) {
+                first_join = base + uint32_t(__ffs(int(jm)) - 1);
+                total_steps = count + first_join;
+            }
+            // carry the state of the last valid step to the next chunk
+            uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            int last = 31 - __clz(int(vm));
+            vec2 lp = v2(__shfl_sync(0xffffffffu, q.x, last), __shfl_sync(0xffffffffu, q.y, last));
+            vec2 lprev = v2(__shfl_sync(0xffffffffu, prev.x, last), __shfl_sync(0xffffffffu, prev.y, last));
+            ws.pivot = lp;
+            ws.tin = unit(lp - lprev);
+            ws.lin = vlen(lp - lprev);
+            base += chunk;
+        } else {
+            // exact serial replay of this chunk by lane 0
+            uint32_t n_chunk = 0, fj = first_join, ts = total_steps;
+            if (lane == 0) {
+                for (uint32_t k = 0; k < chunk; ++k) {
+                    vec2 nxt = point_at(base + k);
+                    bool joined;
+                    if (EMIT) {
+                        point_sink ps = { f.pts, f.pt_loop, out_base + emitted + n_chunk, loop_id };
+                        joined = join_step(ws, nxt, st, ps);
+                        n_chunk = ps.at - (out_base + emitted);
+                    } else {
+                        count_sink cs = { 0 };
+                        joined = join_step(ws, nxt, st, cs);
+                        n_chunk += uint32_t(cs.n);
+                    }
+                    if (joined && closed && fj == 0xffffffffu) { fj = base + k; ts = count + fj; }
+                }
+            }
+            emitted += __shfl_sync(0xffffffffu, n_chunk, 0);
+            first_join = __shfl_sync(0xffffffffu, fj, 0);
+            total_steps = __shfl_sync(0xffffffffu, ts, 0);
+            ws.pivot = v2(__shfl_sync(0xffffffffu, ws.pivot.x, 0), __shfl_sync(0xffffffffu, ws.pivot.y, 0));
+            ws.tin = v2(__shfl_sync(0xffffffffu, ws.tin.x, 0), __shfl_sync(0xffffffffu, ws.tin.y, 0));
+            ws.lin = __shfl_sync(0xffffffffu, ws.lin, 0);
+            base += chunk;
+        }
+    }
+    if (!closed && ws.lin != 0.0f) {
+        uint32_t n_cap = 0;
+        if (lane == 0) {
+            if (EMIT) {
+                point_sink ps = { f.pts, f.pt_loop, out_base + emitted, loop_id };
+                cap_end(ws, st, ps);
+                n_cap = ps.at - (out_base + emitted);
+            } else {
+                count_sink cs = { 0 };
+                cap_end(ws, st, cs);
+                n_cap = uint32_t(cs.n);
+            }
+        }
+        emitted += __shfl_sync(0xffffffffu, n_cap, 0);
+    }
+    return emitted;
 }
 
-__global__ void __launch_bounds__(kBlock) k_stroke_count(device_frame f)
+constexpr int kWarps = kBlock / 32;
+
+// ---- unit-parallel stroking ---------------------------------------------------
+// When no segment of a polyline is shorter than 1e-4 (a "clean" half), the walk
+// state before step s is (V(s-1), V(s-1) - V(s-2)): every join and the final cap
+// are independent work items ("stroke units").  Units are evaluated one per
+// thread with the usual count -> scan -> emit passes; a half that turns out to
+// contain a degenerate segment is flagged dirty by the unit that sees it and is
+// re-done exactly (serial recurrence) by warp_half in the fallback kernels.
+
+struct half_view {
+    uint32_t origin, count;          // first visited point index / number of polyline points
+    bool backwards, closed, dup;     // dup: closed polyline whose last point repeats its first
+    uint32_t joins, units;
+};
+
+__device__ __forceinline__ half_view view_half(const device_frame &f, uint32_t h, stroke_style &st)
+{
+    half_view v;
+    stroke_src src = f.sources[h >> 1];
+    loop_span l = f.loops[src.loop];
+    st = style_of(f.draws[src.draw_closed & 0x7fffffffu]);
+    v.closed = (src.draw_closed >> 31) != 0;
+    v.backwards = (h & 1) != 0;
+    v.count = l.count;
+    v.origin = v.backwards ? l.first + l.count - 1 : l.first;
+    v.dup = false;
+    v.joins = 0;
+    if (l.count >= 2) {
+        if (v.closed) {
+            vec2 a = apply(st.inv, ld(f.pts, l.first)), b = apply(st.inv, ld(f.pts, l.first + l.count - 1));
+            v.dup = vlen(a - b) < 1.0e-4f;
+            v.joins = v.dup ? l.count - 1 : l.count;
+        } else
+            v.joins = l.count - 2;
+    }
+    // every half owns at least one unit so that its output offset is always defined
+    v.units = l.count >= 2 ? v.joins + (v.closed ? 0u : 1u) : 0u;
+    if (v.units == 0) v.units = 1;
+    return v;
+}
+
+// k-th point of the visit sequence V (user space)
+__device__ __forceinline__ vec2 visit(const device_frame &f, const half_view &v, const stroke_style &st, uint32_t k)
+{
+    uint32_t i = k < v.count ? k : (v.dup ? k - v.count + 1 : k - v.count);
+    return apply(st.inv, ld(f.pts, v.backwards ? v.origin - i : v.origin + i));
+}
+
+// Unit u of a half: joins are units 0 .. joins-1 (step s = u + 2), the cap follows.
+template <class Sink>
+__device__ __forceinline__ bool stroke_unit(const device_frame &f, const half_view &v, const stroke_style &st,
+                                            uint32_t u, Sink &sink)
+{
+    const float eps = 1.0e-4f;
+    if (v.count < 2) return true;
+    walk_state ws;
+    if (u < v.joins) {
+        uint32_t s = u + 2;
+        vec2 p2 = visit(f, v, st, s - 2), p1 = visit(f, v, st, s - 1), p0 = visit(f, v, st, s);
+        ws.pivot = p1;
+        ws.tin = unit(p1 - p2);
+        ws.lin = vlen(p1 - p2);
+        bool clean = vlen(p0 - p1) >= eps && (u != 0 || ws.lin >= eps);
+        if (!clean) return false;
+        join_step(ws, p0, st, sink);
+        return true;
+    }
+    // cap of an open half
+    vec2 p2 = visit(f, v, st, v.count - 2), p1 = visit(f, v, st, v.count - 1);
+    ws.pivot = p1;
+    ws.tin = unit(p1 - p2);
+    ws.lin = vlen(p1 - p2);
+    if (v.count == 2 && ws.lin < eps) return false;      // no join unit would have caught it
+    cap_end(ws, st, sink);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t n_halves(const device_frame &f)
+{
+    return 2 * (f.n_dash_items ? f.hdr->n_sources : f.n_static_sources);
+}
+
+// units per half + in-kernel partial scan; total to hdr->n_stroke_units
+__global__ void __launch_bounds__(kBlock) k_stroke_plan(device_frame f)
 {
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
-    uint32_t n = 2 * (f.n_dash_items ? hd->n_sources : f.n_static_sources), begin, end, ipt;
+    uint32_t n = hd->overflow ? 0 : n_halves(f), begin, end, ipt;
     block_slice(n, begin, end, ipt);
     uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    bool bad = hd->overflow != 0;
-    for (uint32_t k = 0; k < ipt && !bad; ++k) {
-        uint32_t h = first + k;
-        if (h >= end) break;
-        count_sink cs = { 0 };
-        stroke_half(f, h, cs);
-        f.half_count[h] = uint32_t(cs.n);
-        sum += uint32_t(cs.n);
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
+        stroke_style st;
+        half_view v = view_half(f, first + k, st);
+        f.half_count[first + k] = v.units;
+        f.half_dirty[first + k] = 0;
+        sum += v.units;
     }
     uint32_t total;
     block_exclusive_scan(sum, sm, total);
     if (threadIdx.x == 0) f.partials[3 * kGrid + blockIdx.x] = total;
-    finish_partials(f.partials + 3 * kGrid, &hd->tickets[3], &hd->n_stroke_points, sm);
+    finish_partials(f.partials + 3 * kGrid, &hd->tickets[3], &hd->n_stroke_units, sm);
 }
 
-__global__ void __launch_bounds__(kBlock) k_stroke_emit(device_frame f)
+// half_count (units per half) -> half_unit_off (exclusive), same slices as k_stroke_plan
+__global__ void __launch_bounds__(kBlock) k_stroke_plan_apply(device_frame f)
 {
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
-    uint32_t n_src = f.n_dash_items ? hd->n_sources : f.n_static_sources;
-    uint32_t n = 2 * n_src, begin, end, ipt;
+    uint32_t n = hd->overflow ? 0 : n_halves(f), begin, end, ipt;
     block_slice(n, begin, end, ipt);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hd->n_stroke_units > f.cap_stroke_units) atomicOr(&hd->overflow, OVF_POINTS);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.half_count[first + k];
+    uint32_t total;
+    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[3 * kGrid + blockIdx.x];
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
+        f.half_unit_off[first + k] = at;
+        at += f.half_count[first + k];
+        if (first + k == n - 1) f.half_unit_off[n] = at;
+    }
+}
+
+__device__ __forceinline__ uint32_t find_half(const uint32_t *off, uint32_t n, uint32_t unit)
+{
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= unit) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// points per unit; dirty halves are flagged
+__global__ void __launch_bounds__(kBlock) k_stroke_unit_count(device_frame f)
+{
+    frame_header *hd = f.hdr;
+    uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t nh = n_halves(f);
+    uint32_t first = begin + threadIdx.x * ipt;
+    if (first >= end) return;
+    uint32_t h = find_half(f.half_unit_off, nh, first);
+    stroke_style st;
+    half_view v = view_half(f, h, st);
+    for (uint32_t k = 0; k < ipt; ++k) {
+        uint32_t u = first + k;
+        if (u >= end) break;
+        while (u >= f.half_unit_off[h + 1]) { ++h; v = view_half(f, h, st); }
+        count_sink cs = { 0 };
+        if (!stroke_unit(f, v, st, u - f.half_unit_off[h], cs)) { f.half_dirty[h] = 1; cs.n = 0; }
+        f.stroke_unit_pts[u] = uint32_t(cs.n);
+    }
+}
+
+// exact serial redo of dirty halves: all their points are booked on their first unit
+__global__ void __launch_bounds__(kBlock) k_stroke_fallback_count(device_frame f)
+{
+    frame_header *hd = f.hdr;
+    if (hd->overflow) return;
+    uint32_t nh = n_halves(f);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = warp; h < nh; h += n_warps) {
+        if (!f.half_dirty[h]) continue;
+        uint32_t c = warp_half<false>(f, h, 0, 0);
+        uint32_t u0 = f.half_unit_off[h], u1 = f.half_unit_off[h + 1];
+        for (uint32_t u = u0 + lane; u < u1; u += 32) f.stroke_unit_pts[u] = u == u0 ? c : 0;
+    }
+}
+
+// block sums of stroke_unit_pts -> partials -> total stroke points
+__global__ void __launch_bounds__(kBlock) k_stroke_unit_sums(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *hd = f.hdr;
+    uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.stroke_unit_pts[first + k];
+    uint32_t total;
+    block_exclusive_scan(sum, sm, total);
+    if (threadIdx.x == 0) f.partials[6 * kGrid + blockIdx.x] = total;
+    finish_partials(f.partials + 6 * kGrid, &hd->tickets[7], &hd->n_stroke_points, sm);
+}
+
+__global__ void __launch_bounds__(kBlock) k_stroke_unit_emit(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    frame_header *hd = f.hdr;
     uint32_t base = hd->n_line_points + hd->n_dash_points;
     if (base + hd->n_stroke_points > f.cap_pts) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&hd->overflow, OVF_POINTS);
         return;
     }
-    if (hd->overflow) return;
+    uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t nh = n_halves(f);
     uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.half_count[first + k];
+    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.stroke_unit_pts[first + k];
     uint32_t total;
-    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[3 * kGrid + blockIdx.x];
+    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[6 * kGrid + blockIdx.x];
+    if (first >= end) return;
+    uint32_t h = find_half(f.half_unit_off, nh, first);
+    stroke_style st;
+    half_view v = view_half(f, h, st);
     for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t h = first + k;
-        if (h >= end) break;
-        f.half_offset[h] = at;
+        uint32_t u = first + k;
+        if (u >= end) break;
+        while (u >= f.half_unit_off[h + 1]) { ++h; v = view_half(f, h, st); }
+        if (u == f.half_unit_off[h]) f.half_offset[h] = at;           // where this half's output starts
+        if (u == n - 1) f.half_offset[nh] = at + f.stroke_unit_pts[u];
+        if (!f.half_dirty[h]) {
+            // closed source: each half is its own loop; open: both halves form one loop
+            uint32_t loop_id = f.stroke_loop_base + (v.closed ? h : (h & ~1u));
+            point_sink ps = { f.pts, f.pt_loop, base + at, loop_id };
+            stroke_unit(f, v, st, u - f.half_unit_off[h], ps);
+        }
+        at += f.stroke_unit_pts[u];
+    }
+}
+
+// dirty halves written serially; loop table for all halves
+__global__ void __launch_bounds__(kBlock) k_stroke_finish(device_frame f)
+{
+    frame_header *hd = f.hdr;
+    if (hd->overflow) return;
+    uint32_t nh = n_halves(f);
+    uint32_t base = hd->n_line_points + hd->n_dash_points;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = warp; h < nh; h += n_warps) {
         bool closed = (f.sources[h >> 1].draw_closed >> 31) != 0;
-        uint32_t count = f.half_count[h];
-        // closed source: each half is its own loop; open: both halves form one loop
-        uint32_t loop_id = f.stroke_loop_base + (closed ? h : (h & ~1u));
-        point_sink ps = { f.pts, f.pt_loop, base + at, loop_id };
-        stroke_half(f, h, ps);
-        loop_span l;
-        if (closed) { l.first = base + at; l.count = count; }
-        else if ((h & 1) == 0) { l.first = base + at; l.count = count + f.half_count[h + 1]; }
-        else { l.first = base + at; l.count = 0; }
-        f.loops[f.stroke_loop_base + h] = l;
-        at += count;
-        if (h == n - 1) f.half_offset[n] = at;
+        uint32_t at = f.half_offset[h], count = f.half_offset[h + 1] - at;
+        if (f.half_dirty[h]) warp_half<true>(f, h, base + at, f.stroke_loop_base + (closed ? h : (h & ~1u)));
+        if (lane == 0) {
+            loop_span l;
+            l.first = base + at;
+            l.count = closed ? count : ((h & 1) == 0 ? f.half_offset[h + 2] - at : 0);
+            f.loops[f.stroke_loop_base + h] = l;
+        }
     }
 }
 
@@ -439,8 +742,13 @@ void launch_dash(const device_frame &f, cudaStream_t s)
 void launch_stroke(const device_frame &f, cudaStream_t s)
 {
     if (!f.n_static_sources && !f.n_dash_items) return;
-    k_stroke_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_emit<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_plan<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_plan_apply<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_unit_count<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_fallback_count<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_unit_sums<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_unit_emit<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_finish<<<kGrid, kBlock, 0, s>>>(f);
 }
 
 }  // namespace cb200

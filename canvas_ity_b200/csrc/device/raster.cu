@@ -400,8 +400,38 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
         uint32_t ex = block_exclusive_scan(tiles, sm, total);
         if (j < n) f.jobs[j].te_base = carry + ex;
         carry += total;
+        if (j < n) {                                      // compact record for the tile compositor
+            const job_rec &jr = f.jobs[j];
+            const draw_rec &d = f.draws[jr.draw];
+            comp_rec c;
+            memset(&c, 0, sizeof c);
+            c.kind = jr.kind; c.op = d.op;
+            bool everywhere = jr.kind == JOB_CLIP || (jr.kind == JOB_MAIN && (~d.op & 8u));
+            c.flags = (everywhere ? COMP_EVERYWHERE : 0u) | (jr.opaque ? COMP_OPAQUE : 0u);
+            c.mask_src = d.mask_src; c.mask_dst = d.mask_dst; c.brush = d.brush; c.draw = jr.draw;
+            c.te_base = jr.te_base;
+            c.tx0 = jr.tx0; c.ty0 = jr.ty0; c.tw = jr.tw; c.th = jr.th;
+            c.cx0 = jr.cx0; c.cy0 = jr.cy0; c.cx1 = jr.cx1; c.cy1 = jr.cy1;
+            c.alpha = d.global_alpha;
+            if (jr.kind == JOB_SHADOW) {
+                for (int k = 0; k < 4; ++k) c.color[k] = d.shadow_color[k];
+                c.border = jr.border; c.left = jr.left; c.top = jr.top; c.bw = jr.bw;
+            } else if (jr.kind == JOB_MAIN) {
+                const brush_rec &b = f.brushes[d.brush];
+                c.brush_type = b.n_colors ? b.type : 0xffu;     // 0xff: empty brush paints nothing
+                if (b.type == CB200_BRUSH_COLOR && b.n_colors) {
+                    float4 col = f.colors[b.first_color];
+                    c.color[0] = col.x; c.color[1] = col.y; c.color[2] = col.z; c.color[3] = col.w;
+                }
+            }
+            f.comp[j] = c;
+        }
         // plane storage: order of allocation does not matter, only disjointness
-        if (plane) f.jobs[j].plane_offset = atomicAdd(&plane_carry, plane);
+        if (plane) {
+            unsigned long long off = atomicAdd(&plane_carry, plane);
+            f.jobs[j].plane_offset = off;
+            f.comp[j].plane_lo = uint32_t(off); f.comp[j].plane_hi = uint32_t(off >> 32);
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0) {

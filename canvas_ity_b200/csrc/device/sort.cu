@@ -3,10 +3,10 @@
 // among runs on the same pixel is irrelevant to the summed coverage).
 //
 // 8-bit digits; only ceil(key_bits / 8) passes run, the host knows key_bits from
-// the canvas size and the job count.  Per pass, two launches with fixed grids
+// the canvas size and the job count.  Per pass, three launches with fixed grids
 // (the run count lives on the device):
-//   k_sort_hist     per-CTA digit histogram of its slice; the last CTA to finish
-//                   turns the kGrid x 256 table into global bases (digit-major)
+//   k_sort_hist     per-CTA digit histogram of its slice (digit-major table)
+//   k_sort_scan     one CTA per digit: exclusive scan across the CTAs + digit total
 //   k_sort_scatter  each CTA re-reads its slice in order, 256 keys per step;
 //                   ranks are made stable with warp match + per-warp digit counts
 #include "frame.cuh"
@@ -29,8 +29,6 @@ __device__ __forceinline__ void sort_slice(uint32_t n, uint32_t &begin, uint32_t
 __global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, int shift)
 {
     __shared__ uint32_t bins[kRadix];
-    __shared__ uint32_t sm[33];
-    __shared__ bool last;
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
     sort_slice(n, begin, end);
@@ -40,23 +38,24 @@ __global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, i
     for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock)
         atomicAdd(&bins[uint32_t(keys[i] >> shift) & 0xffu], 1u);
     __syncthreads();
-    f.sort_hist[threadIdx.x * kGrid + blockIdx.x] = bins[threadIdx.x];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&h->tickets[6], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    // exclusive scan of the digit-major table: digit 0 of every CTA, digit 1, ...
-    const uint32_t total_entries = kRadix * kGrid;
-    const uint32_t per = (total_entries + kBlock - 1) / kBlock;
-    uint32_t lo = threadIdx.x * per, hi = min(lo + per, total_entries), sum = 0;
-    volatile uint32_t *tab = f.sort_hist;
-    for (uint32_t i = lo; i < hi; ++i) sum += tab[i];
-    uint32_t tot;
-    uint32_t at = block_exclusive_scan(sum, sm, tot);
-    for (uint32_t i = lo; i < hi; ++i) { uint32_t v = tab[i]; tab[i] = at; at += v; }
-    if (threadIdx.x == 0) h->tickets[6] = 0;
+    f.sort_hist[threadIdx.x * kGrid + blockIdx.x] = bins[threadIdx.x];     // digit-major
+}
+
+// One CTA per digit: exclusive scan of that digit's per-CTA counts (coalesced),
+// digit total to sort_hist[kRadix * kGrid + digit].
+__global__ void __launch_bounds__(kBlock) k_sort_scan(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t *row = f.sort_hist + blockIdx.x * kGrid;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < kGrid; base += kBlock) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < kGrid ? row[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, sm, total);
+        if (i < kGrid) row[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) f.sort_hist[kRadix * kGrid + blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift)
@@ -66,8 +65,13 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
     sort_slice(n, begin, end);
+    __shared__ uint32_t sm[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = f.sort_hist[threadIdx.x * kGrid + blockIdx.x];
+    {   // global base of digit d = keys with a smaller digit + this digit's keys in earlier CTAs
+        uint32_t total;
+        uint32_t below = block_exclusive_scan(f.sort_hist[kRadix * kGrid + threadIdx.x], sm, total);
+        base[threadIdx.x] = below + f.sort_hist[threadIdx.x * kGrid + blockIdx.x];
+    }
     for (int w = 0; w < kBlock / 32; ++w) warp_count[w][threadIdx.x] = 0;
     __syncthreads();
     const uint64_t *kin = f.keys[src];
@@ -121,6 +125,7 @@ void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *resul
     int src = 0;
     for (int p = 0; p < passes; ++p) {
         k_sort_hist<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
+        k_sort_scan<<<kRadix, kBlock, 0, s>>>(f);
         k_sort_scatter<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
         src ^= 1;
     }

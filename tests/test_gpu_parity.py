@@ -87,7 +87,8 @@ def test_full_size_properties_4096(lib):
     a = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
     b = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
     assert np.array_equal(a, b)
-    assert a[..., 3].min() == 255           # the tiger's first draw paints the whole canvas opaque
+    # the tiger's first draw paints its 733:757 page opaque; the side margins stay transparent
+    assert a[:, 100:3990, 3].min() == 255 and a[:, :60].max() == 0 and a[:, 4040:].max() == 0
     y0, rows = 1500, 300
     h = lib.cv_create_band(size, size, 0, y0, rows)
     try:
