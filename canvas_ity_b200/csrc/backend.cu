@@ -104,7 +104,7 @@ struct cb200_canvas {
 
     // device work buffers
     dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
-        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
+        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
         te_first, partials, sort_hist;
     dev_buf<float2> pts;
     dev_buf<loop_span> loops;
@@ -113,7 +113,7 @@ struct cb200_canvas {
     dev_buf<comp_rec> comp;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
-    dev_buf<uint8_t> rgba8;
+    dev_buf<uint8_t> rgba8, visit_close;
     uint8_t *pinned_rgba8 = nullptr;
     size_t pinned_rgba8_cap = 0;
 
@@ -340,7 +340,10 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->half_offset.reserve(2 * size_t(want_sources) + 4));
     CK(cv->half_unit_off.reserve(2 * size_t(want_sources) + 4));
     CK(cv->half_dirty.reserve(2 * size_t(want_sources) + 4));
-    CK(cv->stroke_unit_pts.reserve(size_t(want_pts) + 2 * size_t(want_sources) + 4));
+    CK(cv->stroke_unit_pts.reserve(size_t(want_pts) + 6 * size_t(want_sources) + 4));
+    CK(cv->visit_prev.reserve(size_t(want_pts) + 6 * size_t(want_sources) + 4));
+    CK(cv->visit_close.reserve(size_t(want_pts) + 6 * size_t(want_sources) + 4));
+    CK(cv->half_last.reserve(2 * size_t(want_sources) + 4));
     CK(cv->loops.reserve(sf.subpaths.size() + want_dash_sub + 2 * size_t(want_sources) + 2));
     CK(cv->pieces.reserve(3 * size_t(want_items)));
     CK(cv->piece_job.reserve(3 * size_t(want_items)));
@@ -469,6 +472,7 @@ int upload_frame(cb200_canvas *cv)
     f.dash_pts_count = cv->dash_pts_count.p; f.dash_sub_count = cv->dash_sub_count.p; f.dash_tail = cv->dash_tail.p;
     f.half_count = cv->half_count.p; f.half_offset = cv->half_offset.p;
     f.half_unit_off = cv->half_unit_off.p; f.half_dirty = cv->half_dirty.p; f.stroke_unit_pts = cv->stroke_unit_pts.p;
+    f.half_last = cv->half_last.p; f.visit_prev = cv->visit_prev.p; f.visit_close = cv->visit_close.p;
     f.cap_stroke_units = uint32_t(cv->stroke_unit_pts.cap);
     f.cap_sources = cv->cap_sources;
     f.stroke_loop_base = uint32_t(sf.subpaths.size()) + cv->cap_dash_subpaths;
@@ -521,7 +525,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
-                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 7) + 7 + 3 * ((sf.key_bits + 7) / 8) + 2 +
+                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * ((sf.key_bits + 7) / 8) + 2 +
                     (sf.shadow_jobs.empty() ? 0 : 7) + 1;
     cv->pending = true;
     CK(cudaGetLastError());
@@ -651,7 +655,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
     cv->unit_count.release(); cv->unit_offset.release(); cv->pt_loop.release();
     cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
-    cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->piece_job.release();
+    cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->half_last.release(); cv->visit_prev.release(); cv->visit_close.release(); cv->piece_job.release();
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->te_flags.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();

@@ -41,6 +41,7 @@ struct device_frame {
     uint32_t *dash_pts_count, *dash_sub_count, *dash_tail, *dash_pts_off, *dash_sub_off;
     uint32_t *half_count, *half_offset;               // 2 per stroke source (+1)
     uint32_t *half_unit_off, *half_dirty, *stroke_unit_pts;  uint32_t cap_stroke_units;
+    uint32_t *half_last, *visit_prev;  uint8_t *visit_close;
     uint32_t cap_sources;
     uint32_t stroke_loop_base;
     // raster

@@ -481,17 +481,26 @@ __device__ uint32_t warp_half(const device_frame &f, uint32_t h, uint32_t out_ba
 constexpr int kWarps = kBlock / 32;
 
 // ---- unit-parallel stroking ---------------------------------------------------
-// When no segment of a polyline is shorter than 1e-4 (a "clean" half), the walk
-// state before step s is (V(s-1), V(s-1) - V(s-2)): every join and the final cap
-// are independent work items ("stroke units").  Units are evaluated one per
-// thread with the usual count -> scan -> emit passes; a half that turns out to
-// contain a degenerate segment is flagged dirty by the unit that sees it and is
-// re-done exactly (serial recurrence) by warp_half in the fallback kernels.
+// The reference walks each polyline serially, but its state before visiting point
+// k is just (last accepted point, the accepted point before that): a greedy filter
+// that skips points closer than 1e-4 to the last accepted one.  Almost everywhere
+// that filter accepts every point, so:
+//   k_stroke_visits   (thread per visited point) marks points that are too close to
+//                     their predecessor and writes the default link prev[k] = k - 1;
+//   k_stroke_resolve  (warp per half) skims the marks 128 at a time and replays the
+//                     greedy filter serially only across marked stretches, fixing
+//                     the links there;
+//   every join prev[prev[k]] -> prev[k] -> k and every cap is then an independent
+//   unit: count -> scan -> emit, one thread each.
+// A closed polyline is visited count + 2 times (the walk runs on to its first join).
+// The rare walks where that is not true (fewer than two accepted points, or the
+// first join not at the second point) go to the exact serial warp_half instead.
+
+constexpr uint32_t kNoLink = 0xffffffffu;
 
 struct half_view {
-    uint32_t origin, count;          // first visited point index / number of polyline points
-    bool backwards, closed, dup;     // dup: closed polyline whose last point repeats its first
-    uint32_t joins, units;
+    uint32_t origin, count, visits, units;
+    bool backwards, closed;
 };
 
 __device__ __forceinline__ half_view view_half(const device_frame &f, uint32_t h, stroke_style &st)
@@ -504,56 +513,18 @@ __device__ __forceinline__ half_view view_half(const device_frame &f, uint32_t h
     v.backwards = (h & 1) != 0;
     v.count = l.count;
     v.origin = v.backwards ? l.first + l.count - 1 : l.first;
-    v.dup = false;
-    v.joins = 0;
-    if (l.count >= 2) {
-        if (v.closed) {
-            vec2 a = apply(st.inv, ld(f.pts, l.first)), b = apply(st.inv, ld(f.pts, l.first + l.count - 1));
-            v.dup = vlen(a - b) < 1.0e-4f;
-            v.joins = v.dup ? l.count - 1 : l.count;
-        } else
-            v.joins = l.count - 2;
-    }
+    v.visits = l.count < 2 ? 0u : (v.closed ? l.count + 2 : l.count);
+    // units: unit i < visits - 1 is the join made on visit i + 1, the last unit is the cap slot;
     // every half owns at least one unit so that its output offset is always defined
-    v.units = l.count >= 2 ? v.joins + (v.closed ? 0u : 1u) : 0u;
-    if (v.units == 0) v.units = 1;
+    v.units = v.visits ? v.visits : 1u;
     return v;
 }
 
-// k-th point of the visit sequence V (user space)
+// k-th visited point in user space
 __device__ __forceinline__ vec2 visit(const device_frame &f, const half_view &v, const stroke_style &st, uint32_t k)
 {
-    uint32_t i = k < v.count ? k : (v.dup ? k - v.count + 1 : k - v.count);
+    uint32_t i = k < v.count ? k : k - v.count;
     return apply(st.inv, ld(f.pts, v.backwards ? v.origin - i : v.origin + i));
-}
-
-// Unit u of a half: joins are units 0 .. joins-1 (step s = u + 2), the cap follows.
-template <class Sink>
-__device__ __forceinline__ bool stroke_unit(const device_frame &f, const half_view &v, const stroke_style &st,
-                                            uint32_t u, Sink &sink)
-{
-    const float eps = 1.0e-4f;
-    if (v.count < 2) return true;
-    walk_state ws;
-    if (u < v.joins) {
-        uint32_t s = u + 2;
-        vec2 p2 = visit(f, v, st, s - 2), p1 = visit(f, v, st, s - 1), p0 = visit(f, v, st, s);
-        ws.pivot = p1;
-        ws.tin = unit(p1 - p2);
-        ws.lin = vlen(p1 - p2);
-        bool clean = vlen(p0 - p1) >= eps && (u != 0 || ws.lin >= eps);
-        if (!clean) return false;
-        join_step(ws, p0, st, sink);
-        return true;
-    }
-    // cap of an open half
-    vec2 p2 = visit(f, v, st, v.count - 2), p1 = visit(f, v, st, v.count - 1);
-    ws.pivot = p1;
-    ws.tin = unit(p1 - p2);
-    ws.lin = vlen(p1 - p2);
-    if (v.count == 2 && ws.lin < eps) return false;      // no join unit would have caught it
-    cap_end(ws, st, sink);
-    return true;
 }
 
 __device__ __forceinline__ uint32_t n_halves(const device_frame &f)
@@ -611,7 +582,111 @@ __device__ __forceinline__ uint32_t find_half(const uint32_t *off, uint32_t n, u
     return lo;
 }
 
-// points per unit; dirty halves are flagged
+// thread per visit: too-close mark and default link
+__global__ void __launch_bounds__(kBlock) k_stroke_visits(device_frame f)
+{
+    frame_header *hd = f.hdr;
+    uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
+    block_slice(n, begin, end, ipt);
+    uint32_t nh = n_halves(f);
+    uint32_t first = begin + threadIdx.x * ipt;
+    if (first >= end) return;
+    uint32_t h = find_half(f.half_unit_off, nh, first);
+    stroke_style st;
+    half_view v = view_half(f, h, st);
+    for (uint32_t i = 0; i < ipt; ++i) {
+        uint32_t u = first + i;
+        if (u >= end) break;
+        while (u >= f.half_unit_off[h + 1]) { ++h; v = view_half(f, h, st); }
+        uint32_t k = u - f.half_unit_off[h];
+        bool close = false;
+        if (k >= 1 && k < v.visits) close = vlen(visit(f, v, st, k) - visit(f, v, st, k - 1)) < 1.0e-4f;
+        f.visit_close[u] = close ? 1 : 0;
+        f.visit_prev[u] = k ? k - 1 : kNoLink;
+    }
+}
+
+// warp per half: replay the greedy filter across marked stretches only
+__global__ void __launch_bounds__(kBlock) k_stroke_resolve(device_frame f)
+{
+    frame_header *hd = f.hdr;
+    if (hd->overflow) return;
+    uint32_t nh = n_halves(f);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = warp; h < nh; h += n_warps) {
+        stroke_style st;
+        half_view v = view_half(f, h, st);
+        if (!v.visits) { if (lane == 0) f.half_last[h] = 0; continue; }
+        const uint32_t off = f.half_unit_off[h];
+        uint32_t pivot = 0, accepted = 0, second = kNoLink;     // second: visit of the 2nd acceptance
+        bool in_sync = true;
+        for (uint32_t base = 1; base < v.visits; base += 128) {
+            uint32_t marks = 0;
+#pragma unroll
+            for (uint32_t m = 0; m < 4; ++m) {
+                uint32_t k = base + 4 * lane + m;
+                if (k < v.visits && f.visit_close[off + k]) marks |= 1u << m;
+            }
+            uint32_t n_here = min(128u, v.visits - base);
+            if (in_sync && !__any_sync(0xffffffffu, marks != 0)) {       // everything accepted
+                if (accepted < 2 && accepted + n_here >= 2) second = base + (1 - accepted);
+                accepted += n_here;
+                pivot = base + n_here - 1;
+                continue;
+            }
+            // serial replay of this stretch by lane 0
+            if (lane == 0) {
+                vec2 pv = visit(f, v, st, pivot);
+                for (uint32_t k = base; k < base + n_here; ++k) {
+                    vec2 q = visit(f, v, st, k);
+                    if (vlen(q - pv) >= 1.0e-4f) {
+                        f.visit_prev[off + k] = pivot;
+                        pivot = k; pv = q;
+                        if (++accepted == 2) second = k;
+                    } else
+                        f.visit_prev[off + k] = kNoLink;
+                }
+            }
+            pivot = __shfl_sync(0xffffffffu, pivot, 0);
+            accepted = __shfl_sync(0xffffffffu, accepted, 0);
+            second = __shfl_sync(0xffffffffu, second, 0);
+            in_sync = pivot == base + n_here - 1;
+        }
+        if (lane == 0) {
+            f.half_last[h] = pivot;
+            // a closed walk runs exactly two visits past its end only if its first join
+            // happened on visit 2; anything else is replayed by the serial fallback
+            if (v.closed && second != 2) f.half_dirty[h] = 1;
+        }
+    }
+}
+
+// Unit i < visits - 1: the join made when the walk visits point i + 1.  Last unit: the cap.
+template <class Sink>
+__device__ __forceinline__ void stroke_unit(const device_frame &f, const half_view &v, const stroke_style &st,
+                                            uint32_t off, uint32_t last, uint32_t unit_index, Sink &sink)
+{
+    if (!v.visits) return;
+    walk_state ws;
+    const uint32_t k = unit_index + 1;
+    if (k >= v.visits) {                                 // cap of an open half, after its last accepted point
+        if (v.closed || last == 0) return;
+        uint32_t p = f.visit_prev[off + last];
+        vec2 a = visit(f, v, st, p), b = visit(f, v, st, last);
+        ws.pivot = b; ws.tin = unit(b - a); ws.lin = vlen(b - a);
+        cap_end(ws, st, sink);
+        return;
+    }
+    uint32_t p1 = f.visit_prev[off + k];
+    if (p1 == kNoLink || p1 == 0) return;                // skipped point, or no incoming segment yet
+    uint32_t p2 = f.visit_prev[off + p1];
+    vec2 a = visit(f, v, st, p2), b = visit(f, v, st, p1);
+    ws.pivot = b; ws.tin = unit(b - a); ws.lin = vlen(b - a);
+    join_step(ws, visit(f, v, st, k), st, sink);
+}
+
+// points per unit
 __global__ void __launch_bounds__(kBlock) k_stroke_unit_count(device_frame f)
 {
     frame_header *hd = f.hdr;
@@ -623,12 +698,12 @@ __global__ void __launch_bounds__(kBlock) k_stroke_unit_count(device_frame f)
     uint32_t h = find_half(f.half_unit_off, nh, first);
     stroke_style st;
     half_view v = view_half(f, h, st);
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t u = first + k;
+    for (uint32_t i = 0; i < ipt; ++i) {
+        uint32_t u = first + i;
         if (u >= end) break;
         while (u >= f.half_unit_off[h + 1]) { ++h; v = view_half(f, h, st); }
         count_sink cs = { 0 };
-        if (!stroke_unit(f, v, st, u - f.half_unit_off[h], cs)) { f.half_dirty[h] = 1; cs.n = 0; }
+        if (!f.half_dirty[h]) stroke_unit(f, v, st, f.half_unit_off[h], f.half_last[h], u - f.half_unit_off[h], cs);
         f.stroke_unit_pts[u] = uint32_t(cs.n);
     }
 }
@@ -644,8 +719,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_fallback_count(device_frame f
     for (uint32_t h = warp; h < nh; h += n_warps) {
         if (!f.half_dirty[h]) continue;
         uint32_t c = warp_half<false>(f, h, 0, 0);
-        uint32_t u0 = f.half_unit_off[h], u1 = f.half_unit_off[h + 1];
-        for (uint32_t u = u0 + lane; u < u1; u += 32) f.stroke_unit_pts[u] = u == u0 ? c : 0;
+        if (lane == 0) f.stroke_unit_pts[f.half_unit_off[h]] = c;
     }
 }
 
@@ -684,19 +758,20 @@ __global__ void __launch_bounds__(kBlock) k_stroke_unit_emit(device_frame f)
     uint32_t h = find_half(f.half_unit_off, nh, first);
     stroke_style st;
     half_view v = view_half(f, h, st);
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t u = first + k;
+    for (uint32_t i = 0; i < ipt; ++i) {
+        uint32_t u = first + i;
         if (u >= end) break;
         while (u >= f.half_unit_off[h + 1]) { ++h; v = view_half(f, h, st); }
-        if (u == f.half_unit_off[h]) f.half_offset[h] = at;           // where this half's output starts
-        if (u == n - 1) f.half_offset[nh] = at + f.stroke_unit_pts[u];
-        if (!f.half_dirty[h]) {
+        uint32_t k = u - f.half_unit_off[h], mine = f.stroke_unit_pts[u];
+        if (k == 0) f.half_offset[h] = at;               // where this half's output starts
+        if (u == n - 1) f.half_offset[nh] = at + mine;
+        if (!f.half_dirty[h] && mine) {
             // closed source: each half is its own loop; open: both halves form one loop
             uint32_t loop_id = f.stroke_loop_base + (v.closed ? h : (h & ~1u));
             point_sink ps = { f.pts, f.pt_loop, base + at, loop_id };
-            stroke_unit(f, v, st, u - f.half_unit_off[h], ps);
+            stroke_unit(f, v, st, f.half_unit_off[h], f.half_last[h], k, ps);
         }
-        at += f.stroke_unit_pts[u];
+        at += mine;
     }
 }
 
@@ -744,6 +819,8 @@ void launch_stroke(const device_frame &f, cudaStream_t s)
     if (!f.n_static_sources && !f.n_dash_items) return;
     k_stroke_plan<<<kGrid, kBlock, 0, s>>>(f);
     k_stroke_plan_apply<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_visits<<<kGrid, kBlock, 0, s>>>(f);
+    k_stroke_resolve<<<kGrid, kBlock, 0, s>>>(f);
     k_stroke_unit_count<<<kGrid, kBlock, 0, s>>>(f);
     k_stroke_fallback_count<<<kGrid, kBlock, 0, s>>>(f);
     k_stroke_unit_sums<<<kGrid, kBlock, 0, s>>>(f);
