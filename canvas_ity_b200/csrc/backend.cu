@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -104,7 +105,7 @@ struct cb200_canvas {
 
     // device work buffers
     dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
-        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags,
+        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, long_rows, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags, te_job,
         te_first, partials, sort_hist;
     dev_buf<float2> pts;
     dev_buf<loop_span> loops;
@@ -303,6 +304,13 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     uint32_t want_dash_sub = sf.dash_items.empty() ? 0u : std::max<uint32_t>(4096u, uint32_t(sf.dash_items.size()) * 64u);
     uint32_t want_items = want_pts * 2, want_rows = 1u << 22, want_runs = 1u << 23, want_tiles = 1u << 17;
     uint64_t want_planes = sf.shadow_jobs.empty() ? 0 : uint64_t(cv->width + 64) * uint64_t(cv->height + 64) * 2;
+    if (getenv("CB200_TEST_SMALL_CAPS")) {
+        // test hook: start with tiny queues so that every frame exercises the overflow -> regrow -> re-run path
+        want_pts = 64; want_items = 64; want_rows = 64; want_runs = 64; want_tiles = 16;
+        want_planes = sf.shadow_jobs.empty() ? 0 : 64;
+        want_dash_sub = sf.dash_items.empty() ? 0u : 4u;
+        want_sources = uint32_t(sf.sources.size()) + 4;
+    }
     if (seen) {
         uint32_t total_pts = seen->n_line_points + seen->n_dash_points + seen->n_stroke_points;
         want_pts = std::max(want_pts, total_pts + total_pts / 4 + 1024);
@@ -356,14 +364,16 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->vals0.reserve(want_runs));
     CK(cv->vals1.reserve(want_runs));
     CK(cv->cumulative.reserve(want_runs));
+    CK(cv->long_rows.reserve(want_runs / 32 + 64));
     CK(cv->te_flags.reserve(want_tiles));
+    CK(cv->te_job.reserve(want_tiles));
     CK(cv->te_backdrop.reserve(size_t(want_tiles) * kTile));
     CK(cv->te_first.reserve(size_t(want_tiles) * kTile));
     CK(cv->planes.reserve(want_planes));
     CK(cv->planes_tmp.reserve(want_planes));
     CK(cv->partials.reserve(8 * kGrid));
     CK(cv->comp.reserve(sf.jobs.size() + 1));
-    CK(cv->sort_hist.reserve(256 * kGrid + 256));
+    CK(cv->sort_hist.reserve(512 * kGrid + 512));
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
     cv->cap_items = want_items; cv->cap_rows = want_rows; cv->cap_runs = want_runs;
@@ -481,8 +491,8 @@ int upload_frame(cb200_canvas *cv)
     f.cap_items = cv->cap_items;
     f.row_runs = cv->row_runs.p; f.cap_rows = cv->cap_rows;
     f.keys[0] = cv->keys0.p; f.keys[1] = cv->keys1.p; f.vals[0] = cv->vals0.p; f.vals[1] = cv->vals1.p;
-    f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p;
-    f.te_flags = cv->te_flags.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
+    f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p; f.long_rows = cv->long_rows.p;
+    f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
     f.cap_tiles = cv->cap_tiles;
     f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
     f.partials = cv->partials.p; f.sort_hist = cv->sort_hist.p;
@@ -525,7 +535,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
-                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * ((sf.key_bits + 7) / 8) + 2 +
+                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
                     (sf.shadow_jobs.empty() ? 0 : 7) + 1;
     cv->pending = true;
     CK(cudaGetLastError());
@@ -541,6 +551,32 @@ int finish_pending(cb200_canvas *cv)
         CK(cudaEventSynchronize(cv->ev[6]));
         CK(cudaGetLastError());
         frame_header seen = *cv->pinned_hdr;
+        if (getenv("CB200_DEBUG"))
+            fprintf(stderr, "[cb200] attempt %d overflow=%#x line_pts=%u stroke_units=%u stroke_pts=%u items=%u rows=%u runs=%u "
+                    "tiles=%u long=%u planes=%llu composited=%llu | caps pts=%u items=%u rows=%u runs=%u tiles=%u\n",
+                    attempt, seen.overflow, seen.n_line_points, seen.n_stroke_units, seen.n_stroke_points, seen.n_items,
+                    seen.n_row_items, seen.n_runs, seen.n_tile_entries, seen.n_long_rows,
+                    (unsigned long long)seen.plane_floats, seen.composited_pixels, cv->cap_pts, cv->cap_items, cv->cap_rows,
+                    cv->cap_runs, cv->cap_tiles);
+        if (getenv("CB200_DEBUG") && cv->staged.subpaths.size() < 64) {
+            size_t ns = cv->staged.subpaths.size(), nu = cv->staged.units.size(), nsrc = cv->staged.sources.size();
+            std::vector<loop_span> lp(ns + 1);
+            std::vector<uint32_t> uo(nu + 1), uc(nu + 1);
+            std::vector<stroke_src> ss(nsrc + 1);
+            cudaMemcpy(lp.data(), cv->loops.p, ns * sizeof(loop_span), cudaMemcpyDeviceToHost);
+            cudaMemcpy(uo.data(), cv->unit_offset.p, (nu + 1) * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(uc.data(), cv->unit_count.p, nu * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ss.data(), cv->sources.p, nsrc * sizeof(stroke_src), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "  loops:");
+            for (size_t i = 0; i < ns; ++i) fprintf(stderr, " (%u,%u)", lp[i].first, lp[i].count);
+            fprintf(stderr, "\n  unit_offset:");
+            for (size_t i = 0; i <= nu; ++i) fprintf(stderr, " %u", uo[i]);
+            fprintf(stderr, "\n  unit_count:");
+            for (size_t i = 0; i < nu; ++i) fprintf(stderr, " %u", uc[i]);
+            fprintf(stderr, "\n  sources:");
+            for (size_t i = 0; i < nsrc; ++i) fprintf(stderr, " (%u,%#x)", ss[i].loop, ss[i].draw_closed);
+            fprintf(stderr, "\n");
+        }
         if (!seen.overflow) {
             float ms = 0.0f;
             cb200_stats &st = cv->stats;
@@ -657,10 +693,10 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
     cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->half_last.release(); cv->visit_prev.release(); cv->visit_close.release(); cv->piece_job.release();
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
-    cv->row_runs.release(); cv->te_flags.release(); cv->te_first.release(); cv->partials.release();
+    cv->row_runs.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->keys0.release(); cv->keys1.release();
-    cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->te_backdrop.release();
+    cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 8; ++i)
         if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
@@ -917,7 +953,7 @@ int64_t cb200_debug_runs(cb200_canvas *cv, uint64_t *keys, float *cumulative, in
     cudaStreamSynchronize(cv->stream);
     frame_header h = *cv->pinned_hdr;
     int64_t n = std::min<int64_t>(h.n_runs, capacity);
-    int sorted = ((cv->staged.key_bits + 7) / 8) & 1;
+    int sorted = sort_passes(cv->staged.key_bits) & 1;
     if (n && keys) cudaMemcpy(keys, sorted ? cv->keys1.p : cv->keys0.p, sizeof(uint64_t) * size_t(n), cudaMemcpyDeviceToHost);
     if (n && cumulative) cudaMemcpy(cumulative, cv->cumulative.p, sizeof(float) * size_t(n), cudaMemcpyDeviceToHost);
     return h.n_runs;

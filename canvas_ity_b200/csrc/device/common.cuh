@@ -122,6 +122,7 @@ struct frame_header {
     uint32_t n_row_items;                  // (piece, scanline) pairs
     uint32_t n_runs;
     uint32_t n_tile_entries;
+    uint32_t n_long_rows;                  // scanline segments handed to k_rows_long
     uint64_t plane_floats;
     uint32_t overflow;                     // bit set: which capacity was exceeded
     uint32_t sort_bits_x, sort_bits_y, sort_bits;
@@ -174,6 +175,18 @@ __device__ __forceinline__ void block_slice(uint32_t n, uint32_t &begin, uint32_
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
     per_thread = (per + blockDim.x - 1) / blockDim.x;            // consecutive items per thread
     per = per_thread * blockDim.x;
+    uint64_t b = uint64_t(per) * blockIdx.x;
+    begin = b < n ? uint32_t(b) : n;
+    end = b + per < n ? uint32_t(b + per) : n;
+}
+
+// Slice for kernels that give one WARP per item: whole warps-worth of items per CTA,
+// spread over the entire grid.
+__device__ __forceinline__ void warp_slice(uint32_t n, uint32_t &begin, uint32_t &end)
+{
+    const uint32_t warps = blockDim.x >> 5;
+    uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + warps - 1) / warps * warps;
     uint64_t b = uint64_t(per) * blockIdx.x;
     begin = b < n ? uint32_t(b) : n;
     end = b + per < n ? uint32_t(b + per) : n;

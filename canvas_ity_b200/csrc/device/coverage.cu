@@ -19,6 +19,8 @@ namespace cb200 {
 
 namespace {
 
+constexpr uint32_t kShortRow = 48;      // longer scanline segments go to the warp-cooperative kernel
+
 __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
 {
     frame_header *h = f.hdr;
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
         uint64_t row = keys[i] >> bx;
         if (i > 0 && (keys[i - 1] >> bx) == row) continue;          // not a segment head
         uint32_t j = uint32_t(row >> by);
+        if (j >= h->n_jobs) continue;
         int y = int(row & ymask);
         const job_rec &jr = f.jobs[j];
         int ty = y / kTile - jr.ty0, ly = y % kTile;
@@ -45,7 +48,9 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
         float sum = 0.0f;
         uint32_t k = i;
         uint64_t key = keys[k];
+        bool too_long = false;
         for (;;) {
+            if (k - i >= kShortRow) { too_long = true; break; }
             int x = int(key & xmask);
             int c = x / kTile;
             if (binned && c > c_prev) {
@@ -55,12 +60,12 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
                     for (int cc = c_prev + 1; cc <= last; ++cc) {
                         uint32_t te = te_row + uint32_t(cc - jr.tx0);
                         f.te_backdrop[te * kTile + ly] = sum;
-                        if (everywhere || fabsf(sum) >= kThreshold) f.te_flags[te] = 1;
+                        if (everywhere || fabsf(sum) >= kThreshold) { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
                     }
                 if (c <= c_end) {
                     uint32_t te = te_row + uint32_t(c - jr.tx0);
                     f.te_first[te * kTile + ly] = k;
-                    f.te_flags[te] = 1;
+                    { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
                 }
                 c_prev = max(c_prev, last);
             }
@@ -73,12 +78,95 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
             k = nk;
             key = nkey;
         }
+        if (too_long) {                                              // redo by a whole warp
+            f.long_rows[atomicAdd(&h->n_long_rows, 1u)] = i;
+            continue;
+        }
         // whatever is left over after the last run spills to the right edge
         if (binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
             for (int cc = c_prev + 1; cc <= c_end; ++cc) {
                 uint32_t te = te_row + uint32_t(cc - jr.tx0);
                 f.te_backdrop[te * kTile + ly] = sum;
-                f.te_flags[te] = 1;
+                { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
+            }
+    }
+}
+
+// Long scanline segments (thin, nearly horizontal shapes put thousands of runs on
+// one scanline): one warp per segment, 32 runs per step, running sum by a warp
+// prefix scan carried in double precision (so the float result does not depend on
+// the scan's association order), same bookkeeping as k_rows.
+__global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
+{
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    const uint32_t n = h->n_runs, n_long = h->n_long_rows;
+    const uint32_t bx = h->sort_bits_x, by = h->sort_bits_y;
+    const uint64_t xmask = (1ull << bx) - 1, ymask = (1ull << by) - 1;
+    const uint64_t *keys = f.keys[sb];
+    const float *delta = f.vals[sb];
+    const float quiet_nan = __int_as_float(0x7fc00000);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = warp; w < n_long; w += n_warps) {
+        const uint32_t head = f.long_rows[w];
+        const uint64_t row = keys[head] >> bx;
+        const uint32_t j = uint32_t(row >> by);
+        const int y = int(row & ymask);
+        const job_rec &jr = f.jobs[j];
+        const int ty = y / kTile - jr.ty0, ly = y % kTile;
+        const bool binned = ty >= 0 && ty < jr.th && jr.tw > 0;
+        const bool everywhere = jr.kind != JOB_MAIN || (~f.draws[jr.draw].op & 8u);
+        const uint32_t te_row = jr.te_base + uint32_t(ty) * uint32_t(jr.tw);
+        const int c_end = jr.tx0 + jr.tw - 1;
+        int c_carry = jr.tx0 - 1;                     // tile column of the last run seen so far
+        double carry = 0.0;
+        for (uint32_t base = head;; base += 32) {
+            uint32_t idx = base + uint32_t(lane);
+            uint64_t key = idx < n ? keys[idx] : ~0ull;
+            bool valid = (key >> bx) == row;
+            uint64_t nkey = idx + 1 < n ? keys[idx + 1] : ~0ull;
+            double v = valid ? double(delta[idx]) : 0.0;
+            double incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            float after = float(carry + incl), before = float(carry + incl - v);
+            int x = int(key & xmask), c = valid ? x / kTile : 0x3fffffff;
+            int c_left = __shfl_up_sync(0xffffffffu, c, 1);
+            if (lane == 0) c_left = c_carry;
+            if (valid) {
+                bool same_x_next = (nkey >> bx) == row && int(nkey & xmask) == x;
+                f.cumulative[idx] = same_x_next ? quiet_nan : after;
+                if (binned && c > c_left) {
+                    int last = min(c, c_end);
+                    if (before != 0.0f)
+                        for (int cc = c_left + 1; cc <= last; ++cc) {
+                            uint32_t te = te_row + uint32_t(cc - jr.tx0);
+                            f.te_backdrop[te * kTile + ly] = before;
+                            if (everywhere || fabsf(before) >= kThreshold) { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
+                        }
+                    if (c <= c_end) {
+                        uint32_t te = te_row + uint32_t(c - jr.tx0);
+                        f.te_first[te * kTile + ly] = idx;
+                        { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
+                    }
+                }
+            }
+            uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            int last_lane = 31 - __clz(int(vm));
+            carry += __shfl_sync(0xffffffffu, incl, last_lane);
+            c_carry = max(c_carry, min(__shfl_sync(0xffffffffu, c, last_lane), c_end));
+            if (vm != 0xffffffffu) break;
+        }
+        float sum = float(carry);
+        if (lane == 0 && binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
+            for (int cc = c_carry + 1; cc <= c_end; ++cc) {
+                uint32_t te = te_row + uint32_t(cc - jr.tx0);
+                f.te_backdrop[te * kTile + ly] = sum;
+                { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
             }
     }
 }
@@ -91,20 +179,14 @@ __global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_ta
 {
     frame_header *h = f.hdr;
     if (h->overflow) return;
-    const uint32_t n_jobs = h->n_jobs;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n = h->n_tile_entries;
-    // one warp per tile entry, one lane per scanline; entry -> job by binary search on te_base
+    // one warp per tile entry, one lane per scanline; te_job remembers which job marked it
     for (uint32_t te = warp; te < n; te += n_warps) {
         uint32_t flags = f.te_flags[te];
         if (!(flags & TE_NONEMPTY)) continue;
-        uint32_t lo = 0, hi = n_jobs;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (f.jobs[mid].te_base <= te) lo = mid; else hi = mid;
-        }
-        while (lo + 1 < n_jobs && f.jobs[lo].tw * f.jobs[lo].th == 0) ++lo;      // skip empty jobs sharing the base
+        uint32_t lo = f.te_job[te];
         const job_rec &jr = f.jobs[lo];
         if (jr.kind != JOB_MAIN || !jr.opaque) continue;
         uint32_t local = te - jr.te_base;
@@ -121,6 +203,7 @@ __global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_ta
 void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
 {
     k_rows<<<kGrid, kBlock, 0, s>>>(f, sorted_buffer);
+    k_rows_long<<<kGrid, kBlock, 0, s>>>(f, sorted_buffer);
     k_tile_flags<<<kGrid, kBlock, 0, s>>>(f, t);
 }
 

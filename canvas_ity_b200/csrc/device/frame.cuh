@@ -51,8 +51,9 @@ struct device_frame {
     uint32_t *row_runs;    uint32_t cap_rows;          // per (piece,row)
     uint64_t *keys[2];     float *vals[2];            uint32_t cap_runs;
     float *cumulative;
+    uint32_t *long_rows;                               // segment heads too long for one thread
     // tiles
-    uint32_t *te_flags;    float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
+    uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
     float *planes, *planes_tmp;  uint64_t cap_planes;
     uint32_t *shadow_jobs; uint32_t n_shadow_jobs;     // job indices with kind JOB_SHADOW
     // scratch
@@ -75,6 +76,7 @@ void launch_stroke(const device_frame &f, cudaStream_t s);
 void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s);
 // sort.cu
 void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer);
+int sort_passes(int key_bits);
 // coverage.cu
 void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
 // composite.cu

@@ -24,64 +24,164 @@ __device__ __forceinline__ vec2 ld(const float2 *p, uint32_t i) { float2 v = p[i
 
 // ------------------------------------------------------------------- K1 ----
 
-template <class Sink>
-__device__ __forceinline__ void flatten_unit(const device_frame &f, uint32_t u, Sink &sink)
-{
-    unit_rec un = f.units[u];
-    subpath_rec sp = f.subpaths[un.subpath];
-    if (un.index == 0) { sink.put(ld(f.in_points, sp.first_point)); return; }
-    uint32_t at = sp.first_point + 3 * (un.index - 1);
-    flatten_cubic(ld(f.in_points, at), ld(f.in_points, at + 1), ld(f.in_points, at + 2),
-                  ld(f.in_points, at + 3), f.draws[sp.draw].angular, sink);
-}
-
-__global__ void __launch_bounds__(kBlock) k_flatten_count(device_frame f)
-{
-    __shared__ uint32_t sm[33];
-    uint32_t n = f.hdr->n_units, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t u = first + k;
-        if (u >= end) break;
-        count_sink cs = { 0 };
-        flatten_unit(f, u, cs);
-        f.unit_count[u] = uint32_t(cs.n);
-        sum += uint32_t(cs.n);
-    }
-    uint32_t total;
-    block_exclusive_scan(sum, sm, total);
-    if (threadIdx.x == 0) f.partials[blockIdx.x] = total;
-    finish_partials(f.partials, &f.hdr->tickets[0], &f.hdr->n_line_points, sm);
-}
-
 struct point_sink {
     float2 *out; uint32_t *loop_of; uint32_t at, loop;
     __device__ __forceinline__ void put(vec2 p) { out[at] = make_float2(p.x, p.y); loop_of[at] = loop; ++at; }
 };
 
+constexpr int kWarps = kBlock / 32;
+constexpr int kNodeWords = 10;          // p0 c1 c2 p3 (8 floats) + budget + state
+
+// One flatten unit by one WARP.  The reference recursion (add_tessellation) is a
+// depth-first walk whose subtrees are independent, so the warp first expands the
+// tree breadth-first -- the monotone pieces of add_bezier are the initial nodes,
+// every level halves the nodes that fail the flatness test, a warp scan keeps the
+// node list in curve order -- until up to 32 nodes exist; then every lane finishes
+// its own subtree depth-first and a second scan orders the output.  Same halving
+// arithmetic and the same tests as the serial routine in geom.cuh, hence the same
+// points in the same order.  `nodes`: kNodeWords * 32 words of warp-private smem.
+template <bool EMIT>
+__device__ uint32_t warp_flatten(const device_frame &f, uint32_t u, uint32_t out_base, float *nodes)
+{
+    const int lane = threadIdx.x & 31;
+    unit_rec un = f.units[u];
+    subpath_rec sp = f.subpaths[un.subpath];
+    if (un.index == 0) {                                  // the subpath's start point
+        if (EMIT && lane == 0) {
+            point_sink ps = { f.pts, f.pt_loop, out_base, un.subpath };
+            ps.put(ld(f.in_points, sp.first_point));
+        }
+        return 1;
+    }
+    const uint32_t at = sp.first_point + 3 * (un.index - 1);
+    const vec2 P0 = ld(f.in_points, at), C1 = ld(f.in_points, at + 1), C2 = ld(f.in_points, at + 2),
+               P3 = ld(f.in_points, at + 3);
+    const float angular = f.draws[sp.draw].angular;
+    {
+        vec2 e1 = C1 - P0, e3 = P3 - C2;
+        if (dot(e1, e1) == 0.0f && dot(e3, e3) == 0.0f) { // a straight segment
+            if (EMIT && lane == 0) {
+                point_sink ps = { f.pts, f.pt_loop, out_base, un.subpath };
+                ps.put(P3);
+            }
+            return 1;
+        }
+    }
+    // initial nodes: the kept monotone pieces, piece m on lane m
+    vec2 p0 = v2(0, 0), c1 = p0, c2 = p0, p3 = p0;
+    int budget = 0, state = 0;                            // 0 empty, 1 open, 2 flat leaf
+    {
+        float cut[7];
+        int n = cubic_cuts(P0, C1, C2, P3, cut), m = 0;
+        vec2 from = P0;
+        for (int i = 0; i + 1 < n; ++i) {
+            if (!cut_is_kept(cut[i], cut[i + 1])) continue;
+            vec2 k1, k2, to;
+            cubic_piece(P0, C1, C2, P3, cut[i], cut[i + 1], k1, k2, to);
+            if (lane == m) { p0 = from; c1 = k1; c2 = k2; p3 = to; budget = 20; state = 1; }
+            from = to;
+            ++m;
+        }
+    }
+    for (;;) {                                            // breadth-first expansion
+        float q1, q2, q3;
+        if (state == 1 && (piece_is_flat(p0, c1, c2, p3, angular, q1, q2, q3) || budget == 0)) state = 2;
+        uint32_t width = state == 0 ? 0u : (state == 1 ? 2u : 1u);
+        uint32_t incl = warp_inclusive_scan(width);
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!__any_sync(0xffffffffu, state == 1) || total > 32) break;
+        uint32_t pos = incl - width;
+        if (state == 2) {
+            float *d = nodes + pos * kNodeWords;
+            d[0] = p0.x; d[1] = p0.y; d[2] = c1.x; d[3] = c1.y; d[4] = c2.x; d[5] = c2.y; d[6] = p3.x; d[7] = p3.y;
+            d[8] = __int_as_float(budget); d[9] = __int_as_float(2);
+        } else if (state == 1) {
+            vec2 l1 = mix(p0, c1, 0.5f), mid = mix(c1, c2, 0.5f), r2 = mix(c2, p3, 0.5f);
+            vec2 l2 = mix(l1, mid, 0.5f), r1 = mix(mid, r2, 0.5f);
+            vec2 split = mix(l2, r1, 0.5f);
+            float *d = nodes + pos * kNodeWords;
+            d[0] = p0.x; d[1] = p0.y; d[2] = l1.x; d[3] = l1.y; d[4] = l2.x; d[5] = l2.y; d[6] = split.x; d[7] = split.y;
+            d[8] = __int_as_float(budget - 1); d[9] = __int_as_float(1);
+            d += kNodeWords;
+            d[0] = split.x; d[1] = split.y; d[2] = r1.x; d[3] = r1.y; d[4] = r2.x; d[5] = r2.y; d[6] = p3.x; d[7] = p3.y;
+            d[8] = __int_as_float(budget - 1); d[9] = __int_as_float(1);
+        }
+        __syncwarp();
+        if (uint32_t(lane) < total) {
+            const float *d = nodes + lane * kNodeWords;
+            p0 = v2(d[0], d[1]); c1 = v2(d[2], d[3]); c2 = v2(d[4], d[5]); p3 = v2(d[6], d[7]);
+            budget = __float_as_int(d[8]); state = __float_as_int(d[9]);
+        } else state = 0;
+        __syncwarp();
+    }
+    // depth-first finish of every lane's subtree; count first, then write in order
+    uint32_t mine = 0;
+    if (state == 2) {
+        float q1, q2, q3;
+        piece_is_flat(p0, c1, c2, p3, angular, q1, q2, q3);
+        count_sink cs = { 0 };
+        emit_flat_piece(c1, c2, p3, angular, q1, q2, q3, cs);
+        mine = uint32_t(cs.n);
+    } else if (state == 1) {
+        count_sink cs = { 0 };
+        subdivide_piece(p0, c1, c2, p3, angular, cs, budget);
+        mine = uint32_t(cs.n);
+    }
+    uint32_t incl = warp_inclusive_scan(mine);
+    if (EMIT && mine) {
+        point_sink ps = { f.pts, f.pt_loop, out_base + incl - mine, un.subpath };
+        if (state == 2) {
+            float q1, q2, q3;
+            piece_is_flat(p0, c1, c2, p3, angular, q1, q2, q3);
+            emit_flat_piece(c1, c2, p3, angular, q1, q2, q3, ps);
+        } else
+            subdivide_piece(p0, c1, c2, p3, angular, ps, budget);
+    }
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+__global__ void __launch_bounds__(kBlock) k_flatten_count(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t block_total;
+    __shared__ float nodes[kWarps][kNodeWords * 32];
+    uint32_t n = f.hdr->n_units, begin, end;
+    warp_slice(n, begin, end);
+    if (threadIdx.x == 0) block_total = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t u = begin + uint32_t(warp); u < end; u += kWarps) {
+        uint32_t c = warp_flatten<false>(f, u, 0, nodes[warp]);
+        if (lane == 0) { f.unit_count[u] = c; atomicAdd(&block_total, c); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) f.partials[blockIdx.x] = block_total;
+    finish_partials(f.partials, &f.hdr->tickets[0], &f.hdr->n_line_points, sm);
+}
+
 __global__ void __launch_bounds__(kBlock) k_flatten_emit(device_frame f)
 {
     __shared__ uint32_t sm[33];
-    uint32_t n = f.hdr->n_units, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
+    __shared__ float nodes[kWarps][kNodeWords * 32];
+    uint32_t n = f.hdr->n_units, begin, end;
+    warp_slice(n, begin, end);
     if (f.hdr->n_line_points > f.cap_pts) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&f.hdr->overflow, OVF_POINTS);
         return;
     }
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.unit_count[first + k];
-    uint32_t total;
-    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[blockIdx.x];
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t u = first + k;
-        if (u >= end) break;
-        f.unit_offset[u] = at;
-        point_sink ps = { f.pts, f.pt_loop, at, f.units[u].subpath };
-        flatten_unit(f, u, ps);
-        at = ps.at;
-        if (u == n - 1) f.unit_offset[n] = at;
+    uint32_t carry = f.partials[blockIdx.x];
+    for (uint32_t chunk = begin; chunk < end; chunk += kBlock) {
+        uint32_t u = chunk + threadIdx.x;
+        uint32_t c = u < end ? f.unit_count[u] : 0, total;
+        uint32_t ex = block_exclusive_scan(c, sm, total);
+        if (u < end) f.unit_offset[u] = carry + ex;
+        if (u < end && u == n - 1) f.unit_offset[n] = carry + ex + c;
+        carry += total;
     }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t u = begin + uint32_t(warp); u < end; u += kWarps)
+        warp_flatten<true>(f, u, f.unit_offset[u], nodes[warp]);
 }
 
 // loops[s] = point span of subpath s in the K1 output
@@ -477,8 +577,6 @@ __device__ uint32_t warp_half(const device_frame &f, uint32_t h, uint32_t out_ba
     }
     return emitted;
 }
-
-constexpr int kWarps = kBlock / 32;
 
 // ---- unit-parallel stroking ---------------------------------------------------
 // The reference walks each polyline serially, but its state before visiting point

@@ -2,8 +2,8 @@
 // (replaces the std::sort of reference lines_to_runs, hpp:2243; the tie order
 // among runs on the same pixel is irrelevant to the summed coverage).
 //
-// 8-bit digits; only ceil(key_bits / 8) passes run, the host knows key_bits from
-// the canvas size and the job count.  Per pass, three launches with fixed grids
+// Digits are up to 9 bits wide: ceil(key_bits / 9) passes of equal width; the host knows
+// key_bits from the canvas size and the job count (34 bits = 4 passes for the 4096x4096 tiger).  Per pass, three launches with fixed grids
 // (the run count lives on the device):
 //   k_sort_hist     per-CTA digit histogram of its slice (digit-major table)
 //   k_sort_scan     one CTA per digit: exclusive scan across the CTAs + digit total
@@ -15,7 +15,7 @@ namespace cb200 {
 
 namespace {
 
-constexpr int kRadix = 256;
+constexpr int kMaxRadix = 512;          // digits are up to 9 bits wide
 
 __device__ __forceinline__ void sort_slice(uint32_t n, uint32_t &begin, uint32_t &end)
 {
@@ -26,23 +26,24 @@ __device__ __forceinline__ void sort_slice(uint32_t n, uint32_t &begin, uint32_t
     end = b + per < n ? uint32_t(b + per) : n;
 }
 
-__global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, int shift)
+__global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, int shift, int width)
 {
-    __shared__ uint32_t bins[kRadix];
+    __shared__ uint32_t bins[kMaxRadix];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
     sort_slice(n, begin, end);
-    bins[threadIdx.x] = 0;
+    const uint32_t radix = 1u << width, mask = radix - 1;
+    for (uint32_t d = threadIdx.x; d < radix; d += kBlock) bins[d] = 0;
     __syncthreads();
     const uint64_t *keys = f.keys[src];
     for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock)
-        atomicAdd(&bins[uint32_t(keys[i] >> shift) & 0xffu], 1u);
+        atomicAdd(&bins[uint32_t(keys[i] >> shift) & mask], 1u);
     __syncthreads();
-    f.sort_hist[threadIdx.x * kGrid + blockIdx.x] = bins[threadIdx.x];     // digit-major
+    for (uint32_t d = threadIdx.x; d < radix; d += kBlock) f.sort_hist[d * kGrid + blockIdx.x] = bins[d];   // digit-major
 }
 
 // One CTA per digit: exclusive scan of that digit's per-CTA counts (coalesced),
-// digit total to sort_hist[kRadix * kGrid + digit].
+// digit total to sort_hist[kMaxRadix * kGrid + digit].
 __global__ void __launch_bounds__(kBlock) k_sort_scan(device_frame f)
 {
     __shared__ uint32_t sm[33];
@@ -55,24 +56,31 @@ __global__ void __launch_bounds__(kBlock) k_sort_scan(device_frame f)
         if (i < kGrid) row[i] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) f.sort_hist[kRadix * kGrid + blockIdx.x] = carry;
+    if (threadIdx.x == 0) f.sort_hist[kMaxRadix * kGrid + blockIdx.x] = carry;
 }
 
-__global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift)
+__global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift, int width)
 {
-    __shared__ uint32_t base[kRadix];              // next free global slot per digit for this CTA
-    __shared__ uint32_t warp_count[kBlock / 32][kRadix];
+    __shared__ uint32_t base[kMaxRadix];             // next free global slot per digit for this CTA
+    __shared__ uint32_t warp_count[kBlock / 32][kMaxRadix];
+    __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
     sort_slice(n, begin, end);
-    __shared__ uint32_t sm[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {   // global base of digit d = keys with a smaller digit + this digit's keys in earlier CTAs
+    const uint32_t radix = 1u << width, mask = radix - 1;
+    {   // global base of digit d = keys with a smaller digit + this digit's keys in earlier CTAs;
+        // thread t owns digits 2t and 2t+1
+        uint32_t d0 = 2 * threadIdx.x, d1 = d0 + 1;
+        uint32_t t0 = d0 < radix ? f.sort_hist[kMaxRadix * kGrid + d0] : 0;
+        uint32_t t1 = d1 < radix ? f.sort_hist[kMaxRadix * kGrid + d1] : 0;
         uint32_t total;
-        uint32_t below = block_exclusive_scan(f.sort_hist[kRadix * kGrid + threadIdx.x], sm, total);
-        base[threadIdx.x] = below + f.sort_hist[threadIdx.x * kGrid + blockIdx.x];
+        uint32_t below = block_exclusive_scan(t0 + t1, sm, total);
+        if (d0 < radix) base[d0] = below + f.sort_hist[d0 * kGrid + blockIdx.x];
+        if (d1 < radix) base[d1] = below + t0 + f.sort_hist[d1 * kGrid + blockIdx.x];
     }
-    for (int w = 0; w < kBlock / 32; ++w) warp_count[w][threadIdx.x] = 0;
+    for (uint32_t d = threadIdx.x; d < radix; d += kBlock)
+        for (int w = 0; w < kBlock / 32; ++w) warp_count[w][d] = 0;
     __syncthreads();
     const uint64_t *kin = f.keys[src];
     const float *vin = f.vals[src];
@@ -83,13 +91,14 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
         bool valid = i < end;
         uint64_t key = valid ? kin[i] : 0;
         float val = valid ? vin[i] : 0.0f;
-        uint32_t digit = valid ? uint32_t(key >> shift) & 0xffu : 0x100u + uint32_t(lane);
+        uint32_t digit = valid ? uint32_t(key >> shift) & mask : kMaxRadix + uint32_t(lane);
         uint32_t peers = __match_any_sync(0xffffffffu, digit);
         uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank == 0) warp_count[warp][digit] = __popc(peers);
         __syncthreads();
-        {   // thread d owns digit d: prefix over the warps, then advance the CTA base
-            uint32_t d = threadIdx.x, run = base[d];
+        // each digit: prefix over the warps, then advance the CTA base
+        for (uint32_t d = threadIdx.x; d < radix; d += kBlock) {
+            uint32_t run = base[d];
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) {
                 uint32_t c = warp_count[w][d];
@@ -106,8 +115,7 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
         }
         __syncthreads();
         // prefixes (also of digits absent from a warp) must not leak into the next step
-        {
-            uint32_t d = threadIdx.x;
+        for (uint32_t d = threadIdx.x; d < radix; d += kBlock) {
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) warp_count[w][d] = 0;
         }
@@ -119,14 +127,17 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
 
 // Sorts keys[0]/vals[0]; *result_buffer receives which of the two buffers holds
 // the sorted data.
+int sort_passes(int key_bits) { return (key_bits + 8) / 9; }
+
 void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer)
 {
-    int passes = (key_bits + 7) / 8;
+    int passes = sort_passes(key_bits);
+    int width = (key_bits + passes - 1) / passes;      // <= 9
     int src = 0;
     for (int p = 0; p < passes; ++p) {
-        k_sort_hist<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
-        k_sort_scan<<<kRadix, kBlock, 0, s>>>(f);
-        k_sort_scatter<<<kGrid, kBlock, 0, s>>>(f, src, p * 8);
+        k_sort_hist<<<kGrid, kBlock, 0, s>>>(f, src, p * width, width);
+        k_sort_scan<<<1 << width, kBlock, 0, s>>>(f);
+        k_sort_scatter<<<kGrid, kBlock, 0, s>>>(f, src, p * width, width);
         src ^= 1;
     }
     *result_buffer = src;

@@ -47,40 +47,55 @@ CB_HD float stroke_angular(float line_width) {
     return (ratio - 2.0f) * ratio * 2.0f + 1.0f;
 }
 
-// One monotone piece: halve until both inner control points sit within 1/8 px
-// of the chord and (strokes) the turn stays under the angular limit; depth cap
-// 20.  Left halves first so points come out in curve order.  `Sink::put(vec2)`.
+// Flatness / turn test of one curve piece (hpp:1341-1369).  Returns true when the
+// piece needs no further halving; q1..q3 are the squared control-polygon edges the
+// emission rule needs.
+CB_HD bool piece_is_flat(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, float &q1, float &q2, float &q3)
+{
+    vec2 e1 = c1 - p0, e2 = c2 - c1, e3 = p3 - c2, chord = p3 - p0;
+    q1 = dot(e1, e1); q2 = dot(e2, e2); q3 = dot(e3, e3);
+    float chord2 = fmaxf(1.0e-4f, dot(chord, chord));
+    float t1 = clamp01(dot(e1, chord) / chord2);
+    float t2 = clamp01(dot(e3, chord) / chord2);
+    vec2 off1 = p0 + t1 * chord - c1;
+    vec2 off2 = p3 - t2 * chord - c2;
+    float cosine = 1.0f;
+    if (angular > -1.0f) {
+        if (q1 * q3 != 0.0f) cosine = dot(e1, e3) / sqrtf(q1 * q3);
+        else if (q1 * q2 != 0.0f) cosine = dot(e1, e2) / sqrtf(q1 * q2);
+        else if (q2 * q3 != 0.0f) cosine = dot(e2, e3) / sqrtf(q2 * q3);
+    }
+    const float flat2 = 0.125f * 0.125f;
+    return dot(off1, off1) <= flat2 && dot(off2, off2) <= flat2 && cosine >= angular;
+}
+
+// What a finished piece contributes (hpp:1371-1376): strokes also get the control
+// points so that joins see true tangents; fills only the end point.
 template <class Sink>
-CB_HD void subdivide_piece(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink)
+CB_HD void emit_flat_piece(vec2 c1, vec2 c2, vec2 p3, float angular, float q1, float q2, float q3, Sink &sink)
 {
     const bool stroking = angular > -1.0f;
+    if (stroking && q1 != 0.0f) sink.put(c1);
+    if (stroking && q2 != 0.0f) sink.put(c2);
+    if (angular == -1.0f || q3 != 0.0f) sink.put(p3);
+}
+
+// One monotone piece: halve until both inner control points sit within 1/8 px
+// of the chord and (strokes) the turn stays under the angular limit; depth budget
+// 20 from the top.  Left halves first so points come out in curve order.
+// `Sink::put(vec2)`.
+template <class Sink>
+CB_HD void subdivide_piece(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink, int budget = 20)
+{
     // pending right halves; their start point is wherever the left subtree ends
     vec2 stack_c1[21], stack_c2[21], stack_p3[21];
     int stack_budget[21];
     int depth = 0;
-    int budget = 20;
     for (;;) {
-        vec2 e1 = c1 - p0, e2 = c2 - c1, e3 = p3 - c2, chord = p3 - p0;
-        float q1 = dot(e1, e1), q2 = dot(e2, e2), q3 = dot(e3, e3);
-        float chord2 = fmaxf(1.0e-4f, dot(chord, chord));
-        float t1 = clamp01(dot(e1, chord) / chord2);
-        float t2 = clamp01(dot(e3, chord) / chord2);
-        vec2 off1 = p0 + t1 * chord - c1;
-        vec2 off2 = p3 - t2 * chord - c2;
-        float cosine = 1.0f;
-        if (stroking) {
-            if (q1 * q3 != 0.0f) cosine = dot(e1, e3) / sqrtf(q1 * q3);
-            else if (q1 * q2 != 0.0f) cosine = dot(e1, e2) / sqrtf(q1 * q2);
-            else if (q2 * q3 != 0.0f) cosine = dot(e2, e3) / sqrtf(q2 * q3);
-        }
-        const float flat2 = 0.125f * 0.125f;
-        bool done = (dot(off1, off1) <= flat2 && dot(off2, off2) <= flat2 &&
-                     cosine >= angular) || budget == 0;
+        float q1, q2, q3;
+        bool done = piece_is_flat(p0, c1, c2, p3, angular, q1, q2, q3) || budget == 0;
         if (done) {
-            // strokes also get the control points so joins see true tangents
-            if (stroking && q1 != 0.0f) sink.put(c1);
-            if (stroking && q2 != 0.0f) sink.put(c2);
-            if (angular == -1.0f || q3 != 0.0f) sink.put(p3);
+            emit_flat_piece(c1, c2, p3, angular, q1, q2, q3, sink);
             if (depth == 0) return;
             --depth;
             p0 = p3;                       // right half starts where we stopped
@@ -121,17 +136,11 @@ CB_HD int axis_extrema(float a, float b, float c, float *cut, int n)
     return n;
 }
 
-// A whole cubic: cut at x/y extrema and at the curvature extremum so every
-// piece is monotone and turns < 90 degrees, then subdivide each piece.
-template <class Sink>
-CB_HD void flatten_cubic(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink)
+// Cut parameters of a cubic (hpp:1414-1465): 0, 1, the x/y extrema and the curvature
+// extremum, insertion-sorted.  Returns how many.
+CB_HD int cubic_cuts(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float *cut)
 {
     vec2 e1 = c1 - p0, e2 = c2 - c1, e3 = p3 - c2;
-    if (dot(e1, e1) == 0.0f && dot(e3, e3) == 0.0f) {   // a line (or a point)
-        sink.put(p3);
-        return;
-    }
-    float cut[7];
     cut[0] = 0.0f; cut[1] = 1.0f;
     int n = 2;
     vec2 qa = -9.0f * e2 + 3.0f * (p3 - p0);
@@ -150,18 +159,41 @@ CB_HD void flatten_cubic(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink
         for (; j >= 0 && v < cut[j]; --j) cut[j + 1] = cut[j];
         cut[j + 1] = v;
     }
+    return n;
+}
+
+CB_HD bool cut_is_kept(float lo, float hi) { return 0.0f <= lo && hi <= 1.0f && lo != hi; }
+
+// Control points of the piece [lo, hi] by blossoming (hpp:1472-1481): de Casteljau
+// at hi, then again at lo/hi from the left.  `from` is where the previous piece ended.
+CB_HD void cubic_piece(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float lo, float hi, vec2 &k1, vec2 &k2, vec2 &to)
+{
+    float rel = lo / hi;
+    vec2 a1 = mix(p0, c1, hi), a2 = mix(c1, c2, hi), a3 = mix(c2, p3, hi);
+    vec2 b1 = mix(a1, a2, hi), b2 = mix(a2, a3, hi);
+    vec2 g = mix(a1, b1, rel);
+    to = mix(b1, b2, hi);
+    k2 = mix(b1, to, rel);
+    k1 = mix(g, k2, rel);
+}
+
+// A whole cubic: cut at x/y extrema and at the curvature extremum so every
+// piece is monotone and turns < 90 degrees, then subdivide each piece.
+template <class Sink>
+CB_HD void flatten_cubic(vec2 p0, vec2 c1, vec2 c2, vec2 p3, float angular, Sink &sink)
+{
+    vec2 e1 = c1 - p0, e3 = p3 - c2;
+    if (dot(e1, e1) == 0.0f && dot(e3, e3) == 0.0f) {   // a line (or a point)
+        sink.put(p3);
+        return;
+    }
+    float cut[7];
+    int n = cubic_cuts(p0, c1, c2, p3, cut);
     vec2 from = p0;
     for (int i = 0; i + 1 < n; ++i) {
-        float lo = cut[i], hi = cut[i + 1];
-        if (!(0.0f <= lo && hi <= 1.0f && lo != hi)) continue;
-        // blossom [lo,hi]: de Casteljau at hi, then again at lo/hi from the left
-        float rel = lo / hi;
-        vec2 a1 = mix(p0, c1, hi), a2 = mix(c1, c2, hi), a3 = mix(c2, p3, hi);
-        vec2 b1 = mix(a1, a2, hi), b2 = mix(a2, a3, hi);
-        vec2 g = mix(a1, b1, rel);
-        vec2 to = mix(b1, b2, hi);
-        vec2 k2 = mix(b1, to, rel);
-        vec2 k1 = mix(g, k2, rel);
+        if (!cut_is_kept(cut[i], cut[i + 1])) continue;
+        vec2 k1, k2, to;
+        cubic_piece(p0, c1, c2, p3, cut[i], cut[i + 1], k1, k2, to);
         subdivide_piece(from, k1, k2, to, angular, sink);
         from = to;
     }

@@ -149,3 +149,24 @@ def test_python_mirror_reads_like_the_reference(lib):
     orc.oracle_canvas_destroy(o)
     nbad, worst = H.float_mismatch(got, want)
     assert nbad == 0, worst
+
+
+def test_queue_overflow_regrow_path(lib):
+    """Every device work queue starts tiny (CB200_TEST_SMALL_CAPS) so each frame overflows several
+    times and is re-run with larger buffers; the result must not change (the compositor does not
+    touch the framebuffer of an overflowed attempt)."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests import harness as H\n"
+            "lib = H.product_library()\n"
+            "bad = 0\n"
+            "for name in ['stroke', 'line_dash', 'shadow_blur', 'clip', 'pattern', 'fill_text']:\n"
+            "    s = H.golden_script(name)\n"
+            "    got = H.render_script(lib, s, 256, 256)\n"
+            "    want = H.render_oracle(s, 256, 256)\n"
+            "    n, worst = H.float_mismatch(got['f32'], want['f32'])\n"
+            "    bad += n\n"
+            "print('BAD', bad)\n") % H.ROOT
+    env = dict(os.environ, CB200_TEST_SMALL_CAPS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "BAD 0" in out.stdout, out.stdout + out.stderr
