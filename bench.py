@@ -253,6 +253,16 @@ def main():
             lib.cv_get_image_data(h, out.ctypes.data, size, size, 4 * size, 0, 0)
         for _ in range(args.warmup):
             one_frame()
+        if os.environ.get("CB200_E2E_BREAKDOWN"):
+            tc = tr = tg = 0.0
+            for _ in range(10):
+                a = time.perf_counter(); check(lib.cb200_clear(lib.cv_device(h)))
+                b = time.perf_counter(); lib.cv_run_script(h, e2e_script, len(e2e_script), None, 0, None); lib.cv_flush(h)
+                c = time.perf_counter(); lib.cv_get_image_data(h, out.ctypes.data, size, size, 4 * size, 0, 0)
+                d = time.perf_counter()
+                tc += b - a; tr += c - b; tg += d - c
+            print("e2e breakdown ms: clear %.3f script+lower+submit %.3f get_image_data %.3f" %
+                  (tc * 100, tr * 100, tg * 100), file=sys.stderr)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):

@@ -112,6 +112,8 @@ struct cb200_canvas {
     dev_buf<stroke_src> sources;
     dev_buf<float4> pieces, texels;
     dev_buf<comp_rec> comp;
+    dev_buf<uint2> job_box;
+    dev_buf<uint32_t> job_te;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -373,6 +375,8 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->planes_tmp.reserve(want_planes));
     CK(cv->partials.reserve(8 * kGrid));
     CK(cv->comp.reserve(sf.jobs.size() + 1));
+    CK(cv->job_box.reserve(sf.jobs.size() + 1));
+    CK(cv->job_te.reserve(sf.jobs.size() + 1));
     CK(cv->sort_hist.reserve(512 * kGrid + 512));
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
@@ -472,7 +476,7 @@ int upload_frame(cb200_canvas *cv)
     f.sources = cv->sources.p;
     f.n_static_sources = uint32_t(sf.sources.size());
     f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
-    f.comp = cv->comp.p;
+    f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p;
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
     f.texels = cv->texels.p;
@@ -695,7 +699,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
-    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->keys0.release(); cv->keys1.release();
+    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 8; ++i)

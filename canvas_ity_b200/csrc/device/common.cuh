@@ -107,6 +107,9 @@ struct comp_rec {
 static_assert(sizeof(comp_rec) == 128, "comp_rec must be one 128 B line");
 enum { COMP_EVERYWHERE = 1, COMP_OPAQUE = 2 };   // comp_rec.flags
 enum { TE_NONEMPTY = 1, TE_COVERED = 2 };        // te_flags
+// job_box[j]: tile rectangle the job composites into, 11 bits per coordinate, + kind and flags:
+//   x = tx0 | ty0 << 11 | (tx1 & 0x3ff) << 22      y = tx1 >> 10 | ty1 << 1 | kind << 12 | flags
+enum { JOBBOX_EVERYWHERE = 1u << 14, JOBBOX_OPAQUE = 1u << 15 };
 
 struct frame_header {
     // inputs

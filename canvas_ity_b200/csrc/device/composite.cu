@@ -188,6 +188,19 @@ __global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_
     const int tile_x0 = tx * kTile, tile_y0p = ty * kTile;
     const uint32_t n_jobs = h->n_jobs;
 
+    // Jobs are found through a compact 12-byte-per-job table (tile box + kind/flags word, first tile
+    // entry): one coalesced 8 B load per job and thread instead of the 128 B record.
+    auto box_hits = [&](uint2 box) -> bool {
+        int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
+        int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
+        return tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
+    };
+    auto entry_of = [&](uint2 box, uint32_t te_base) -> uint32_t {
+        int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
+        int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10);
+        return te_base + uint32_t(ty - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
+    };
+
     // Pass 1 -- occlusion culling: the last job that paints this whole tile with an
     // opaque solid colour (covered tile entry, source_over/copy, alpha 1, unclipped)
     // makes every earlier job, and the old framebuffer content, irrelevant.
@@ -196,12 +209,9 @@ __global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_
     for (uint32_t base = 0; base < n_jobs; base += kBlock) {
         uint32_t j = base + threadIdx.x;
         if (j < n_jobs) {
-            const comp_rec &c = f.comp[j];
-            if ((c.flags & COMP_OPAQUE) && c.cx0 < tile_x0 + kTile && c.cx1 > tile_x0 &&
-                c.cy0 < tile_y0p + kTile && c.cy1 > tile_y0p) {
-                uint32_t te = c.te_base + uint32_t(ty - c.ty0) * uint32_t(c.tw) + uint32_t(tx - c.tx0);
-                if (f.te_flags[te] & TE_COVERED) atomicMax(&s_start, int(j));
-            }
+            uint2 box = f.job_box[j];
+            if ((box.y & JOBBOX_OPAQUE) && box_hits(box) && (f.te_flags[entry_of(box, f.job_te[j])] & TE_COVERED))
+                atomicMax(&s_start, int(j));
         }
     }
     __syncthreads();
@@ -214,9 +224,10 @@ __global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_
     for (int k = 0; k < kRowsPerThread; ++k) {
         py[k] = ty * kTile + warp + k * (kBlock / 32);
         live[k] = x_in && py[k] >= t.band_y0 && py[k] < band_y1;
-        px[k] = (live[k] && start_job < 0) ? t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]
-                                            : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        px[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    bool loaded = start_job >= 0;              // a covering job replaces the old pixels: nothing to load
+    bool touched = false;
     const cov_source cs = make_cov_source(f, sb);
     const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
     unsigned long long painted = 0;
@@ -224,30 +235,47 @@ __global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_
     // Pass 2 -- replay the surviving jobs in submission order.
     const uint32_t first_job = start_job < 0 ? 0u : uint32_t(start_job);
     for (uint32_t base = first_job - first_job % kBlock; base < n_jobs; base += kBlock) {
-        // which of these 256 jobs touch this tile?  (ordered compaction)
-        uint32_t j = base + threadIdx.x, hit = 0, te = 0;
+        // which of these 256 jobs touch this tile?  (ordered compaction: ballot + per-warp counts)
+        uint32_t j = base + threadIdx.x, te = 0;
+        bool hit = false;
         if (j < n_jobs && j >= first_job) {
-            const comp_rec &c = f.comp[j];
-            if (c.cx0 < tile_x0 + kTile && c.cx1 > tile_x0 && c.cy0 < tile_y0p + kTile && c.cy1 > tile_y0p) {
-                if (c.kind == JOB_SHADOW) hit = 1;
+            uint2 box = f.job_box[j];
+            if (box_hits(box)) {
+                if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
                 else {
-                    te = c.te_base + uint32_t(ty - c.ty0) * uint32_t(c.tw) + uint32_t(tx - c.tx0);
-                    hit = ((c.flags & COMP_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY)) ? 1 : 0;
+                    te = entry_of(box, f.job_te[j]);
+                    hit = (box.y & JOBBOX_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY);
                 }
             }
         }
-        uint32_t n_hit;
-        uint32_t slot = block_exclusive_scan(hit, sm, n_hit);
+        uint32_t votes = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) sm[warp] = __popc(votes);
+        __syncthreads();
+        uint32_t slot = __popc(votes & ((1u << lane) - 1u)), n_hit = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) {
+            uint32_t c = sm[w];
+            if (w < warp) slot += c;
+            n_hit += c;
+        }
         if (hit) { s_job[slot] = j; s_te[slot] = te; }
         __syncthreads();
+        if (n_hit && !loaded) {                   // first job that touches the tile: fetch the old pixels
+#pragma unroll
+            for (int k = 0; k < kRowsPerThread; ++k)
+                if (live[k]) px[k] = t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)];
+            loaded = true;
+        }
+        touched = touched || n_hit != 0;
 
         for (uint32_t b0 = 0; b0 < n_hit; b0 += kBatch) {
             // stage up to kBatch jobs: one warp per job fetches its record and the 32
             // (backdrop, first run) pairs of this tile entry -- all loads in flight at once
             if (b0 + warp < n_hit) {
                 uint32_t jj = s_job[b0 + warp], tte = s_te[b0 + warp];
-                reinterpret_cast<uint32_t *>(&s_rec[warp])[lane] = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
-                bool has_rows = f.comp[jj].kind != JOB_SHADOW;
+                uint32_t word = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
+                reinterpret_cast<uint32_t *>(&s_rec[warp])[lane] = word;
+                bool has_rows = __shfl_sync(0xffffffffu, word, 0) != JOB_SHADOW;     // word 0 = kind
                 s_back[warp][lane] = has_rows ? f.te_backdrop[tte * kTile + lane] : 0.0f;
                 s_first[warp][lane] = has_rows ? f.te_first[tte * kTile + lane] : kNoRun;
             }
@@ -298,6 +326,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_
             __syncthreads();
         }
     }
+    if (!touched) return;                          // no job reaches this tile: its pixels stay as they are
 #pragma unroll
     for (int k = 0; k < kRowsPerThread; ++k)
         if (live[k]) t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)] = px[k];

@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
     }
     for (uint32_t k = 0; k < ipt; ++k) {
         uint32_t it = first + k;
-        if (it >= end) break;
+        const bool valid = it < end;
+        int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;     // pixel bounds of this item's pieces
+        if (valid) {
         while (it >= f.jobs[j].first_item + f.jobs[j].n_items) ++j;
         const job_rec &job = f.jobs[j];
         uint32_t p = job.first_point + (it - job.first_item);
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
                     int y_lo = e.down ? int(e.fy0) + r_first : int(e.fy0) - r_last;
                     int y_hi = e.down ? int(e.fy0) + r_last : int(e.fy0) - r_first;
                     int x_lo = int(e.fx0), x_hi = int(floorf(e.to.x)) + 1;
-                    atomicMin(&f.jobs[j].min_x, x_lo); atomicMax(&f.jobs[j].max_x, x_hi);
-                    atomicMin(&f.jobs[j].min_y, y_lo); atomicMax(&f.jobs[j].max_y, y_hi);
+                    bx0 = min(bx0, x_lo); bx1 = max(bx1, x_hi);
+                    by0 = min(by0, y_lo); by1 = max(by1, y_hi);
                 }
             }
             if (made < 3) {
@@ -213,6 +215,18 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
             }
         }
         for (; made < 3; ++made) f.piece_rows[it * 3 + made] = 0;
+        }
+        // job bounding boxes: neighbouring items nearly always belong to the same job, so lanes
+        // with equal job combine their bounds first and one of them issues the four atomics
+        const int lane = threadIdx.x & 31;
+        const bool has = valid && bx1 >= 0;
+        uint32_t peers = __match_any_sync(0xffffffffu, has ? j : 0x80000000u | uint32_t(lane));
+        int gx0 = __reduce_min_sync(peers, bx0), gy0 = __reduce_min_sync(peers, by0);
+        int gx1 = __reduce_max_sync(peers, bx1), gy1 = __reduce_max_sync(peers, by1);
+        if (has && lane == __ffs(int(peers)) - 1) {
+            atomicMin(&f.jobs[j].min_x, gx0); atomicMax(&f.jobs[j].max_x, gx1);
+            atomicMin(&f.jobs[j].min_y, gy0); atomicMax(&f.jobs[j].max_y, gy1);
+        }
     }
     uint32_t total;
     block_exclusive_scan(sum, sm, total);
@@ -425,6 +439,18 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
                 }
             }
             f.comp[j] = c;
+            // compact hit-test record: tile box of the composite rectangle (empty box: tx1 < tx0)
+            uint32_t bx0 = 1, by0 = 1, bx1 = 0, by1 = 0;
+            if (jr.cx1 > jr.cx0 && jr.cy1 > jr.cy0) {
+                bx0 = uint32_t(jr.cx0 / kTile); by0 = uint32_t(jr.cy0 / kTile);
+                bx1 = uint32_t((jr.cx1 - 1) / kTile); by1 = uint32_t((jr.cy1 - 1) / kTile);
+            }
+            uint2 box;
+            box.x = bx0 | by0 << 11 | (bx1 & 0x3ffu) << 22;
+            box.y = bx1 >> 10 | by1 << 1 | uint32_t(jr.kind) << 12 | (everywhere ? JOBBOX_EVERYWHERE : 0u) |
+                    (jr.opaque && jr.kind == JOB_MAIN ? JOBBOX_OPAQUE : 0u);
+            f.job_box[j] = box;
+            f.job_te[j] = jr.te_base;
         }
         // plane storage: order of allocation does not matter, only disjointness
         if (plane) {
