@@ -67,6 +67,8 @@ SIGNATURES = {
     "cb200_sync": (C.c_int, [C.c_void_p]),
     "cb200_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
     "cb200_write_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
+    "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cb200_host_free": (None, [C.c_void_p]),
     "cb200_read_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cb200_read_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cb200_clear": (C.c_int, [C.c_void_p]),

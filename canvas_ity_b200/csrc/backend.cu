@@ -131,6 +131,7 @@ struct cb200_canvas {
     bool resident = false;                    // staged frame came from cb200_frame_upload
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
     cudaEvent_t ev[8];
+    std::vector<cudaEvent_t> chunk_events;
     cb200_stats stats;
     uint64_t launches = 0;
 };
@@ -704,6 +705,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 8; ++i)
         if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
+    for (cudaEvent_t e : cv->chunk_events) cudaEventDestroy(e);
     if (cv->stream) cudaStreamDestroy(cv->stream);
     delete cv;
 }
@@ -776,6 +778,22 @@ static int readback_to_device(cb200_canvas *cv, int width, int height, int x, in
     return CB200_OK;
 }
 
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+void *cb200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
 int cb200_read_rgba8(cb200_canvas *cv, uint8_t *dst, int width, int height, int stride, int x, int y)
 {
     if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
@@ -785,24 +803,51 @@ int cb200_read_rgba8(cb200_canvas *cv, uint8_t *dst, int width, int height, int 
     if (rc != CB200_OK) return rc;
     rc = readback_to_device(cv, width, height, x, y);
     if (rc != CB200_OK) return rc;
-    size_t bytes = 4 * size_t(width) * size_t(height);
-    if (bytes > cv->pinned_rgba8_cap) {
-        if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
-        cv->pinned_rgba8 = nullptr;
-        cv->pinned_rgba8_cap = 0;
-        CK(cudaMallocHost(&cv->pinned_rgba8, bytes));
-        cv->pinned_rgba8_cap = bytes;
+    const size_t row_bytes = 4 * size_t(width), bytes = row_bytes * size_t(height);
+    if (stride >= int(row_bytes) && is_pinned_host(dst)) {
+        // caller's buffer is page-locked: one strided DMA, no staging
+        CK(cudaMemcpy2DAsync(dst, size_t(stride), cv->rgba8.p, row_bytes, row_bytes, size_t(height),
+                             cudaMemcpyDeviceToHost, cv->stream));
+        CK(cudaEventRecord(cv->ev[6], cv->stream));
+        CK(cudaStreamSynchronize(cv->stream));
+    } else {
+        // pageable destination: DMA into pinned staging in chunks and copy each chunk out while the
+        // next one is still in flight
+        if (bytes > cv->pinned_rgba8_cap) {
+            if (cv->pinned_rgba8) cudaFreeHost(cv->pinned_rgba8);
+            cv->pinned_rgba8 = nullptr;
+            cv->pinned_rgba8_cap = 0;
+            CK(cudaMallocHost(&cv->pinned_rgba8, bytes));
+            cv->pinned_rgba8_cap = bytes;
+        }
+        const int rows_per_chunk = std::max(1, int((size_t(4) << 20) / row_bytes));
+        const int n_chunks = (height + rows_per_chunk - 1) / rows_per_chunk;
+        if (int(cv->chunk_events.size()) < n_chunks) {
+            size_t old = cv->chunk_events.size();
+            cv->chunk_events.resize(size_t(n_chunks));
+            for (size_t i = old; i < cv->chunk_events.size(); ++i)
+                CK(cudaEventCreateWithFlags(&cv->chunk_events[i], cudaEventDisableTiming));
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            int r0 = c * rows_per_chunk, rows = std::min(rows_per_chunk, height - r0);
+            CK(cudaMemcpyAsync(cv->pinned_rgba8 + size_t(r0) * row_bytes, cv->rgba8.p + size_t(r0) * row_bytes,
+                               size_t(rows) * row_bytes, cudaMemcpyDeviceToHost, cv->stream));
+            CK(cudaEventRecord(cv->chunk_events[size_t(c)], cv->stream));
+        }
+        CK(cudaEventRecord(cv->ev[6], cv->stream));
+        for (int c = 0; c < n_chunks; ++c) {
+            int r0 = c * rows_per_chunk, rows = std::min(rows_per_chunk, height - r0);
+            CK(cudaEventSynchronize(cv->chunk_events[size_t(c)]));
+            if (stride == int(row_bytes))
+                memcpy(dst + size_t(r0) * row_bytes, cv->pinned_rgba8 + size_t(r0) * row_bytes, size_t(rows) * row_bytes);
+            else
+                for (int row = r0; row < r0 + rows; ++row)
+                    memcpy(dst + ptrdiff_t(row) * stride, cv->pinned_rgba8 + size_t(row) * row_bytes, row_bytes);
+        }
     }
-    CK(cudaMemcpyAsync(cv->pinned_rgba8, cv->rgba8.p, bytes, cudaMemcpyDeviceToHost, cv->stream));
-    CK(cudaEventRecord(cv->ev[6], cv->stream));
-    CK(cudaStreamSynchronize(cv->stream));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, cv->ev[7], cv->ev[6]);
     cv->stats.readback_ms = ms;
-    if (stride == 4 * width) memcpy(dst, cv->pinned_rgba8, bytes);
-    else
-        for (int row = 0; row < height; ++row)
-            memcpy(dst + ptrdiff_t(row) * stride, cv->pinned_rgba8 + size_t(row) * size_t(width) * 4, size_t(width) * 4);
     return CB200_OK;
 }
 

@@ -143,6 +143,11 @@ int cb200_sync(cb200_canvas *canvas);
  * (x, y) is the canvas-space origin of the destination; out-of-canvas = 0. */
 int cb200_read_rgba8(cb200_canvas *canvas, uint8_t *dst, int width, int height,
                      int stride, int x, int y);
+/* Page-locked host memory for image buffers: cb200_read_rgba8 / cb200_write_rgba8 copy
+ * straight between the device and such a buffer (no staging copy).  Any other host
+ * pointer works too, through a chunked, pipelined staging copy. */
+void *cb200_host_alloc(size_t bytes);
+void cb200_host_free(void *ptr);
 /* put_image_data (hpp:3383). */
 int cb200_write_rgba8(cb200_canvas *canvas, const uint8_t *src, int width,
                       int height, int stride, int x, int y);

@@ -170,3 +170,29 @@ def test_queue_overflow_regrow_path(lib):
     env = dict(os.environ, CB200_TEST_SMALL_CAPS="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "BAD 0" in out.stdout, out.stdout + out.stderr
+
+
+def test_readback_paths_agree(lib):
+    """get_image_data into page-locked memory (one DMA) and into pageable memory (chunked staging)
+    return the same bytes, also with a stride and an offset."""
+    size = 300
+    script = H.tiger_script(size, size)
+    h = lib.cv_create(size, size)
+    try:
+        H._run(lib, h, script)
+        a = np.zeros((size, size, 4), np.uint8)
+        lib.cv_get_image_data(h, a.ctypes.data, size, size, 4 * size, 0, 0)
+        ptr = lib.cb200_host_alloc(size * (4 * size + 64))
+        assert ptr
+        b = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(size, 4 * size + 64))
+        b[:] = 7
+        lib.cv_get_image_data(h, ptr, size, size, 4 * size + 64, 0, 0)
+        assert np.array_equal(b[:, :4 * size].reshape(size, size, 4), a)
+        assert (b[:, 4 * size:] == 7).all()
+        c = np.zeros((40, 50, 4), np.uint8)
+        lib.cv_get_image_data(h, c.ctypes.data, 50, 40, 200, 120, 130)
+        assert np.array_equal(c, a[130:170, 120:170])
+        del b
+        lib.cb200_host_free(ptr)
+    finally:
+        lib.cv_destroy(h)
