@@ -478,6 +478,8 @@ int upload_frame(cb200_canvas *cv)
     f.n_static_sources = uint32_t(sf.sources.size());
     f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
     f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p;
+    f.n_opaque_jobs = 0;
+    for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
     f.texels = cv->texels.p;

@@ -1,7 +1,7 @@
 // composite.cu -- K7: tile compositor.  One CTA owns one 32x32 framebuffer tile,
-// keeps its 1024 linear premultiplied float RGBA pixels in registers (4 per
-// thread), replays every job that touches the tile IN SUBMISSION ORDER and stores
-// the tile once.  Per job and pixel it does what the reference does per span
+// split into four independent warps of 8 scanlines; each keeps its 256 linear
+// premultiplied float RGBA pixels in registers (8 per lane), replays every job
+// that touches the tile IN SUBMISSION ORDER and stores its pixels once.  Per job and pixel it does what the reference does per span
 // pixel: coverage from the sorted runs (tile_cov.cuh), paint_pixel (hpp:2265-2377),
 // the 4-bit Porter-Duff mix and the visibility lerp (hpp:2570-2591).  Shadow jobs
 // take their coverage from the blurred plane instead (hpp:2504-2538) and clip jobs
@@ -13,6 +13,8 @@
 // registers.
 #include "frame.cuh"
 #include "tile_cov.cuh"
+
+#include <cstdlib>
 
 namespace cb200 {
 
@@ -126,8 +128,10 @@ __device__ __forceinline__ void blend(float4 &back, rgba fore, uint32_t op, floa
                        vis * a + keep * back.w);
 }
 
-constexpr int kRowsPerThread = kTile * kTile / kBlock;      // 4
-constexpr int kBatch = kBlock / 32;                         // jobs staged in shared memory at a time
+constexpr int kWarpRows = 8;                                 // scanlines of a tile owned by one warp
+constexpr int kTileWarps = kTile / kWarpRows;               // 4 warps per tile
+constexpr int kCompBlock = 32 * kTileWarps;                 // one CTA = one tile = 128 threads
+constexpr int kList = 64;                                   // job list capacity per warp
 
 // Coverage of one tile row from staged row info (see tile_cov.cuh for the global
 // memory variant used by the shadow rasteriser).
@@ -168,168 +172,165 @@ __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t
     return paint_at(f, f.brushes[brush], f.draws[draw].inverse, v2(x, y));
 }
 
-__global__ void __launch_bounds__(kBlock, 3) k_composite(device_frame f, canvas_target t, int sb,
-                                                          int tiles_x, int tile_y0)
+// Per-warp scratch in shared memory.
+struct warp_scratch {
+    comp_rec rec;                       // staged job record (128 B)
+    float back[kTile];                  // staged tile-entry rows: sum carried in from the left ...
+    uint32_t first[kTile];              // ... and first run inside the tile
+    float row_buf[kTile];
+    uint32_t job[kList], te[kList];
+};
+
+// One WARP owns 8 scanlines x 32 pixels of a tile (8 pixels per lane, in registers) and works
+// completely on its own: no block-wide barrier anywhere, so an SM keeps ~20 independent
+// tile-quarters in flight and their dependent loads (job table -> tile entry -> runs) overlap.
+__global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, canvas_target t, int sb,
+                                                          int tiles_x, int tile_y0, int eager_load)
 {
-    __shared__ uint32_t sm[33];
-    __shared__ uint32_t s_job[kBlock], s_te[kBlock];
-    __shared__ int s_start;
-    __shared__ __align__(16) comp_rec s_rec[kBatch];
-    __shared__ float s_back[kBatch][kTile];
-    __shared__ uint32_t s_first[kBatch][kTile];
-    __shared__ float row_buf[kBlock / 32][kTile];
+    __shared__ __align__(16) warp_scratch scratch[kTileWarps];
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_scratch &ws = scratch[warp];
     const int tx = blockIdx.x % tiles_x, ty = tile_y0 + blockIdx.x / tiles_x;
     const int x = tx * kTile + lane;
     const int band_y1 = t.band_y0 + t.band_rows;
-    const bool x_in = x < t.width;
-    const int tile_x0 = tx * kTile, tile_y0p = ty * kTile;
+    const int tile_x0 = tx * kTile;
+    const int row0 = ty * kTile + warp * kWarpRows;          // first scanline of this warp
     const uint32_t n_jobs = h->n_jobs;
+    if (row0 >= band_y1 || row0 + kWarpRows <= t.band_y0) return;
 
-    // Jobs are found through a compact 12-byte-per-job table (tile box + kind/flags word, first tile
-    // entry): one coalesced 8 B load per job and thread instead of the 128 B record.
-    auto box_hits = [&](uint2 box) -> bool {
-        int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
-        int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
-        return tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
-    };
-    auto entry_of = [&](uint2 box, uint32_t te_base) -> uint32_t {
-        int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
-        int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10);
-        return te_base + uint32_t(ty - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
-    };
-
-    // Pass 1 -- occlusion culling: the last job that paints this whole tile with an
-    // opaque solid colour (covered tile entry, source_over/copy, alpha 1, unclipped)
-    // makes every earlier job, and the old framebuffer content, irrelevant.
-    if (threadIdx.x == 0) s_start = -1;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_jobs; base += kBlock) {
-        uint32_t j = base + threadIdx.x;
-        if (j < n_jobs) {
-            uint2 box = f.job_box[j];
-            if ((box.y & JOBBOX_OPAQUE) && box_hits(box) && (f.te_flags[entry_of(box, f.job_te[j])] & TE_COVERED))
-                atomicMax(&s_start, int(j));
-        }
-    }
-    __syncthreads();
-    const int start_job = s_start;
-
-    float4 px[kRowsPerThread];
-    int py[kRowsPerThread];
-    bool live[kRowsPerThread];
+    // The old pixels are requested right away so that their latency overlaps the job search
+    // (they are dropped again if a covering job turns up).
+    float4 px[kWarpRows];
+    bool live[kWarpRows];
 #pragma unroll
-    for (int k = 0; k < kRowsPerThread; ++k) {
-        py[k] = ty * kTile + warp + k * (kBlock / 32);
-        live[k] = x_in && py[k] >= t.band_y0 && py[k] < band_y1;
-        px[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int r = 0; r < kWarpRows; ++r) {
+        int y = row0 + r;
+        live[r] = x < t.width && y >= t.band_y0 && y < band_y1;
+        px[r] = (live[r] && eager_load) ? __ldcs(&t.fb[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)])
+                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    bool loaded = start_job >= 0;              // a covering job replaces the old pixels: nothing to load
-    bool touched = false;
+    bool loaded = eager_load != 0;
     const cov_source cs = make_cov_source(f, sb);
     const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
     unsigned long long painted = 0;
+    bool touched = false;
+    uint32_t n_list = 0;
 
-    // Pass 2 -- replay the surviving jobs in submission order.
-    const uint32_t first_job = start_job < 0 ? 0u : uint32_t(start_job);
-    for (uint32_t base = first_job - first_job % kBlock; base < n_jobs; base += kBlock) {
-        // which of these 256 jobs touch this tile?  (ordered compaction: ballot + per-warp counts)
-        uint32_t j = base + threadIdx.x, te = 0;
-        bool hit = false;
-        if (j < n_jobs && j >= first_job) {
-            uint2 box = f.job_box[j];
-            if (box_hits(box)) {
+    // Replays the jobs collected in ws.job[0 .. n_list) in order.
+    auto flush = [&]() {
+        if (n_list && !loaded) {                          // lazy variant: fetch the old pixels on first use
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r)
+                if (live[r]) px[r] = __ldcs(&t.fb[size_t(row0 + r - t.band_y0) * size_t(t.width) + size_t(x)]);
+            loaded = true;
+        }
+        for (uint32_t q = 0; q < n_list; ++q) {
+            const uint32_t jj = ws.job[q], tte = ws.te[q];
+            // stage the job record and this tile entry's rows: three independent coalesced loads
+            uint32_t word = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
+            const bool has_rows = __shfl_sync(0xffffffffu, word, 0) != JOB_SHADOW;      // word 0 = kind
+            float bk = has_rows ? f.te_backdrop[tte * kTile + lane] : 0.0f;
+            uint32_t fr = has_rows ? f.te_first[tte * kTile + lane] : kNoRun;
+            __syncwarp();
+            reinterpret_cast<uint32_t *>(&ws.rec)[lane] = word;
+            ws.back[lane] = bk;
+            ws.first[lane] = fr;
+            __syncwarp();
+            const comp_rec &c = ws.rec;
+            const float *mask = c.mask_src ? t.mask_planes[c.mask_src] : nullptr;
+            const uint32_t op = c.op;
+            if (c.kind == JOB_SHADOW) {
+                const float *plane = f.planes + (uint64_t(c.plane_hi) << 32 | c.plane_lo);
+                const rgba tint = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
+#pragma unroll
+                for (int r = 0; r < kWarpRows; ++r) {
+                    const int y = row0 + r;
+                    if (!live[r] || x < c.cx0 || x >= c.cx1 || y < c.cy0 || y >= c.cy1) continue;
+                    float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
+                    if (vis < kThreshold) continue;
+                    float s = plane[size_t(y + c.border - c.top) * size_t(c.bw) + size_t(x + c.border - c.left)];
+                    blend(px[r], scale(c.alpha * s, tint), op, vis);
+                    ++painted;
+                }
+                continue;
+            }
+            const bool everywhere = (~op & 8u) != 0;
+            const uint32_t brush_type = c.brush_type;
+            const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
+            const float alpha = c.alpha;
+            float *mask_out = c.kind == JOB_CLIP ? t.mask_planes[c.mask_dst] : nullptr;
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r) {
+                const int ly = warp * kWarpRows + r, y = row0 + r;
+                // warp-uniform: every lane of the warp shares the row
+                float sum = staged_row_sum(cs, ws.back[ly], ws.first[ly], jj, y, tile_x0, ws.row_buf);
+                float cov = fminf(fabsf(sum), 1.0f);
+                if (!live[r]) continue;
+                size_t at = size_t(y - t.band_y0) * size_t(t.width) + size_t(x);
+                float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
+                if (mask_out) { mask_out[at] = cov * vis; continue; }
+                if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
+                rgba paint = brush_type == CB200_BRUSH_COLOR ? flat
+                           : (brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
+                                                  : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f));
+                blend(px[r], scale(cov * alpha, paint), op, vis);
+                ++painted;
+            }
+        }
+        touched = touched || n_list != 0;
+        n_list = 0;
+    };
+
+    // Job search through the compact table (8 B tile box + flags, 4 B first tile entry per job),
+    // 32 candidates per step.  Occlusion culling: a job that paints this whole tile with an opaque
+    // solid colour (covered tile entry, source_over/copy, alpha 1, unclipped -- then cov = vis = 1
+    // replaces the pixel exactly) voids everything collected or painted before it.
+    for (uint32_t base = 0; base < n_jobs; base += 32) {
+        const uint32_t j = base + uint32_t(lane);
+        uint32_t te = 0;
+        bool hit = false, cover = false;
+        if (j < n_jobs) {
+            const uint2 box = f.job_box[j];
+            const int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
+            const int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
+            if (tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1) {
                 if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
                 else {
-                    te = entry_of(box, f.job_te[j]);
-                    hit = (box.y & JOBBOX_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY);
+                    te = f.job_te[j] + uint32_t(ty - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
+                    const uint32_t flags = f.te_flags[te];
+                    hit = (box.y & JOBBOX_EVERYWHERE) || (flags & TE_NONEMPTY);
+                    cover = (box.y & JOBBOX_OPAQUE) && (flags & TE_COVERED);
                 }
             }
         }
         uint32_t votes = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) sm[warp] = __popc(votes);
-        __syncthreads();
-        uint32_t slot = __popc(votes & ((1u << lane) - 1u)), n_hit = 0;
+        const uint32_t covers = __ballot_sync(0xffffffffu, cover);
+        if (covers) {
+            const int last = 31 - __clz(int(covers));
+            votes &= ~((1u << last) - 1u);                   // the covering job itself stays
+            n_list = 0;
+            loaded = true;                                 // the covering job replaces the old pixels
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) {
-            uint32_t c = sm[w];
-            if (w < warp) slot += c;
-            n_hit += c;
+            for (int r = 0; r < kWarpRows; ++r) px[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        if (hit) { s_job[slot] = j; s_te[slot] = te; }
-        __syncthreads();
-        if (n_hit && !loaded) {                   // first job that touches the tile: fetch the old pixels
-#pragma unroll
-            for (int k = 0; k < kRowsPerThread; ++k)
-                if (live[k]) px[k] = t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)];
-            loaded = true;
-        }
-        touched = touched || n_hit != 0;
-
-        for (uint32_t b0 = 0; b0 < n_hit; b0 += kBatch) {
-            // stage up to kBatch jobs: one warp per job fetches its record and the 32
-            // (backdrop, first run) pairs of this tile entry -- all loads in flight at once
-            if (b0 + warp < n_hit) {
-                uint32_t jj = s_job[b0 + warp], tte = s_te[b0 + warp];
-                uint32_t word = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
-                reinterpret_cast<uint32_t *>(&s_rec[warp])[lane] = word;
-                bool has_rows = __shfl_sync(0xffffffffu, word, 0) != JOB_SHADOW;     // word 0 = kind
-                s_back[warp][lane] = has_rows ? f.te_backdrop[tte * kTile + lane] : 0.0f;
-                s_first[warp][lane] = has_rows ? f.te_first[tte * kTile + lane] : kNoRun;
+        if (votes) {
+            if (votes >> lane & 1u) {
+                uint32_t slot = n_list + __popc(votes & ((1u << lane) - 1u));
+                ws.job[slot] = j;
+                ws.te[slot] = te;
             }
-            __syncthreads();
-            const uint32_t n_here = min(uint32_t(kBatch), n_hit - b0);
-            for (uint32_t q = 0; q < n_here; ++q) {
-                const comp_rec &c = s_rec[q];
-                const uint32_t jj = s_job[b0 + q];
-                const float *mask = c.mask_src ? t.mask_planes[c.mask_src] : nullptr;
-                const uint32_t op = c.op;
-                if (c.kind == JOB_SHADOW) {
-                    const float *plane = f.planes + (uint64_t(c.plane_hi) << 32 | c.plane_lo);
-                    const rgba tint = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
-#pragma unroll
-                    for (int k = 0; k < kRowsPerThread; ++k) {
-                        if (!live[k] || x < c.cx0 || x >= c.cx1 || py[k] < c.cy0 || py[k] >= c.cy1) continue;
-                        float vis = mask ? fminf(fabsf(mask[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
-                        if (vis < kThreshold) continue;
-                        float s = plane[size_t(py[k] + c.border - c.top) * size_t(c.bw) + size_t(x + c.border - c.left)];
-                        blend(px[k], scale(c.alpha * s, tint), op, vis);
-                        ++painted;
-                    }
-                    continue;
-                }
-                const bool everywhere = (~op & 8u) != 0;
-                const bool solid = c.brush_type == CB200_BRUSH_COLOR;
-                const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
-                const float alpha = c.alpha;
-                float *mask_out = c.kind == JOB_CLIP ? t.mask_planes[c.mask_dst] : nullptr;
-#pragma unroll
-                for (int k = 0; k < kRowsPerThread; ++k) {
-                    const int ly = warp + k * (kBlock / 32);
-                    // warp-uniform: every lane of the warp shares the row
-                    float sum = staged_row_sum(cs, s_back[q][ly], s_first[q][ly], jj, py[k], tile_x0, row_buf[warp]);
-                    float cov = fminf(fabsf(sum), 1.0f);
-                    if (!live[k]) continue;
-                    size_t at = size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x);
-                    float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
-                    if (mask_out) { mask_out[at] = cov * vis; continue; }
-                    if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
-                    rgba paint = solid ? flat
-                                       : (c.brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
-                                                                : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(py[k]) + 0.5f));
-                    blend(px[k], scale(cov * alpha, paint), op, vis);
-                    ++painted;
-                }
-            }
-            __syncthreads();
+            n_list += __popc(votes);
+            __syncwarp();
+            if (n_list > kList - 32) flush();
         }
     }
-    if (!touched) return;                          // no job reaches this tile: its pixels stay as they are
+    flush();
+    if (!touched) return;                                    // no job reaches these pixels: leave them alone
 #pragma unroll
-    for (int k = 0; k < kRowsPerThread; ++k)
-        if (live[k]) t.fb[size_t(py[k] - t.band_y0) * size_t(t.width) + size_t(x)] = px[k];
+    for (int r = 0; r < kWarpRows; ++r)
+        if (live[r]) t.fb[size_t(row0 + r - t.band_y0) * size_t(t.width) + size_t(x)] = px[r];
     // statistics: composited pixel count of the frame
     for (int off = 16; off; off >>= 1) painted += __shfl_down_sync(0xffffffffu, painted, off);
     if (lane == 0 && painted) atomicAdd(&h->composited_pixels, painted);
@@ -342,7 +343,13 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     int tiles_x = (t.width + kTile - 1) / kTile;
     int ty0 = t.band_y0 / kTile, ty1 = (t.band_y0 + t.band_rows - 1) / kTile;
     int tiles = tiles_x * (ty1 - ty0 + 1);
-    k_composite<<<tiles, kBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0);
+    // Eager: request the old pixels before the job search (hides their latency) -- best when no job
+    // can cover a tile.  Frames with opaque jobs load on first use instead, so tiles that a covering
+    // job overwrites are never read (measured on the tiger: 0.342 vs 0.362 ms).  CB200_EAGER_LOAD=0/1
+    // overrides.
+    int eager = f.n_opaque_jobs == 0;
+    if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
+    k_composite<<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
 }
 
 }  // namespace cb200

@@ -412,6 +412,16 @@ void canvas::host_state::flush()
     }
     ++frames_flushed;
     reset_frame();
+    // Clip-mask planes are immutable device slots; every so often tell the back end which ones
+    // are still reachable (current mask + save stack) so the rest can be freed.
+    if (device && next_mask - masks_at_last_keep >= 16) {
+        std::vector<uint32_t> alive;
+        if (mask) alive.push_back(mask);
+        for (size_t i = 0; i < saves.size(); ++i)
+            if (saves[i].mask) alive.push_back(saves[i].mask);
+        cb200_masks_keep(device, alive.data(), uint32_t(alive.size()));
+        masks_at_last_keep = next_mask;
+    }
 }
 
 // Pool a brush; `which` 0/1/2 = fill/stroke/image lets unchanged brushes be

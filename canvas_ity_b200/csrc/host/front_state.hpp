@@ -85,6 +85,7 @@ struct canvas::host_state {
     path_state path;
     uint32_t mask = 0;               // current clip-mask slot (0 = whole canvas)
     uint32_t next_mask = 1;
+    uint32_t masks_at_last_keep = 1;
     font_state face;
     std::vector<drawing_state> saves;
     uint64_t serial_counter = 1;
