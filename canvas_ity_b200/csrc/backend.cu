@@ -482,6 +482,11 @@ int upload_frame(cb200_canvas *cv)
     for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
+    f.max_shadow_pad = 0; f.max_shadow_radius = 0;
+    for (uint32_t sj : sf.shadow_jobs) {
+        f.max_shadow_pad = std::max(f.max_shadow_pad, int(sf.jobs[sj].pad));
+        f.max_shadow_radius = std::max(f.max_shadow_radius, int(sf.jobs[sj].radius));
+    }
     f.texels = cv->texels.p;
     f.unit_count = cv->unit_count.p; f.unit_offset = cv->unit_offset.p;
     f.pts = cv->pts.p; f.cap_pts = cv->cap_pts; f.pt_loop = cv->pt_loop.p;
@@ -543,7 +548,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
                     ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-                    (sf.shadow_jobs.empty() ? 0 : 7) + 1;
+                    (sf.shadow_jobs.empty() ? 0 : 5) + 1;
     cv->pending = true;
     CK(cudaGetLastError());
     return CB200_OK;

@@ -58,6 +58,7 @@ struct device_frame {
     uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
     float *planes, *planes_tmp;  uint64_t cap_planes;
     uint32_t *shadow_jobs; uint32_t n_shadow_jobs;     // job indices with kind JOB_SHADOW
+    int max_shadow_pad, max_shadow_radius;
     // scratch
     uint32_t *partials;                                // several kGrid-sized slices
     uint32_t *sort_hist;

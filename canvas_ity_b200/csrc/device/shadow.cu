@@ -4,18 +4,17 @@
 //                    canvas space): coverage * paint.alpha -> float plane
 //                    (hpp:2430-2452), coverage rebuilt from the sorted runs exactly
 //                    like the compositor does (tile_cov.cuh)
-//   k_blur_pass      one extended-box pass (Gwosdek et al.) along rows or columns,
-//                    zero outside the working rectangle; three passes per axis
-//                    (hpp:2453-2503).  Each output is the direct windowed sum
+//   k_blur_rows      the three extended-box passes (Gwosdek et al.) of one axis fused in shared
+//                    memory, zero outside the working rectangle (hpp:2453-2503).  Each output is
 //                      (w1+w2) * sum_{|d|<=r} s[i+d] + w1 * (s[i-r-1] + s[i+r+1])
 //                    which is what the reference's running sum maintains.
+//   k_transpose      32x32 tiled transpose so the column passes reuse the row kernel with
+//                    coalesced accesses: rows, transpose, rows, transpose back.
 // The blurred plane is consumed by the tile compositor (composite.cu).
-//
-// Round-1 shape: six streaming passes that ping-pong between two planes through
-// L2; fusing the three passes of an axis in shared memory is the next step for
-// this kernel.
 #include "frame.cuh"
 #include "tile_cov.cuh"
+
+#include <algorithm>
 
 namespace cb200 {
 
@@ -127,31 +126,114 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     }
 }
 
-// grid: (element stride, shadow job); axis 0 = along rows, 1 = along columns
-__global__ void __launch_bounds__(kBlock) k_blur_pass(device_frame f, const float *src_base, float *dst_base,
-                                                       int axis)
+// Three extended-box passes along the rows of a plane, fused: a CTA stages one row in shared
+// memory (zero-padded by r + 1 on both sides, which is exactly the reference's "zero outside the
+// working rectangle"), runs the three passes between two shared buffers and writes the row back --
+// one global read and one global write per pixel for all three passes.  Each thread produces runs
+// of 8 consecutive outputs with a sliding window (direct sum for the first, +new -old for the next
+// seven), so shared-memory traffic is ~3 loads per output per pass.
+// grid: (row stride, shadow job).  `transposed`: the plane is stored bw-major (after k_transpose).
+constexpr int kBlurRun = 8;
+
+// Shared-memory rows are skewed by one word per 32 so that threads walking runs of 8 consecutive
+// pixels (addresses 8c + d) hit 32 different banks instead of 4.
+__device__ __forceinline__ int sk(int i) { return i + (i >> 5); }
+
+// One row by a group of `G` threads (a warp for short rows, the whole CTA for long ones).
+template <int G>
+__device__ __forceinline__ void blur_one_row(const float *in, float *out, int len, int r, float w1, float w12,
+                                             float *buf0, float *buf1, int rank)
 {
+    const int pad = r + 1;
+    auto group_sync = [] { if (G == 32) __syncwarp(); else __syncthreads(); };
+    for (int i = rank; i < len; i += G) buf0[sk(pad + i)] = in[i];
+    group_sync();
+    float *from = buf0, *to = buf1;
+    const int runs = (len + kBlurRun - 1) / kBlurRun;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int c = rank; c < runs; c += G) {
+            const int at = pad + c * kBlurRun;                   // buffer index of this run's first pixel
+            float inner = 0.0f;
+            for (int d = -r; d <= r; ++d) inner += from[sk(at + d)];
+#pragma unroll
+            for (int k = 0; k < kBlurRun; ++k) {
+                if (c * kBlurRun + k < len) {
+                    float lead = from[sk(at + k + r + 1)];
+                    to[sk(at + k)] = w12 * inner + w1 * (from[sk(at + k - r - 1)] + lead);
+                    inner += lead - from[sk(at + k - r)];
+                }
+            }
+        }
+        group_sync();
+        float *t = from; from = to; to = t;
+    }
+    for (int i = rank; i < len; i += G) out[i] = from[sk(pad + i)];
+    group_sync();
+}
+
+__global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const float *src_base, float *dst_base,
+                                                       int transposed, int smem_floats)
+{
+    extern __shared__ float blur_smem[];
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const job_rec &jr = f.jobs[f.shadow_jobs[blockIdx.y]];
-    const size_t n = size_t(jr.bw) * size_t(jr.bh);
+    const int len = transposed ? jr.bh : jr.bw, rows = transposed ? jr.bw : jr.bh;
+    const int r = jr.radius, pad = r + 1;
+    if (len <= 0 || rows <= 0) return;
+    const int stride = sk(len + 2 * pad) + 1;
+    const float w1 = jr.w1, w12 = jr.w1 + jr.w2;
     const float *src = src_base + jr.plane_offset;
     float *dst = dst_base + jr.plane_offset;
-    const int r = jr.radius, bw = jr.bw, bh = jr.bh;
-    const float w1 = jr.w1, w12 = jr.w1 + jr.w2;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int x = int(i % size_t(bw)), y = int(i / size_t(bw));
-        int at = axis ? y : x, len = axis ? bh : bw;
-        size_t step = axis ? size_t(bw) : 1;
-        const float *line = src + (axis ? size_t(x) : size_t(y) * size_t(bw));
-        float inner = 0.0f;
-        int lo = max(at - r, 0), hi = min(at + r, len - 1);
-        for (int k = lo; k <= hi; ++k) inner += line[size_t(k) * step];
-        float outer = 0.0f;
-        if (at - r - 1 >= 0) outer += line[size_t(at - r - 1) * step];
-        if (at + r + 1 < len) outer += line[size_t(at + r + 1) * step];
-        dst[i] = w12 * inner + w1 * outer;
+    constexpr int kWarpsPerCta = kBlock / 32;
+    if (2 * stride * kWarpsPerCta <= smem_floats) {
+        // short rows: every warp blurs its own row, eight rows per CTA in flight
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (int(blockIdx.x) * kWarpsPerCta >= rows) return;
+        float *buf0 = blur_smem + size_t(warp) * 2 * stride, *buf1 = buf0 + stride;
+        for (int i = lane; i < 2 * stride; i += 32) buf0[i] = 0.0f;
+        __syncwarp();
+        for (int row = blockIdx.x * kWarpsPerCta + warp; row < rows; row += gridDim.x * kWarpsPerCta)
+            blur_one_row<32>(src + size_t(row) * size_t(len), dst + size_t(row) * size_t(len), len, r, w1, w12,
+                             buf0, buf1, lane);
+        return;
+    }
+    if (2 * stride > smem_floats || int(blockIdx.x) >= rows) return;      // host sized smem for the largest row
+    float *buf0 = blur_smem, *buf1 = blur_smem + stride;
+    for (int i = threadIdx.x; i < 2 * stride; i += kBlock) buf0[i] = 0.0f;
+    __syncthreads();
+    for (int row = blockIdx.x; row < rows; row += gridDim.x)
+        blur_one_row<kBlock>(src + size_t(row) * size_t(len), dst + size_t(row) * size_t(len), len, r, w1, w12,
+                             buf0, buf1, threadIdx.x);
+}
+
+// 32x32 tiled transpose of every shadow plane (bh x bw -> bw x bh or back), grid: (tile stride, job)
+__global__ void __launch_bounds__(kBlock) k_transpose(device_frame f, const float *src_base, float *dst_base,
+                                                       int back)
+{
+    __shared__ float tile[32][33];
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    const job_rec &jr = f.jobs[f.shadow_jobs[blockIdx.y]];
+    const int sw = back ? jr.bh : jr.bw, sh = back ? jr.bw : jr.bh;   // source is sh rows of sw
+    if (sw <= 0 || sh <= 0) return;
+    const float *src = src_base + jr.plane_offset;
+    float *dst = dst_base + jr.plane_offset;
+    const int tiles_x = (sw + 31) / 32, tiles_y = (sh + 31) / 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;             // 32 x 8 threads
+    for (int tl = blockIdx.x; tl < tiles_x * tiles_y; tl += gridDim.x) {
+        const int x0 = (tl % tiles_x) * 32, y0 = (tl / tiles_x) * 32;
+        for (int k = ly; k < 32; k += 8) {
+            int x = x0 + lx, y = y0 + k;
+            tile[k][lx] = (x < sw && y < sh) ? src[size_t(y) * size_t(sw) + size_t(x)] : 0.0f;
+        }
+        __syncthreads();
+        for (int k = ly; k < 32; k += 8) {
+            int x = y0 + lx, y = x0 + k;                                  // destination is sw rows of sh
+            if (x < sh && y < sw) dst[size_t(y) * size_t(sh) + size_t(x)] = tile[lx][k];
+        }
+        __syncthreads();
     }
 }
 
@@ -159,19 +241,26 @@ __global__ void __launch_bounds__(kBlock) k_blur_pass(device_frame f, const floa
 
 void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
 {
-    (void)t;
     if (!f.n_shadow_jobs) return;
     dim3 grid(64, f.n_shadow_jobs);
     k_shadow_raster<<<grid, kBlock, 0, s>>>(f, sorted_buffer);
-    dim3 bgrid(128, f.n_shadow_jobs);
-    const float *src = f.planes;
-    float *dst = f.planes_tmp;
-    for (int pass = 0; pass < 6; ++pass) {
-        k_blur_pass<<<bgrid, kBlock, 0, s>>>(f, src, dst, pass >= 3 ? 1 : 0);
-        const float *was = src;
-        src = dst;
-        dst = const_cast<float *>(was);
+    // rows -> transpose -> rows (= columns) -> transpose back; the result ends up in f.planes
+    const int longest = std::max(t.width, t.height) + f.max_shadow_pad;
+    // room for one longest row (CTA mode) and for eight rows of up to 512 pixels (warp mode)
+    const int pad2 = 2 * (f.max_shadow_radius + 1);
+    auto skewed = [](int n) { return n + (n >> 5) + 1; };
+    const int smem_floats = std::max(2 * skewed(longest + pad2), 16 * skewed(std::min(longest, 512) + pad2));
+    const size_t smem_bytes = size_t(smem_floats) * sizeof(float);
+    static size_t configured = 0;
+    if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
+        cudaFuncSetAttribute(k_blur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+        configured = smem_bytes;
     }
+    dim3 rgrid(256, f.n_shadow_jobs), tgrid(128, f.n_shadow_jobs);
+    k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 0, smem_floats);
+    k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 0);
+    k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 1, smem_floats);
+    k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 1);
 }
 
 }  // namespace cb200
