@@ -61,6 +61,10 @@ SIGNATURES = {
     "cb200_canvas_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cb200_canvas_create_band": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_void_p)]),
     "cb200_canvas_destroy": (None, [C.c_void_p]),
+    "cb200_batch_create": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_void_p)]),
+    "cb200_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cb200_batch_read_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p] + [C.c_int] * 5),
+    "cb200_batch_read_f32": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cb200_submit": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_upload": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_replay": (C.c_int, [C.c_void_p, C.c_int]),
@@ -93,6 +97,13 @@ SIGNATURES = {
     "cv_is_point_in_path": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "cv_measure_text": (C.c_float, [C.c_void_p, C.c_char_p]),
     "cv_flush": (C.c_int, [C.c_void_p]),
+    "cv_batch_create": (C.c_void_p, [C.c_int] * 4),
+    "cv_batch_canvas": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "cv_batch_flush": (C.c_int, [C.c_void_p]),
+    "cv_batch_get_image_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5),
+    "cv_batch_read_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cv_batch_device": (C.c_void_p, [C.c_void_p]),
+    "cv_batch_destroy": (None, [C.c_void_p]),
     "cv_read_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cv_device": (C.c_void_p, [C.c_void_p]),
     "cv_last_error": (C.c_char_p, []),

@@ -76,6 +76,7 @@ struct staged_frame {
     std::vector<uint32_t> shadow_jobs;
     std::vector<uint8_t> texels_u8;
     std::vector<float *> mask_table;
+    std::vector<uint2> canvas_jobs;              // per canvas: first job, job count
     uint64_t n_texels = 0;
     int key_bits = 0, bits_x = 0, bits_y = 0;
     uint32_t n_dash_subpath_cap = 0;
@@ -93,6 +94,9 @@ int bits_for(uint32_t max_value)
 
 struct cb200_canvas {
     int device = 0, width = 0, height = 0, band_y0 = 0, band_rows = 0;
+    int n_canvases = 1, slot_rows = 0;        // batch: canvases stacked vertically, slot_rows (multiple of 32) apart
+    std::map<uint32_t, std::map<uint32_t, uint32_t> > batch_masks;   // canvas -> local clip slot -> batch slot
+    uint32_t next_batch_mask = 1;
     cudaStream_t stream = nullptr;
     float4 *fb = nullptr;
     std::map<uint32_t, float *> masks;
@@ -138,6 +142,8 @@ struct cb200_canvas {
 
 namespace {
 
+size_t fb_rows(const cb200_canvas *cv) { return cv->n_canvases > 1 ? size_t(cv->n_canvases) * size_t(cv->slot_rows) : size_t(cv->band_rows); }
+
 // ---------------------------------------------------------------- staging ----
 
 // Extended-box blur parameters of one draw, hpp:2402-2405, 2453-2459.
@@ -156,144 +162,183 @@ void blur_params(float blur, int &radius, int &border, float &w1, float &w2)
 
 affine to_affine(const float *m) { affine a = { m[0], m[1], m[2], m[3], m[4], m[5] }; return a; }
 
-int stage_frame(cb200_canvas *cv, const cb200_frame *in, staged_frame &sf)
+// Translate one or more lowered frames (one per canvas of a batch, canvas indices ascending)
+// into the device records of ONE device frame.  Indices of later frames are rebased onto the
+// shared pools; clip-mask slots are renamed to batch-wide slots.
+int stage_frames(cb200_canvas *cv, const cb200_frame *const *frames, const uint32_t *canvas_index,
+                 uint32_t n_frames, staged_frame &sf)
 {
     sf = staged_frame();
-    if (in->n_draws && !in->draws) return fail(CB200_ERR_BAD_ARG, "frame.draws is null");
-    sf.draws.resize(in->n_draws);
-    sf.subpaths.resize(in->n_subpaths);
-    sf.draw_src.assign(in->n_draws, make_uint2(0, 0));
-    for (uint32_t s = 0; s < in->n_subpaths; ++s) {
-        const cb200_subpath &sp = in->subpaths[s];
-        if (uint64_t(sp.first_point) + 1 + 3ull * sp.n_cubics > in->n_points)
-            return fail(CB200_ERR_BAD_ARG, "subpath points out of range");
-        subpath_rec r = { sp.first_point, sp.n_cubics, sp.closed, 0xffffffffu, 0 };
-        sf.subpaths[s] = r;
-    }
+    sf.canvas_jobs.assign(size_t(cv->n_canvases), make_uint2(0, 0));
     int max_pad = 0;
-    for (uint32_t i = 0; i < in->n_draws; ++i) {
-        const cb200_draw &d = in->draws[i];
-        if (uint64_t(d.first_subpath) + d.n_subpaths > in->n_subpaths)
-            return fail(CB200_ERR_BAD_ARG, "draw subpaths out of range");
-        if (d.kind != CB200_CLIP && d.brush >= in->n_brushes) return fail(CB200_ERR_BAD_ARG, "draw brush out of range");
-        if (uint64_t(d.first_dash) + d.n_dash > in->n_dashes) return fail(CB200_ERR_BAD_ARG, "draw dashes out of range");
-        draw_rec r;
-        memset(&r, 0, sizeof r);
-        r.kind = d.kind; r.op = d.op;
-        r.first_subpath = d.first_subpath; r.n_subpaths = d.n_subpaths;
-        r.brush = d.brush; r.mask_src = d.mask_src; r.mask_dst = d.mask_dst;
-        r.cap = d.cap; r.join = d.join;
-        r.first_dash = d.first_dash; r.n_dash = d.kind == CB200_STROKE ? d.n_dash : 0;
-        r.dash_offset = d.dash_offset; r.global_alpha = d.global_alpha;
-        r.line_width = d.line_width; r.miter_limit = d.miter_limit;
-        r.forward = to_affine(d.forward); r.inverse = to_affine(d.inverse);
-        memcpy(r.shadow_color, d.shadow_color, sizeof r.shadow_color);
-        r.shadow_dx = d.shadow_offset_x; r.shadow_dy = d.shadow_offset_y; r.shadow_blur = d.shadow_blur;
-        r.angular = d.kind == CB200_STROKE ? stroke_angular(d.line_width) : -1.0f;
-        r.first_unit = uint32_t(sf.units.size());
-        for (uint32_t s = 0; s < d.n_subpaths; ++s) {
-            subpath_rec &sp = sf.subpaths[d.first_subpath + s];
-            if (sp.draw != 0xffffffffu) return fail(CB200_ERR_BAD_ARG, "subpath shared by two draws");
-            sp.draw = i;
-            sp.first_unit = uint32_t(sf.units.size());
-            for (uint32_t k = 0; k <= sp.n_cubics; ++k) {
-                unit_rec u = { d.first_subpath + s, k };
-                sf.units.push_back(u);
-            }
+    uint32_t last_canvas = 0;
+    for (uint32_t fi = 0; fi < n_frames; ++fi) {
+        const cb200_frame *in = frames[fi];
+        const uint32_t canvas = canvas_index ? canvas_index[fi] : 0;
+        if (!in) return fail(CB200_ERR_BAD_ARG, "null frame");
+        if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
+        if (fi && canvas <= last_canvas) return fail(CB200_ERR_BAD_ARG, "batch frames must have ascending canvas indices");
+        last_canvas = canvas;
+        if (in->n_draws && !in->draws) return fail(CB200_ERR_BAD_ARG, "frame.draws is null");
+        const uint32_t draw_base = uint32_t(sf.draws.size()), sub_base = uint32_t(sf.subpaths.size());
+        const uint32_t pt_base = uint32_t(sf.points.size() / 2), brush_base = uint32_t(sf.brushes.size());
+        const uint32_t color_base = uint32_t(sf.stops.size()), dash_base = uint32_t(sf.dashes.size());
+        const uint32_t job_base = uint32_t(sf.jobs.size());
+        sf.draws.resize(draw_base + in->n_draws);
+        sf.subpaths.resize(sub_base + in->n_subpaths);
+        sf.draw_src.resize(draw_base + in->n_draws, make_uint2(0, 0));
+        for (uint32_t s = 0; s < in->n_subpaths; ++s) {
+            const cb200_subpath &sp = in->subpaths[s];
+            if (uint64_t(sp.first_point) + 1 + 3ull * sp.n_cubics > in->n_points)
+                return fail(CB200_ERR_BAD_ARG, "subpath points out of range");
+            subpath_rec r = { pt_base + sp.first_point, sp.n_cubics, sp.closed, 0xffffffffu, 0 };
+            sf.subpaths[sub_base + s] = r;
         }
-        r.n_units = uint32_t(sf.units.size()) - r.first_unit;
-        // stroke sources: un-dashed strokes list their subpaths now, dashed ones are
-        // appended on the device by K2
-        if (d.kind == CB200_STROKE) {
-            if (r.n_dash) {
-                for (uint32_t s = 0; s < d.n_subpaths; ++s) {
-                    dash_item it = { d.first_subpath + s, (s == 0 ? 1u : 0u) | (s + 1 == d.n_subpaths ? 2u : 0u) };
-                    sf.dash_items.push_back(it);
+        std::map<uint32_t, uint32_t> *slots = cv->n_canvases > 1 ? &cv->batch_masks[canvas] : nullptr;
+        auto global_slot = [&](uint32_t local, bool define) -> uint32_t {
+            if (!slots || local == 0) return local;
+            if (define) return (*slots)[local] = cv->next_batch_mask++;
+            std::map<uint32_t, uint32_t>::iterator it = slots->find(local);
+            return it == slots->end() ? 0xffffffffu : it->second;
+        };
+        for (uint32_t i = 0; i < in->n_draws; ++i) {
+            const cb200_draw &d = in->draws[i];
+            const uint32_t di = draw_base + i;
+            if (uint64_t(d.first_subpath) + d.n_subpaths > in->n_subpaths)
+                return fail(CB200_ERR_BAD_ARG, "draw subpaths out of range");
+            if (d.kind != CB200_CLIP && d.brush >= in->n_brushes) return fail(CB200_ERR_BAD_ARG, "draw brush out of range");
+            if (uint64_t(d.first_dash) + d.n_dash > in->n_dashes) return fail(CB200_ERR_BAD_ARG, "draw dashes out of range");
+            draw_rec r;
+            memset(&r, 0, sizeof r);
+            r.kind = d.kind; r.op = d.op;
+            r.first_subpath = sub_base + d.first_subpath; r.n_subpaths = d.n_subpaths;
+            r.brush = brush_base + d.brush;
+            r.mask_src = global_slot(d.mask_src, false);
+            if (r.mask_src == 0xffffffffu) return fail(CB200_ERR_BAD_ARG, "draw reads a clip-mask slot that was never written");
+            r.mask_dst = d.kind == CB200_CLIP ? global_slot(d.mask_dst, true) : 0;
+            r.cap = d.cap; r.join = d.join;
+            r.first_dash = dash_base + d.first_dash; r.n_dash = d.kind == CB200_STROKE ? d.n_dash : 0;
+            r.dash_offset = d.dash_offset; r.global_alpha = d.global_alpha;
+            r.line_width = d.line_width; r.miter_limit = d.miter_limit;
+            r.forward = to_affine(d.forward); r.inverse = to_affine(d.inverse);
+            memcpy(r.shadow_color, d.shadow_color, sizeof r.shadow_color);
+            r.shadow_dx = d.shadow_offset_x; r.shadow_dy = d.shadow_offset_y; r.shadow_blur = d.shadow_blur;
+            r.angular = d.kind == CB200_STROKE ? stroke_angular(d.line_width) : -1.0f;
+            r.canvas = canvas;
+            r.first_unit = uint32_t(sf.units.size());
+            for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+                subpath_rec &sp = sf.subpaths[sub_base + d.first_subpath + s];
+                if (sp.draw != 0xffffffffu) return fail(CB200_ERR_BAD_ARG, "subpath shared by two draws");
+                sp.draw = di;
+                sp.first_unit = uint32_t(sf.units.size());
+                for (uint32_t k = 0; k <= sp.n_cubics; ++k) {
+                    unit_rec u = { sub_base + d.first_subpath + s, k };
+                    sf.units.push_back(u);
                 }
             }
-        }
-        sf.draws[i] = r;
-        // jobs in composite order: shadow (if any) before the draw itself
-        bool shadow = d.kind != CB200_CLIP && d.shadow_color[3] != 0.0f &&
-                      (d.shadow_blur != 0.0f || d.shadow_offset_x != 0.0f || d.shadow_offset_y != 0.0f);
-        if (shadow) {
+            r.n_units = uint32_t(sf.units.size()) - r.first_unit;
+            // stroke sources: un-dashed strokes list their subpaths now, dashed ones are
+            // appended on the device by K2
+            if (d.kind == CB200_STROKE && r.n_dash)
+                for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+                    dash_item it = { sub_base + d.first_subpath + s, (s == 0 ? 1u : 0u) | (s + 1 == d.n_subpaths ? 2u : 0u) };
+                    sf.dash_items.push_back(it);
+                }
+            sf.draws[di] = r;
+            // jobs in composite order: shadow (if any) before the draw itself
+            bool shadow = d.kind != CB200_CLIP && d.shadow_color[3] != 0.0f &&
+                          (d.shadow_blur != 0.0f || d.shadow_offset_x != 0.0f || d.shadow_offset_y != 0.0f);
+            if (shadow) {
+                job_rec j;
+                memset(&j, 0, sizeof j);
+                j.draw = di; j.kind = JOB_SHADOW; j.canvas = canvas;
+                blur_params(d.shadow_blur, j.radius, j.border, j.w1, j.w2);
+                j.off_x = static_cast<float>(j.border) + d.shadow_offset_x;
+                j.off_y = static_cast<float>(j.border) + d.shadow_offset_y;
+                j.pad = 2 * j.border;
+                max_pad = std::max(max_pad, j.pad);
+                sf.shadow_jobs.push_back(uint32_t(sf.jobs.size()));
+                sf.jobs.push_back(j);
+            }
             job_rec j;
             memset(&j, 0, sizeof j);
-            j.draw = i; j.kind = JOB_SHADOW;
-            blur_params(d.shadow_blur, j.radius, j.border, j.w1, j.w2);
-            j.off_x = static_cast<float>(j.border) + d.shadow_offset_x;
-            j.off_y = static_cast<float>(j.border) + d.shadow_offset_y;
-            j.pad = 2 * j.border;
-            max_pad = std::max(max_pad, j.pad);
-            sf.shadow_jobs.push_back(uint32_t(sf.jobs.size()));
+            j.draw = di; j.canvas = canvas;
+            j.kind = d.kind == CB200_CLIP ? JOB_CLIP : JOB_MAIN;
+            // occlusion-culling candidate: where its coverage is exactly 1 this draw REPLACES the pixel
+            // (hpp:2583-2591 with cov = vis = 1): solid colour, unclipped, and either source_copy or
+            // source_over with global_alpha == colour alpha == 1
+            if (j.kind == JOB_MAIN && d.mask_src == 0 && in->brushes[d.brush].type == CB200_BRUSH_COLOR &&
+                in->brushes[d.brush].n_colors == 1) {
+                float a = in->colors[4 * size_t(in->brushes[d.brush].first_color) + 3];
+                if (d.op == 2u || (d.op == 14u && d.global_alpha == 1.0f && a == 1.0f)) j.opaque = 1;
+            }
             sf.jobs.push_back(j);
         }
-        job_rec j;
-        memset(&j, 0, sizeof j);
-        j.draw = i;
-        j.kind = d.kind == CB200_CLIP ? JOB_CLIP : JOB_MAIN;
-        // occlusion-culling candidate: where its coverage is exactly 1 this draw REPLACES the pixel
-        // (hpp:2583-2591 with cov = vis = 1): solid colour, unclipped, and either source_copy or
-        // source_over with global_alpha == colour alpha == 1
-        if (j.kind == JOB_MAIN && d.mask_src == 0 && in->brushes[d.brush].type == CB200_BRUSH_COLOR &&
-            in->brushes[d.brush].n_colors == 1) {
-            float a = in->colors[4 * size_t(in->brushes[d.brush].first_color) + 3];
-            if (d.op == 2u || (d.op == 14u && d.global_alpha == 1.0f && a == 1.0f)) j.opaque = 1;
+        sf.canvas_jobs[canvas] = make_uint2(job_base, uint32_t(sf.jobs.size()) - job_base);
+        // static stroke sources, grouped by draw (keeps every draw's K3 output contiguous)
+        for (uint32_t i = 0; i < in->n_draws; ++i) {
+            const cb200_draw &d = in->draws[i];
+            const uint32_t di = draw_base + i;
+            if (d.kind != CB200_STROKE || sf.draws[di].n_dash) continue;
+            sf.draw_src[di].x = uint32_t(sf.sources.size());
+            for (uint32_t s = 0; s < d.n_subpaths; ++s) {
+                stroke_src src = { sub_base + d.first_subpath + s,
+                                   di | (in->subpaths[d.first_subpath + s].closed ? 0x80000000u : 0u) };
+                sf.sources.push_back(src);
+            }
+            sf.draw_src[di].y = uint32_t(sf.sources.size());
         }
-        sf.jobs.push_back(j);
-    }
-    // static stroke sources, grouped by draw (keeps every draw's K3 output contiguous)
-    for (uint32_t i = 0; i < in->n_draws; ++i) {
-        const cb200_draw &d = in->draws[i];
-        if (d.kind != CB200_STROKE || sf.draws[i].n_dash) continue;
-        sf.draw_src[i].x = uint32_t(sf.sources.size());
-        for (uint32_t s = 0; s < d.n_subpaths; ++s) {
-            stroke_src src = { d.first_subpath + s, i | (in->subpaths[d.first_subpath + s].closed ? 0x80000000u : 0u) };
-            sf.sources.push_back(src);
+        if (in->n_points) sf.points.insert(sf.points.end(), in->points, in->points + 2 * size_t(in->n_points));
+        if (in->n_colors) {
+            sf.colors.insert(sf.colors.end(), in->colors, in->colors + 4 * size_t(in->n_colors));
+            sf.stops.insert(sf.stops.end(), in->stops, in->stops + in->n_colors);
         }
-        sf.draw_src[i].y = uint32_t(sf.sources.size());
+        if (in->n_dashes) sf.dashes.insert(sf.dashes.end(), in->dashes, in->dashes + in->n_dashes);
+        // brushes; pattern images are converted to float4 texels on the device
+        std::vector<uint64_t> image_texel_base(in->n_images);
+        for (uint32_t k = 0; k < in->n_images; ++k) {
+            const cb200_image &im = in->images[k];
+            if (im.width <= 0 || im.height <= 0 ||
+                im.texel_offset + 4ull * uint64_t(im.width) * uint64_t(im.height) > in->texel_bytes)
+                return fail(CB200_ERR_BAD_ARG, "image out of range");
+            image_texel_base[k] = sf.n_texels;
+            size_t bytes = 4 * size_t(im.width) * size_t(im.height);
+            sf.texels_u8.insert(sf.texels_u8.end(), in->texels + im.texel_offset, in->texels + im.texel_offset + bytes);
+            sf.n_texels += uint64_t(im.width) * uint64_t(im.height);
+        }
+        sf.brushes.resize(brush_base + in->n_brushes);
+        for (uint32_t k = 0; k < in->n_brushes; ++k) {
+            const cb200_brush &b = in->brushes[k];
+            brush_rec r;
+            memset(&r, 0, sizeof r);
+            r.type = b.type; r.flags = b.flags; r.first_color = color_base + b.first_color; r.n_colors = b.n_colors;
+            r.sx = b.start[0]; r.sy = b.start[1]; r.ex = b.end[0]; r.ey = b.end[1];
+            r.r0 = b.start_radius; r.r1 = b.end_radius; r.repetition = b.repetition;
+            if (b.type == CB200_BRUSH_PATTERN) {
+                if (b.image >= in->n_images) return fail(CB200_ERR_BAD_ARG, "brush image out of range");
+                r.width = in->images[b.image].width;
+                r.height = in->images[b.image].height;
+                r.texel_offset = image_texel_base[b.image];
+                r.n_colors = 1;
+            } else if (uint64_t(b.first_color) + b.n_colors > in->n_colors)
+                return fail(CB200_ERR_BAD_ARG, "brush colours out of range");
+            sf.brushes[brush_base + k] = r;
+        }
     }
-    sf.points.assign(in->points, in->points + 2 * size_t(in->n_points));
-    sf.colors.assign(in->colors, in->colors + 4 * size_t(in->n_colors));
-    sf.stops.assign(in->stops, in->stops + in->n_colors);
-    sf.dashes.assign(in->dashes, in->dashes + in->n_dashes);
-    // brushes; pattern images are converted to float4 texels on the device
-    std::vector<uint64_t> image_texel_base(in->n_images);
-    for (uint32_t k = 0; k < in->n_images; ++k) {
-        const cb200_image &im = in->images[k];
-        if (im.width <= 0 || im.height <= 0 ||
-            im.texel_offset + 4ull * uint64_t(im.width) * uint64_t(im.height) > in->texel_bytes)
-            return fail(CB200_ERR_BAD_ARG, "image out of range");
-        image_texel_base[k] = sf.n_texels;
-        size_t bytes = 4 * size_t(im.width) * size_t(im.height);
-        sf.texels_u8.insert(sf.texels_u8.end(), in->texels + im.texel_offset, in->texels + im.texel_offset + bytes);
-        sf.n_texels += uint64_t(im.width) * uint64_t(im.height);
-    }
-    sf.brushes.resize(in->n_brushes);
-    for (uint32_t k = 0; k < in->n_brushes; ++k) {
-        const cb200_brush &b = in->brushes[k];
-        brush_rec r;
-        memset(&r, 0, sizeof r);
-        r.type = b.type; r.flags = b.flags; r.first_color = b.first_color; r.n_colors = b.n_colors;
-        r.sx = b.start[0]; r.sy = b.start[1]; r.ex = b.end[0]; r.ey = b.end[1];
-        r.r0 = b.start_radius; r.r1 = b.end_radius; r.repetition = b.repetition;
-        if (b.type == CB200_BRUSH_PATTERN) {
-            if (b.image >= in->n_images) return fail(CB200_ERR_BAD_ARG, "brush image out of range");
-            r.width = in->images[b.image].width;
-            r.height = in->images[b.image].height;
-            r.texel_offset = image_texel_base[b.image];
-            r.n_colors = 1;
-        } else if (uint64_t(b.first_color) + b.n_colors > in->n_colors)
-            return fail(CB200_ERR_BAD_ARG, "brush colours out of range");
-        sf.brushes[k] = r;
-    }
-    // sort key layout: job | y | x
+    if (cv->n_canvases == 1) sf.canvas_jobs[0] = make_uint2(0, uint32_t(sf.jobs.size()));
+    // sort key layout: job | y | x   (y, x local to the job's canvas)
     sf.bits_x = bits_for(uint32_t(cv->width + max_pad + 1));
     sf.bits_y = bits_for(uint32_t(cv->height + max_pad + 1));
     sf.key_bits = sf.bits_x + sf.bits_y + bits_for(uint32_t(sf.jobs.size()));
     if (sf.key_bits > 64) return fail(CB200_ERR_BAD_ARG, "too many jobs for the sort key");
     sf.valid = true;
     return CB200_OK;
+}
+
+int stage_frame(cb200_canvas *cv, const cb200_frame *in, staged_frame &sf)
+{
+    if (cv->n_canvases != 1) return fail(CB200_ERR_BAD_ARG, "use cb200_batch_submit on a batch");
+    return stage_frames(cv, &in, nullptr, 1, sf);
 }
 
 // ------------------------------------------------------------ capacities ----
@@ -407,7 +452,7 @@ int upload_frame(cb200_canvas *cv)
         max_slot = std::max(max_slot, std::max(d.mask_src, d.mask_dst));
         if (d.kind == CB200_CLIP && !cv->masks.count(d.mask_dst)) {
             float *p = nullptr;
-            CK(cudaMalloc(&p, sizeof(float) * size_t(cv->width) * size_t(cv->band_rows)));
+            CK(cudaMalloc(&p, sizeof(float) * size_t(cv->width) * size_t(cv->band_rows)));   // per canvas
             cv->masks[d.mask_dst] = p;
         }
     }
@@ -440,6 +485,7 @@ int upload_frame(cb200_canvas *cv)
     size_t o_ditems = place(plan, at, sf.dash_items), o_dsrc = place(plan, at, sf.draw_src);
     size_t o_jobs = place(plan, at, sf.jobs), o_sjobs = place(plan, at, sf.shadow_jobs);
     size_t o_masks = place(plan, at, sf.mask_table), o_tex = place(plan, at, sf.texels_u8);
+    size_t o_cjobs = place(plan, at, sf.canvas_jobs);
     size_t o_src = place(plan, at, sf.sources);
 
     if (at > cv->pinned_cap) {
@@ -514,6 +560,9 @@ int upload_frame(cb200_canvas *cv)
     t.band_y0 = cv->band_y0; t.band_rows = cv->band_rows;
     t.mask_planes = reinterpret_cast<float **>(b + o_masks);
     t.n_masks = uint32_t(sf.mask_table.size());
+    t.n_canvases = cv->n_canvases;
+    t.slot_rows = cv->n_canvases > 1 ? cv->slot_rows : cv->band_rows;
+    t.canvas_jobs = reinterpret_cast<uint2 *>(b + o_cjobs);
 
     if (sf.n_texels) {
         launch_texel_convert(b + o_tex, cv->texels.p, sf.n_texels, cv->stream);
@@ -650,6 +699,8 @@ int cb200_device_count(void)
 
 const char *cb200_last_error(void) { return g_error.c_str(); }
 
+static thread_local int g_batch_n = 1;       // consumed by cb200_canvas_create_band (set by cb200_batch_create)
+
 int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, int device, cb200_canvas **out)
 {
     if (!out) return fail(CB200_ERR_BAD_ARG, "out is null");
@@ -669,9 +720,11 @@ int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, 
     cb200_canvas *cv = new cb200_canvas;
     cv->device = device; cv->width = width; cv->height = height;
     cv->band_y0 = band_y0; cv->band_rows = band_rows;
+    cv->n_canvases = g_batch_n;
+    cv->slot_rows = (height + kTile - 1) / kTile * kTile;
     memset(&cv->stats, 0, sizeof cv->stats);
     cudaError_t err = cudaStreamCreateWithFlags(&cv->stream, cudaStreamNonBlocking);
-    size_t px = size_t(width) * size_t(band_rows);
+    size_t px = size_t(width) * fb_rows(cv);
     if (err == cudaSuccess) err = cudaMalloc(&cv->fb, px * sizeof(float4));
     if (err == cudaSuccess) err = cudaMemsetAsync(cv->fb, 0, px * sizeof(float4), cv->stream);
     if (err == cudaSuccess) err = cudaMallocHost(&cv->pinned_hdr, sizeof(frame_header));
@@ -682,6 +735,69 @@ int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, 
         return fail(err == cudaErrorMemoryAllocation ? CB200_ERR_OOM : CB200_ERR_CUDA, "canvas create: " + why);
     }
     *out = cv;
+    return CB200_OK;
+}
+
+int cb200_batch_create(int n_canvases, int width, int height, int device, cb200_canvas **out)
+{
+    if (n_canvases < 1 || n_canvases > (1 << 22)) return fail(CB200_ERR_BAD_ARG, "batch size must be 1..4194304");
+    g_batch_n = n_canvases;
+    int rc = cb200_canvas_create_band(width, height, 0, height, device, out);
+    g_batch_n = 1;
+    return rc;
+}
+
+int cb200_batch_submit(cb200_canvas *cv, const cb200_frame *const *frames, const uint32_t *canvas_index,
+                       uint32_t n_frames)
+{
+    if (!cv || (n_frames && (!frames || !canvas_index))) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    if (n_frames == 0) return CB200_OK;
+    rc = stage_frames(cv, frames, canvas_index, n_frames, cv->staged);
+    if (rc != CB200_OK) return rc;
+    if (cv->staged.draws.empty()) return CB200_OK;
+    cv->resident = false;
+    rc = ensure_capacity(cv, cv->staged, nullptr);
+    if (rc != CB200_OK) return rc;
+    rc = upload_frame(cv);
+    if (rc != CB200_OK) return rc;
+    return run_frame(cv);
+}
+
+int cb200_batch_read_rgba8(cb200_canvas *cv, uint32_t canvas, uint8_t *dst, int width, int height, int stride,
+                           int x, int y)
+{
+    if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
+    if (width <= 0 || height <= 0) return CB200_OK;
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    size_t bytes = 4 * size_t(width) * size_t(height);
+    CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
+    const float4 *slot = cv->fb + size_t(canvas) * size_t(cv->n_canvases > 1 ? cv->slot_rows : 0) * size_t(cv->width);
+    launch_readback(slot, cv->width, 0, cv->height, cv->rgba8.p, width, height, x, y, cv->stream);
+    ++cv->launches;
+    std::vector<uint8_t> tmp(bytes);
+    CK(cudaMemcpyAsync(tmp.data(), cv->rgba8.p, bytes, cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
+    for (int row = 0; row < height; ++row)
+        memcpy(dst + ptrdiff_t(row) * stride, tmp.data() + size_t(row) * size_t(width) * 4, size_t(width) * 4);
+    return CB200_OK;
+}
+
+int cb200_batch_read_f32(cb200_canvas *cv, uint32_t canvas, float *dst)
+{
+    if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    const float4 *slot = cv->fb + size_t(canvas) * size_t(cv->n_canvases > 1 ? cv->slot_rows : 0) * size_t(cv->width);
+    CK(cudaMemcpyAsync(dst, slot, sizeof(float4) * size_t(cv->width) * size_t(cv->height), cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaStreamSynchronize(cv->stream));
     return CB200_OK;
 }
 
@@ -758,7 +874,7 @@ int cb200_frame_replay(cb200_canvas *cv, int clear)
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
     if (clear)
-        CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows), cv->stream));
+        CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * fb_rows(cv), cv->stream));
     // the header is consumed by a run: restore it from its pristine twin (device to device)
     CK(cudaMemcpyAsync(cv->blob.p + cv->hdr_offset, cv->blob.p + cv->hdr_pristine_offset, sizeof(frame_header),
                        cudaMemcpyDeviceToDevice, cv->stream));
@@ -957,7 +1073,7 @@ int cb200_clear(cb200_canvas *cv)
     CK(cudaSetDevice(cv->device));
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
-    CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows), cv->stream));
+    CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * fb_rows(cv), cv->stream));
     CK(cudaStreamSynchronize(cv->stream));
     for (auto &kv : cv->masks) cudaFree(kv.second);
     cv->masks.clear();

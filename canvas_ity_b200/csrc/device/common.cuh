@@ -91,6 +91,7 @@ struct job_rec {
     uint64_t plane_offset;
     float w1, w2; int32_t radius;
     uint32_t opaque;                       // host: solid, alpha 1, source_over/copy, unclipped
+    uint32_t canvas;                       // batch slot this job draws into
 };
 
 // Everything the tile compositor needs to know about one job, packed into one

@@ -196,8 +196,17 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     const int x = tx * kTile + lane;
     const int band_y1 = t.band_y0 + t.band_rows;
     const int tile_x0 = tx * kTile;
-    const int row0 = ty * kTile + warp * kWarpRows;          // first scanline of this warp
-    const uint32_t n_jobs = h->n_jobs;
+    // batches stack their canvases vertically: which canvas is this tile in, and where does it start?
+    int canvas = 0, ty_local = ty;
+    if (t.n_canvases > 1) {
+        const int slot_tiles = t.slot_rows / kTile;
+        canvas = ty / slot_tiles;
+        ty_local = ty - canvas * slot_tiles;
+    }
+    const int yoff = canvas * t.slot_rows;                   // fb row of the canvas' row 0 (0 unless batched)
+    const int row0 = ty_local * kTile + warp * kWarpRows;    // first scanline of this warp, canvas coordinates
+    const uint2 job_range = t.canvas_jobs[canvas];
+    const uint32_t job_begin = job_range.x, job_end = job_range.x + job_range.y;
     if (row0 >= band_y1 || row0 + kWarpRows <= t.band_y0) return;
 
     // The old pixels are requested right away so that their latency overlaps the job search
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     for (int r = 0; r < kWarpRows; ++r) {
         int y = row0 + r;
         live[r] = x < t.width && y >= t.band_y0 && y < band_y1;
-        px[r] = (live[r] && eager_load) ? __ldcs(&t.fb[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)])
+        px[r] = (live[r] && eager_load) ? __ldcs(&t.fb[size_t(yoff + y - t.band_y0) * size_t(t.width) + size_t(x)])
                                         : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     bool loaded = eager_load != 0;
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
         if (n_list && !loaded) {                          // lazy variant: fetch the old pixels on first use
 #pragma unroll
             for (int r = 0; r < kWarpRows; ++r)
-                if (live[r]) px[r] = __ldcs(&t.fb[size_t(row0 + r - t.band_y0) * size_t(t.width) + size_t(x)]);
+                if (live[r]) px[r] = __ldcs(&t.fb[size_t(yoff + row0 + r - t.band_y0) * size_t(t.width) + size_t(x)]);
             loaded = true;
         }
         for (uint32_t q = 0; q < n_list; ++q) {
@@ -287,18 +296,18 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     // 32 candidates per step.  Occlusion culling: a job that paints this whole tile with an opaque
     // solid colour (covered tile entry, source_over/copy, alpha 1, unclipped -- then cov = vis = 1
     // replaces the pixel exactly) voids everything collected or painted before it.
-    for (uint32_t base = 0; base < n_jobs; base += 32) {
+    for (uint32_t base = job_begin; base < job_end; base += 32) {
         const uint32_t j = base + uint32_t(lane);
         uint32_t te = 0;
         bool hit = false, cover = false;
-        if (j < n_jobs) {
+        if (j < job_end) {
             const uint2 box = f.job_box[j];
             const int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
             const int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
-            if (tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1) {
+            if (tx >= bx0 && tx <= bx1 && ty_local >= by0 && ty_local <= by1) {
                 if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
                 else {
-                    te = f.job_te[j] + uint32_t(ty - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
+                    te = f.job_te[j] + uint32_t(ty_local - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
                     const uint32_t flags = f.te_flags[te];
                     hit = (box.y & JOBBOX_EVERYWHERE) || (flags & TE_NONEMPTY);
                     cover = (box.y & JOBBOX_OPAQUE) && (flags & TE_COVERED);
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     if (!touched) return;                                    // no job reaches these pixels: leave them alone
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r)
-        if (live[r]) t.fb[size_t(row0 + r - t.band_y0) * size_t(t.width) + size_t(x)] = px[r];
+        if (live[r]) t.fb[size_t(yoff + row0 + r - t.band_y0) * size_t(t.width) + size_t(x)] = px[r];
     // statistics: composited pixel count of the frame
     for (int off = 16; off; off >>= 1) painted += __shfl_down_sync(0xffffffffu, painted, off);
     if (lane == 0 && painted) atomicAdd(&h->composited_pixels, painted);
@@ -342,6 +351,7 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
 {
     int tiles_x = (t.width + kTile - 1) / kTile;
     int ty0 = t.band_y0 / kTile, ty1 = (t.band_y0 + t.band_rows - 1) / kTile;
+    if (t.n_canvases > 1) { ty0 = 0; ty1 = t.n_canvases * (t.slot_rows / kTile) - 1; }
     int tiles = tiles_x * (ty1 - ty0 + 1);
     // Eager: request the old pixels before the job search (hides their latency) -- best when no job
     // can cover a tile.  Frames with opaque jobs load on first use instead, so tiles that a covering

@@ -69,6 +69,10 @@ struct canvas_target {
     int width, height, band_y0, band_rows;
     float **mask_planes;   // device array of plane pointers indexed by slot (slot 0 unused)
     uint32_t n_masks;
+    // batches: n_canvases equal canvases stacked vertically in fb, slot_rows (multiple of 32) apart;
+    // every job belongs to one canvas and works in that canvas' own coordinates
+    int n_canvases, slot_rows;
+    const uint2 *canvas_jobs;   // per canvas: first job, job count
 };
 
 // geometry.cu

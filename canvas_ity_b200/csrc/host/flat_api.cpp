@@ -6,6 +6,7 @@
 #include "../../../include/canvas_b200_api.h"
 
 #include <new>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -25,7 +26,135 @@ struct ns_tag {
 canvas_ity::canvas *front(cv_canvas *c) { return reinterpret_cast<canvas_ity::canvas *>(c); }
 }
 
+// ---- batches ---------------------------------------------------------------------
+namespace {
+struct owned_frame {                   // deep copy of a lowered frame (the tap's pointers die with the call)
+    std::vector<cb200_draw> draws; std::vector<cb200_subpath> subpaths; std::vector<float> points;
+    std::vector<cb200_brush> brushes; std::vector<float> colors, stops, dashes;
+    std::vector<cb200_image> images; std::vector<uint8_t> texels;
+    cb200_frame view;
+    explicit owned_frame(const cb200_frame &f)
+        : draws(f.draws, f.draws + f.n_draws), subpaths(f.subpaths, f.subpaths + f.n_subpaths),
+          points(f.points, f.points + 2 * size_t(f.n_points)), brushes(f.brushes, f.brushes + f.n_brushes),
+          colors(f.colors, f.colors + 4 * size_t(f.n_colors)), stops(f.stops, f.stops + f.n_colors),
+          dashes(f.dashes, f.dashes + f.n_dashes), images(f.images, f.images + f.n_images),
+          texels(f.texels, f.texels + f.texel_bytes)
+    {
+        view = f;
+    }
+    const cb200_frame *frame()
+    {
+        view.draws = draws.data(); view.subpaths = subpaths.data(); view.points = points.data();
+        view.brushes = brushes.data(); view.colors = colors.data(); view.stops = stops.data();
+        view.dashes = dashes.data(); view.images = images.data(); view.texels = texels.data();
+        return &view;
+    }
+};
+}
+
+struct cv_batch {
+    cb200_canvas *device = nullptr;
+    int n = 0, width = 0, height = 0;
+    std::vector<canvas_ity::canvas *> members;
+    std::vector<std::vector<owned_frame *> > pending;      // per canvas, in flush order
+    struct slot { cv_batch *batch; int index; };
+    std::vector<slot> slots;
+};
+
+namespace {
+void batch_on_frame(void *user, const cb200_frame *frame)
+{
+    cv_batch::slot *s = static_cast<cv_batch::slot *>(user);
+    s->batch->pending[size_t(s->index)].push_back(new owned_frame(*frame));
+}
+void batch_on_read(void *user, uint8_t *dst, int w, int h, int stride, int x, int y)
+{
+    cv_batch::slot *s = static_cast<cv_batch::slot *>(user);
+    cv_batch_get_image_data(s->batch, s->index, dst, w, h, stride, x, y);
+}
+}
+
 extern "C" {
+
+cv_batch *cv_batch_create(int n_canvases, int width, int height, int device)
+{
+    cv_batch *b = new cv_batch;
+    if (cb200_batch_create(n_canvases, width, height, device, &b->device) != CB200_OK) {
+        g_api_error = cb200_last_error();
+        delete b;
+        return nullptr;
+    }
+    b->n = n_canvases; b->width = width; b->height = height;
+    b->pending.resize(size_t(n_canvases));
+    b->slots.resize(size_t(n_canvases));
+    for (int i = 0; i < n_canvases; ++i) {
+        b->slots[size_t(i)].batch = b;
+        b->slots[size_t(i)].index = i;
+        canvas_ity::canvas *c = new canvas_ity::canvas(width, height, -1, 0, height);
+        c->b200()->tap.user = &b->slots[size_t(i)];
+        c->b200()->tap.frame = batch_on_frame;
+        c->b200()->tap.read_rgba8 = batch_on_read;
+        b->members.push_back(c);
+    }
+    return b;
+}
+
+cv_canvas *cv_batch_canvas(cv_batch *b, int index)
+{
+    return b && index >= 0 && index < b->n ? reinterpret_cast<cv_canvas *>(b->members[size_t(index)]) : nullptr;
+}
+
+int cv_batch_flush(cv_batch *b)
+{
+    if (!b) return CB200_ERR_BAD_ARG;
+    for (int i = 0; i < b->n; ++i) b->members[size_t(i)]->b200()->flush();
+    // round k submits the k-th queued frame of every canvas (almost always there is just one round)
+    for (size_t round = 0;; ++round) {
+        std::vector<const cb200_frame *> frames;
+        std::vector<uint32_t> index;
+        for (int i = 0; i < b->n; ++i)
+            if (round < b->pending[size_t(i)].size()) {
+                frames.push_back(b->pending[size_t(i)][round]->frame());
+                index.push_back(uint32_t(i));
+            }
+        if (frames.empty()) break;
+        int rc = cb200_batch_submit(b->device, frames.data(), index.data(), uint32_t(frames.size()));
+        if (rc != CB200_OK) { g_api_error = cb200_last_error(); return rc; }
+    }
+    int rc = cb200_sync(b->device);                        // the frames are about to be freed
+    for (int i = 0; i < b->n; ++i) {
+        for (owned_frame *f : b->pending[size_t(i)]) delete f;
+        b->pending[size_t(i)].clear();
+    }
+    return rc;
+}
+
+int cv_batch_get_image_data(cv_batch *b, int index, uint8_t *image, int width, int height, int stride, int x, int y)
+{
+    if (!b || index < 0 || index >= b->n || !image) return CB200_ERR_BAD_ARG;
+    int rc = cv_batch_flush(b);
+    if (rc != CB200_OK) return rc;
+    return cb200_batch_read_rgba8(b->device, uint32_t(index), image, width, height, stride, x, y);
+}
+
+int cv_batch_read_f32(cv_batch *b, int index, float *dst)
+{
+    if (!b || index < 0 || index >= b->n || !dst) return CB200_ERR_BAD_ARG;
+    int rc = cv_batch_flush(b);
+    if (rc != CB200_OK) return rc;
+    return cb200_batch_read_f32(b->device, uint32_t(index), dst);
+}
+
+cb200_canvas *cv_batch_device(cv_batch *b) { return b ? b->device : nullptr; }
+
+void cv_batch_destroy(cv_batch *b)
+{
+    if (!b) return;
+    for (canvas_ity::canvas *c : b->members) delete c;      // tapped members drop unflushed draws
+    for (auto &q : b->pending) for (owned_frame *f : q) delete f;
+    cb200_canvas_destroy(b->device);
+    delete b;
+}
 
 cv_canvas *cv_create(int width, int height)
 {

@@ -127,6 +127,18 @@ int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows,
 
 void cb200_canvas_destroy(cb200_canvas *canvas);
 
+/* A batch of `n_canvases` independent, equally sized canvases that are rendered
+ * together: one upload and one launch sequence for all of them (the reference has
+ * no shared state between canvases, hpp:73-74, so they are one big data-parallel
+ * job).  The result is a cb200_canvas for destroy/sync/stats; submit and reads go
+ * through the cb200_batch_* calls, frames carry their canvas index (ascending). */
+int cb200_batch_create(int n_canvases, int width, int height, int device, cb200_canvas **out);
+int cb200_batch_submit(cb200_canvas *batch, const cb200_frame *const *frames,
+                       const uint32_t *canvas_index, uint32_t n_frames);
+int cb200_batch_read_rgba8(cb200_canvas *batch, uint32_t canvas, uint8_t *dst, int width,
+                           int height, int stride, int x, int y);
+int cb200_batch_read_f32(cb200_canvas *batch, uint32_t canvas, float *dst);
+
 /* Run `frame` (draws in order) on the canvas' stream.  Asynchronous: returns
  * once the frame is copied to pinned staging and the kernels are enqueued. */
 int cb200_submit(cb200_canvas *canvas, const cb200_frame *frame);

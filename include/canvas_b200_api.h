@@ -53,6 +53,20 @@ int   cv_put_image_data(cv_canvas *canvas, const uint8_t *image, int width, int 
 int   cv_is_point_in_path(cv_canvas *canvas, float x, float y);    /* :843 */
 float cv_measure_text(cv_canvas *canvas, const char *text);        /* :1025 */
 
+/* A batch of n independent width x height canvases rendered together on one GPU
+ * (cb200_batch_*): cv_batch_canvas(i) is an ordinary front-end canvas whose draws
+ * are queued in the batch; cv_batch_flush() lowers and submits all of them in one
+ * device frame.  get_image_data on a member canvas flushes the whole batch. */
+typedef struct cv_batch cv_batch;
+cv_batch *cv_batch_create(int n_canvases, int width, int height, int device);
+cv_canvas *cv_batch_canvas(cv_batch *batch, int index);
+int cv_batch_flush(cv_batch *batch);
+int cv_batch_get_image_data(cv_batch *batch, int index, uint8_t *image, int width, int height,
+                            int stride, int x, int y);
+int cv_batch_read_f32(cv_batch *batch, int index, float *dst);
+cb200_canvas *cv_batch_device(cv_batch *batch);
+void cv_batch_destroy(cv_batch *batch);
+
 /* Flush queued draws (no-op on the reference build). */
 int cv_flush(cv_canvas *canvas);
 /* Linear premultiplied float framebuffer, rows * width * 4 floats. */

@@ -67,6 +67,14 @@ int cv_put_image_data(cv_canvas *c, const uint8_t *image, int w, int h, int stri
 int cv_is_point_in_path(cv_canvas *c, float x, float y) { return ref(c)->is_point_in_path(x, y); }
 float cv_measure_text(cv_canvas *c, const char *text) { return ref(c)->measure_text(text); }
 int cv_flush(cv_canvas *) { return 0; }
+// batches are a back-end concept: the reference renders canvases one by one
+cv_batch *cv_batch_create(int, int, int, int) { return nullptr; }
+cv_canvas *cv_batch_canvas(cv_batch *, int) { return nullptr; }
+int cv_batch_flush(cv_batch *) { return -1; }
+int cv_batch_get_image_data(cv_batch *, int, uint8_t *, int, int, int, int, int) { return -1; }
+int cv_batch_read_f32(cv_batch *, int, float *) { return -1; }
+cb200_canvas *cv_batch_device(cv_batch *) { return nullptr; }
+void cv_batch_destroy(cv_batch *) {}
 
 int cv_read_f32(cv_canvas *c, float *dst)
 {

@@ -244,3 +244,53 @@ def hash_image(image):
 
 def hamming(a, b):
     return bin((a ^ b) & 0xffffffff).count("1")
+
+
+# ---------------------------------------------------------------- config 5 scenes ----
+
+_font_a = None
+
+
+def font_a():
+    """The reference suite's main test font (test.cpp:114-170), recovered from a captured script."""
+    global _font_a
+    if _font_a is None:
+        blob = golden_script("text_align")
+        at = blob.index(b"\x00\x01\x00\x00")            # TrueType version tag = start of the font blob
+        n = struct.unpack_from("<I", blob, at - 4)[0]
+        _font_a = blob[at:at + n]
+    return _font_a
+
+
+def config5_script(index, with_text=True):
+    """BASELINE.json config 5 / SURVEY 8d: canvas `index` of the 16384-canvas batch (256x256):
+    8 random draws of 1-3 subpaths with 3-8 cubics each, half filled half stroked, plus one
+    fill_text of 6 characters; everything from the LCG seeded with 0x9E3779B9 * (index + 1)."""
+    state = [(0x9E3779B9 * (index + 1)) & 0xffffffff]
+
+    def u():
+        state[0] = (state[0] * 1664525 + 1013904223) & 0xffffffff
+        return (state[0] >> 8) / float(1 << 24)
+
+    w = ScriptWriter()
+    for _ in range(8):
+        w.bare("BEGIN_PATH")
+        for _ in range(1 + int(u() * 3)):
+            w.floats("MOVE_TO", -32 + 320 * u(), -32 + 320 * u())
+            for _ in range(3 + int(u() * 6)):
+                w.floats("BEZIER_CURVE_TO", *[-32 + 320 * u() for _ in range(6)])
+        stroke = u() < 0.5
+        w.floats("SET_LINE_WIDTH", 0.5 + 11.5 * u())
+        w.ints("SET_LINE_JOIN", int(u() * 3))
+        w.ints("SET_LINE_CAP", int(u() * 3))
+        w.ints("SET_COLOR", 1 if stroke else 0)
+        w.raw("4f", u(), u(), u(), u())
+        w.bare("STROKE" if stroke else "FILL")
+    if with_text:
+        alphabet = " *CDEFGHIanstvy"
+        text = "".join(alphabet[int(u() * len(alphabet))] for _ in range(6))
+        w.floats("SET_FONT", 16 + 48 * u()); w.raw("B", 1); w.blob(font_a())
+        w.ints("SET_COLOR", 0); w.raw("4f", u(), u(), u(), 1.0)
+        x, y = 192 * u(), 192 * u()
+        w.floats("FILL_TEXT", x, y, 1.0e30); w.blob(text.encode())
+    return w.take()

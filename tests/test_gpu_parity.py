@@ -196,3 +196,57 @@ def test_readback_paths_agree(lib):
         lib.cb200_host_free(ptr)
     finally:
         lib.cv_destroy(h)
+
+
+def test_batch_equals_individual_canvases(lib):
+    """Config 5 in miniature: a batch of independent 256x256 canvases (random paths + glyph text)
+    rendered as ONE device frame gives, per canvas, exactly the floats of rendering it alone, and
+    matches the oracle."""
+    n, size = 12, 256
+    scripts = [H.config5_script(i) for i in range(n)]
+    batch = lib.cv_batch_create(n, size, size, 0)
+    assert batch, lib.cv_last_error()
+    try:
+        for i, s in enumerate(scripts):
+            H._run(lib, lib.cv_batch_canvas(batch, i), s)
+        assert lib.cv_batch_flush(batch) == 0, lib.cv_last_error()
+        for i, s in enumerate(scripts):
+            got = np.zeros((size, size, 4), np.float32)
+            assert lib.cv_batch_read_f32(batch, i, got.ctypes.data) == 0
+            alone = H.render_script(lib, s, size, size)
+            assert np.array_equal(got.view(np.uint32), alone["f32"].view(np.uint32)), "canvas %d differs from solo render" % i
+            img = np.zeros((size, size, 4), np.uint8)
+            assert lib.cv_batch_get_image_data(batch, i, img.ctypes.data, size, size, 4 * size, 0, 0) == 0
+            assert np.array_equal(img, alone["rgba8"])
+            if i < 4:
+                want = H.render_oracle(s, size, size)
+                nbad, worst = H.float_mismatch(got, want["f32"])
+                assert nbad == 0, "canvas %d: %d floats off (max %.3g)" % (i, nbad, worst)
+    finally:
+        lib.cv_batch_destroy(batch)
+
+
+def test_batch_with_clip_masks_and_odd_size(lib):
+    """Batch canvases whose height is not a multiple of the tile size, with clips and shadows."""
+    n, w, h = 5, 100, 77
+    import canvas_ity_b200 as cb
+    def scene(i):
+        s = cb.script.ScriptWriter()
+        s.bare("BEGIN_PATH"); s.floats("ARC", 50, 38, 30 + 2 * i, 0, 6.28318531); s.raw("i", 0); s.bare("CLIP")
+        s.floats("SET_SHADOW_BLUR", 4.0); s.floats("SET_SHADOW_COLOR", 0, 0, 0, 0.8); s.floats("SET_SHADOW_OFFSET_X", 3.0)
+        s.ints("SET_COLOR", 0); s.raw("4f", 0.1 * i, 0.5, 0.8, 0.9)
+        s.floats("FILL_RECTANGLE", 10 + i, 5, 60, 60)
+        return s.take()
+    batch = lib.cv_batch_create(n, w, h, 0)
+    try:
+        for i in range(n):
+            H._run(lib, lib.cv_batch_canvas(batch, i), scene(i))
+        assert lib.cv_batch_flush(batch) == 0, lib.cv_last_error()
+        for i in range(n):
+            got = np.zeros((h, w, 4), np.float32)
+            assert lib.cv_batch_read_f32(batch, i, got.ctypes.data) == 0
+            want = H.render_oracle(scene(i), w, h)
+            nbad, worst = H.float_mismatch(got, want["f32"])
+            assert nbad == 0, "canvas %d: %d floats off (max %.3g)" % (i, nbad, worst)
+    finally:
+        lib.cv_batch_destroy(batch)
