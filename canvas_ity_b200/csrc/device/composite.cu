@@ -114,18 +114,20 @@ __device__ rgba paint_at(const paint_tables &f, const brush_rec &b, const affine
     return mk(c.x * c.w, c.y * c.w, c.z * c.w, c.w);
 }
 
-// the mix program of hpp:2583-2591
+// the mix program of hpp:2583-2591.  The products are fused (fmaf): the reference's own builds
+// differ by more than that between compilers, and with cov = vis = 1 and an opaque
+// source the result is still exactly `fore`, which is what occlusion culling relies on.
 __device__ __forceinline__ void blend(float4 &back, rgba fore, uint32_t op, float vis)
 {
     float mf = (op & 1u) ? back.w : 0.0f;
     if (op & 2u) mf = 1.0f - mf;
     float mb = (op & 4u) ? fore.a : 0.0f;
     if (op & 8u) mb = 1.0f - mb;
-    float r = mf * fore.r + mb * back.x, g = mf * fore.g + mb * back.y, b = mf * fore.b + mb * back.z;
-    float a = fminf(mf * fore.a + mb * back.w, 1.0f);
+    float r = fmaf(mf, fore.r, mb * back.x), g = fmaf(mf, fore.g, mb * back.y), b = fmaf(mf, fore.b, mb * back.z);
+    float a = fminf(fmaf(mf, fore.a, mb * back.w), 1.0f);
     float keep = 1.0f - vis;
-    back = make_float4(vis * r + keep * back.x, vis * g + keep * back.y, vis * b + keep * back.z,
-                       vis * a + keep * back.w);
+    back = make_float4(fmaf(vis, r, keep * back.x), fmaf(vis, g, keep * back.y), fmaf(vis, b, keep * back.z),
+                       fmaf(vis, a, keep * back.w));
 }
 
 constexpr int kWarpRows = 8;                                 // scanlines of a tile owned by one warp
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     bool loaded = eager_load != 0;
     const cov_source cs = make_cov_source(f, sb);
     const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
-    unsigned long long painted = 0;
+    uint32_t painted = 0;
     bool touched = false;
     uint32_t n_list = 0;
 
@@ -281,11 +283,11 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
                 float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
                 if (mask_out) { mask_out[at] = cov * vis; continue; }
                 if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
+                ++painted;
                 rgba paint = brush_type == CB200_BRUSH_COLOR ? flat
                            : (brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
                                                   : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f));
                 blend(px[r], scale(cov * alpha, paint), op, vis);
-                ++painted;
             }
         }
         touched = touched || n_list != 0;
@@ -341,8 +343,8 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     for (int r = 0; r < kWarpRows; ++r)
         if (live[r]) t.fb[size_t(yoff + row0 + r - t.band_y0) * size_t(t.width) + size_t(x)] = px[r];
     // statistics: composited pixel count of the frame
-    for (int off = 16; off; off >>= 1) painted += __shfl_down_sync(0xffffffffu, painted, off);
-    if (lane == 0 && painted) atomicAdd(&h->composited_pixels, painted);
+    painted = __reduce_add_sync(0xffffffffu, painted);
+    if (lane == 0 && painted) atomicAdd(&h->composited_pixels, (unsigned long long)painted);
 }
 
 }  // namespace
