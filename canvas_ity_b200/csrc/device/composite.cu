@@ -214,13 +214,15 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     // The old pixels are requested right away so that their latency overlaps the job search
     // (they are dropped again if a covering job turns up).
     float4 px[kWarpRows];
-    bool live[kWarpRows];
+    uint32_t live_mask = 0;                                  // bit r: scanline row0 + r is ours and x is on the canvas
+    const size_t local_index = size_t(row0 - t.band_y0) * size_t(t.width) + size_t(x);   // into canvas-sized planes
+    float4 *const fb_at = t.fb + (size_t(yoff) * size_t(t.width) + local_index);         // this lane's first pixel
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
-        int y = row0 + r;
-        live[r] = x < t.width && y >= t.band_y0 && y < band_y1;
-        px[r] = (live[r] && eager_load) ? __ldcs(&t.fb[size_t(yoff + y - t.band_y0) * size_t(t.width) + size_t(x)])
-                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int y = row0 + r;
+        const bool live = x < t.width && y >= t.band_y0 && y < band_y1;
+        live_mask |= uint32_t(live) << r;
+        px[r] = (live && eager_load) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     bool loaded = eager_load != 0;
     const cov_source cs = make_cov_source(f, sb);
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
         if (n_list && !loaded) {                          // lazy variant: fetch the old pixels on first use
 #pragma unroll
             for (int r = 0; r < kWarpRows; ++r)
-                if (live[r]) px[r] = __ldcs(&t.fb[size_t(yoff + row0 + r - t.band_y0) * size_t(t.width) + size_t(x)]);
+                if (live_mask >> r & 1u) px[r] = __ldcs(fb_at + size_t(r) * size_t(t.width));
             loaded = true;
         }
         for (uint32_t q = 0; q < n_list; ++q) {
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
-                    if (!live[r] || x < c.cx0 || x >= c.cx1 || y < c.cy0 || y >= c.cy1) continue;
+                    if (!(live_mask >> r & 1u) || x < c.cx0 || x >= c.cx1 || y < c.cy0 || y >= c.cy1) continue;
                     float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
                     if (vis < kThreshold) continue;
                     float s = plane[size_t(y + c.border - c.top) * size_t(c.bw) + size_t(x + c.border - c.left)];
@@ -272,22 +274,36 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
             const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
             const float alpha = c.alpha;
             float *mask_out = c.kind == JOB_CLIP ? t.mask_planes[c.mask_dst] : nullptr;
+            const float *back_row = ws.back + warp * kWarpRows;
+            const uint32_t *first_row = ws.first + warp * kWarpRows;
+            if (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR) {
+                // the common case -- unclipped solid colour -- carries no per-row address arithmetic
 #pragma unroll
-            for (int r = 0; r < kWarpRows; ++r) {
-                const int ly = warp * kWarpRows + r, y = row0 + r;
-                // warp-uniform: every lane of the warp shares the row
-                float sum = staged_row_sum(cs, ws.back[ly], ws.first[ly], jj, y, tile_x0, ws.row_buf);
-                float cov = fminf(fabsf(sum), 1.0f);
-                if (!live[r]) continue;
-                size_t at = size_t(y - t.band_y0) * size_t(t.width) + size_t(x);
-                float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
-                if (mask_out) { mask_out[at] = cov * vis; continue; }
-                if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
-                ++painted;
-                rgba paint = brush_type == CB200_BRUSH_COLOR ? flat
-                           : (brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
-                                                  : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f));
-                blend(px[r], scale(cov * alpha, paint), op, vis);
+                for (int r = 0; r < kWarpRows; ++r) {
+                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, row0 + r, tile_x0, ws.row_buf);
+                    float cov = fminf(fabsf(sum), 1.0f);
+                    if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
+                    ++painted;
+                    blend(px[r], scale(cov * alpha, flat), op, 1.0f);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kWarpRows; ++r) {
+                    const int y = row0 + r;
+                    // warp-uniform: every lane of the warp shares the row
+                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, y, tile_x0, ws.row_buf);
+                    float cov = fminf(fabsf(sum), 1.0f);
+                    if (!(live_mask >> r & 1u)) continue;
+                    const size_t at = local_index + size_t(r) * size_t(t.width);
+                    float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
+                    if (mask_out) { mask_out[at] = cov * vis; continue; }
+                    if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
+                    ++painted;
+                    rgba paint = brush_type == CB200_BRUSH_COLOR ? flat
+                               : (brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
+                                                      : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f));
+                    blend(px[r], scale(cov * alpha, paint), op, vis);
+                }
             }
         }
         touched = touched || n_list != 0;
@@ -341,7 +357,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
     if (!touched) return;                                    // no job reaches these pixels: leave them alone
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r)
-        if (live[r]) t.fb[size_t(yoff + row0 + r - t.band_y0) * size_t(t.width) + size_t(x)] = px[r];
+        if (live_mask >> r & 1u) fb_at[size_t(r) * size_t(t.width)] = px[r];
     // statistics: composited pixel count of the frame
     painted = __reduce_add_sync(0xffffffffu, painted);
     if (lane == 0 && painted) atomicAdd(&h->composited_pixels, (unsigned long long)painted);

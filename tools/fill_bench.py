@@ -53,8 +53,10 @@ def main():
     n = 256 if SIZE <= 2048 else 1024
     IMAGE[n] = lcg_image(n)
     rows = []
-    for kind in ("solid", "linear", "radial", "image"):
-        for opname, op in OPS.items():
+    kinds = os.environ.get("FILL_KINDS", "solid,linear,radial,image").split(",")
+    ops = {k: v for k, v in OPS.items() if k in os.environ.get("FILL_OPS", ",".join(OPS)).split(",")}
+    for kind in kinds:
+        for opname, op in ops.items():
             # background first so that the measured draw blends over real pixels
             bg = ScriptWriter(); bg.ints("SET_COLOR", 0); bg.raw("4f", 0.9, 0.8, 0.1, 0.6); bg.floats("FILL_RECTANGLE", 0, 0, float(SIZE), float(SIZE))
             frame = H.lower_script(scene(kind, op), SIZE, SIZE)[0]
