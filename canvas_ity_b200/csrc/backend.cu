@@ -526,6 +526,11 @@ int upload_frame(cb200_canvas *cv)
     f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p;
     f.n_opaque_jobs = 0;
     for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
+    f.general_compositor = 0;
+    for (const job_rec &j : sf.jobs) {
+        const draw_rec &d = sf.draws[j.draw];
+        if (j.kind != JOB_MAIN || d.mask_src || sf.brushes[d.brush].type != CB200_BRUSH_COLOR) f.general_compositor = 1;
+    }
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
     f.max_shadow_pad = 0; f.max_shadow_radius = 0;

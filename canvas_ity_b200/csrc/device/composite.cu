@@ -168,6 +168,120 @@ __device__ __forceinline__ float staged_row_sum(const cov_source &c, float backd
     return upto ? got : backdrop;
 }
 
+// A non-solid brush staged in shared memory once per (job, warp): record, brush-space matrix and
+// up to kStagedStops gradient stops, so the per-pixel code touches no global tables.
+constexpr uint32_t kStagedStops = 16;
+struct staged_brush {
+    brush_rec b;
+    affine inv;
+    float stops[kStagedStops];
+    float4 colors[kStagedStops];
+};
+
+// Linear / radial gradient at a device-space pixel centre (hpp:2331-2376), from the staged copy.
+__device__ __noinline__ rgba paint_gradient(const staged_brush &sb, float x, float y)
+{
+    const brush_rec &b = sb.b;
+    vec2 p = apply(sb.inv, v2(x, y));
+    vec2 rel = p - v2(b.sx, b.sy), axis = v2(b.ex, b.ey) - v2(b.sx, b.sy);
+    float along = dot(rel, axis), axis2 = dot(axis, axis);
+    float t;
+    if (b.type == CB200_BRUSH_LINEAR) {
+        if (axis2 == 0.0f) return mk(0.0f, 0.0f, 0.0f, 0.0f);
+        t = along / axis2;
+    } else {
+        float dr = b.r1 - b.r0;
+        float qa = axis2 - dr * dr;
+        float qb = -2.0f * (along + b.r0 * dr);
+        float qc = dot(rel, rel) - b.r0 * b.r0;
+        float disc = qb * qb - 4.0f * qa * qc;
+        if (disc < 0.0f || (axis2 == 0.0f && dr == 0.0f)) return mk(0.0f, 0.0f, 0.0f, 0.0f);
+        float root = sqrtf(disc), inv2a = 1.0f / (2.0f * qa);
+        float ta = (-qb - root) * inv2a, tb = (-qb + root) * inv2a;
+        if (b.r0 + dr * tb >= 0.0f) t = tb;
+        else if (b.r0 + dr * ta >= 0.0f) t = ta;
+        else return mk(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    uint32_t hi = 0;                                    // first stop strictly greater than t (NaN: none)
+    while (hi < b.n_colors && !(t < sb.stops[hi])) ++hi;
+    float4 c;
+    if (hi == 0) c = sb.colors[0];
+    else if (hi == b.n_colors) c = sb.colors[b.n_colors - 1];
+    else {
+        float m = (t - sb.stops[hi - 1]) / (sb.stops[hi] - sb.stops[hi - 1]);
+        float4 lo = sb.colors[hi - 1], up = sb.colors[hi];
+        c = make_float4(lo.x + m * (up.x - lo.x), lo.y + m * (up.y - lo.y), lo.z + m * (up.z - lo.z),
+                        lo.w + m * (up.w - lo.w));
+    }
+    return mk(c.x * c.w, c.y * c.w, c.z * c.w, c.w);
+}
+
+// Bicubic (Keys) pattern / image sample (hpp:2274-2330).  Same taps, weights and summation order as
+// the reference (rows outer, columns inner), but the column weights and wrapped column indices are
+// computed once per pixel instead of once per tap, and clamp addressing skips the modulo.
+constexpr int kMaxTapsX = 8;
+__device__ __noinline__ rgba paint_pattern(const float4 *texels, const staged_brush *sbp, float x, float y)
+{
+    const staged_brush &sb = *sbp;
+    const brush_rec &b = sb.b;
+    const affine &inv = sb.inv;
+    vec2 p = apply(inv, v2(x, y));
+    float w = float(b.width), h = float(b.height);
+    if (((b.repetition & 2u) && (p.x < 0.0f || w <= p.x)) || ((b.repetition & 1u) && (p.y < 0.0f || h <= p.y)))
+        return mk(0.0f, 0.0f, 0.0f, 0.0f);
+    float sx = fabsf(inv.a) + fabsf(inv.c), sy = fabsf(inv.b) + fabsf(inv.d);
+    sx = fmaxf(1.0f, fminf(sx, w * 0.25f));
+    sy = fmaxf(1.0f, fminf(sy, h * 0.25f));
+    float rx = 1.0f / sx, ry = 1.0f / sy;
+    p = p - v2(0.5f, 0.5f);
+    int x0 = int(ceilf(p.x - sx * 2.0f)), y0 = int(ceilf(p.y - sy * 2.0f));
+    int x1 = int(ceilf(p.x + sx * 2.0f)), y1 = int(ceilf(p.y + sy * 2.0f));
+    const float4 *tex = texels + b.texel_offset;
+    const bool clamp_mode = (b.flags & CB200_BRUSH_CLAMP) != 0;
+    auto wrap = [clamp_mode](int i, int n) -> int {
+        if (clamp_mode) return min(max(i, 0), n - 1);
+        int m = i % n;
+        return m < 0 ? m + n : m;
+    };
+    rgba acc = mk(0.0f, 0.0f, 0.0f, 0.0f);
+    float wsum = 0.0f;
+    const int nx = x1 - x0;
+    if (nx <= kMaxTapsX) {
+        float wx[kMaxTapsX];
+        int ix[kMaxTapsX];
+#pragma unroll
+        for (int k = 0; k < kMaxTapsX; ++k) {
+            wx[k] = k < nx ? keys_weight(fabsf(rx * (float(x0 + k) - p.x))) : 0.0f;
+            ix[k] = k < nx ? wrap(x0 + k, b.width) : 0;
+        }
+        for (int ty = y0; ty < y1; ++ty) {
+            float wy = keys_weight(fabsf(ry * (float(ty) - p.y)));
+            const float4 *row = tex + size_t(wrap(ty, b.height)) * size_t(b.width);
+#pragma unroll
+            for (int k = 0; k < kMaxTapsX; ++k) {
+                if (k < nx) {
+                    float wgt = wx[k] * wy;
+                    float4 c = __ldg(row + ix[k]);
+                    acc = plus(acc, scale(wgt, mk(c.x, c.y, c.z, c.w)));
+                    wsum += wgt;
+                }
+            }
+        }
+    } else {
+        for (int ty = y0; ty < y1; ++ty) {
+            float wy = keys_weight(fabsf(ry * (float(ty) - p.y)));
+            const float4 *row = tex + size_t(wrap(ty, b.height)) * size_t(b.width);
+            for (int tx = x0; tx < x1; ++tx) {
+                float wgt = keys_weight(fabsf(rx * (float(tx) - p.x))) * wy;
+                float4 c = __ldg(row + wrap(tx, b.width));
+                acc = plus(acc, scale(wgt, mk(c.x, c.y, c.z, c.w)));
+                wsum += wgt;
+            }
+        }
+    }
+    return scale(1.0f / wsum, acc);
+}
+
 // Non-solid brushes: kept out of line so the solid path stays small.
 __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t draw, float x, float y)
 {
@@ -181,12 +295,17 @@ struct warp_scratch {
     uint32_t first[kTile];              // ... and first run inside the tile
     float row_buf[kTile];
     uint32_t job[kList], te[kList];
+    staged_brush brush;
 };
 
 // One WARP owns 8 scanlines x 32 pixels of a tile (8 pixels per lane, in registers) and works
 // completely on its own: no block-wide barrier anywhere, so an SM keeps ~20 independent
 // tile-quarters in flight and their dependent loads (job table -> tile entry -> runs) overlap.
-__global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, canvas_target t, int sb,
+// kGeneral = false is the lean build for frames that only hold unclipped solid-colour fills and
+// strokes without shadows (the tiger, most UI and plots): no gradient/pattern/mask/shadow code, so
+// no register spills on the hot path.  The host picks the variant per frame.
+template <bool kGeneral>
+__global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
     __shared__ __align__(16) warp_scratch scratch[kTileWarps];
@@ -252,9 +371,9 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
             ws.first[lane] = fr;
             __syncwarp();
             const comp_rec &c = ws.rec;
-            const float *mask = c.mask_src ? t.mask_planes[c.mask_src] : nullptr;
+            const float *mask = (kGeneral && c.mask_src) ? t.mask_planes[c.mask_src] : nullptr;
             const uint32_t op = c.op;
-            if (c.kind == JOB_SHADOW) {
+            if (kGeneral && c.kind == JOB_SHADOW) {
                 const float *plane = f.planes + (uint64_t(c.plane_hi) << 32 | c.plane_lo);
                 const rgba tint = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
 #pragma unroll
@@ -273,10 +392,29 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
             const uint32_t brush_type = c.brush_type;
             const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
             const float alpha = c.alpha;
-            float *mask_out = c.kind == JOB_CLIP ? t.mask_planes[c.mask_dst] : nullptr;
+            float *mask_out = (kGeneral && c.kind == JOB_CLIP) ? t.mask_planes[c.mask_dst] : nullptr;
+            const bool gradient = brush_type == CB200_BRUSH_LINEAR || brush_type == CB200_BRUSH_RADIAL;
+            bool staged = false;
+            if (kGeneral && (gradient || brush_type == CB200_BRUSH_PATTERN) && c.kind == JOB_MAIN) {
+                // stage the brush: record (14 words), brush-space matrix (6 words), gradient stops
+                const brush_rec *gb = &f.brushes[c.brush];
+                const uint32_t n_stops = gradient ? gb->n_colors : 0;
+                staged = n_stops <= kStagedStops;
+                if (staged) {
+                    if (lane < int(sizeof(brush_rec) / 4))
+                        reinterpret_cast<uint32_t *>(&ws.brush.b)[lane] = reinterpret_cast<const uint32_t *>(gb)[lane];
+                    if (lane < 6)
+                        reinterpret_cast<float *>(&ws.brush.inv)[lane] = reinterpret_cast<const float *>(&f.draws[c.draw].inverse)[lane];
+                    if (uint32_t(lane) < n_stops) {
+                        ws.brush.stops[lane] = f.stops[gb->first_color + lane];
+                        ws.brush.colors[lane] = f.colors[gb->first_color + lane];
+                    }
+                }
+                __syncwarp();
+            }
             const float *back_row = ws.back + warp * kWarpRows;
             const uint32_t *first_row = ws.first + warp * kWarpRows;
-            if (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR) {
+            if (!kGeneral || (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR)) {
                 // the common case -- unclipped solid colour -- carries no per-row address arithmetic
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
@@ -286,7 +424,7 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
                     ++painted;
                     blend(px[r], scale(cov * alpha, flat), op, 1.0f);
                 }
-            } else {
+            } else if (kGeneral) {
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
@@ -299,9 +437,12 @@ __global__ void __launch_bounds__(kCompBlock, 5) k_composite(device_frame f, can
                     if (mask_out) { mask_out[at] = cov * vis; continue; }
                     if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
                     ++painted;
-                    rgba paint = brush_type == CB200_BRUSH_COLOR ? flat
-                               : (brush_type == 0xffu ? mk(0.0f, 0.0f, 0.0f, 0.0f)
-                                                      : paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f));
+                    rgba paint;
+                    if (brush_type == CB200_BRUSH_COLOR) paint = flat;
+                    else if (brush_type == 0xffu) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (staged && gradient) paint = paint_gradient(ws.brush, float(x) + 0.5f, float(y) + 0.5f);
+                    else if (staged) paint = paint_pattern(f.texels, &ws.brush, float(x) + 0.5f, float(y) + 0.5f);
+                    else paint = paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f);
                     blend(px[r], scale(cov * alpha, paint), op, vis);
                 }
             }
@@ -377,7 +518,8 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     // overrides.
     int eager = f.n_opaque_jobs == 0;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
-    k_composite<<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
+    if (f.general_compositor) k_composite<true><<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
+    else k_composite<false><<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
 }
 
 }  // namespace cb200

@@ -34,6 +34,7 @@ struct device_frame {
     comp_rec *comp;                                    // per job, built by k_job_tiles
     uint2 *job_box;  uint32_t *job_te;                 // compact per-job tile box + first tile entry
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
+    int general_compositor;                            // frame needs gradients / patterns / masks / shadows / clips
     float4 *texels;
     // geometry
     uint32_t *unit_count, *unit_offset;               // n_units + 1
