@@ -117,7 +117,7 @@ struct cb200_canvas {
     dev_buf<float4> pieces, texels;
     dev_buf<comp_rec> comp;
     dev_buf<uint2> job_box;
-    dev_buf<uint32_t> job_te;
+    dev_buf<uint32_t> job_te, blur_units;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -423,6 +423,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->comp.reserve(sf.jobs.size() + 1));
     CK(cv->job_box.reserve(sf.jobs.size() + 1));
     CK(cv->job_te.reserve(sf.jobs.size() + 1));
+    CK(cv->blur_units.reserve(2 * (sf.shadow_jobs.size() + 1) + 2));
     CK(cv->sort_hist.reserve(512 * kGrid + 512));
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
@@ -523,7 +524,7 @@ int upload_frame(cb200_canvas *cv)
     f.sources = cv->sources.p;
     f.n_static_sources = uint32_t(sf.sources.size());
     f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
-    f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p;
+    f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p; f.blur_units = cv->blur_units.p;
     f.n_opaque_jobs = 0;
     for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
     f.general_compositor = 0;
@@ -533,8 +534,9 @@ int upload_frame(cb200_canvas *cv)
     }
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());
-    f.max_shadow_pad = 0; f.max_shadow_radius = 0;
+    f.max_shadow_pad = 0; f.max_shadow_radius = 0; f.min_shadow_radius = 1 << 30;
     for (uint32_t sj : sf.shadow_jobs) {
+        f.min_shadow_radius = std::min(f.min_shadow_radius, int(sf.jobs[sj].radius));
         f.max_shadow_pad = std::max(f.max_shadow_pad, int(sf.jobs[sj].pad));
         f.max_shadow_radius = std::max(f.max_shadow_radius, int(sf.jobs[sj].radius));
     }
@@ -828,7 +830,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
-    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->keys0.release(); cv->keys1.release();
+    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 8; ++i)

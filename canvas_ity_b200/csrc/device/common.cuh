@@ -30,7 +30,8 @@ namespace cb200 {
 
 constexpr int kTile = 32;                  // compositor tile is kTile x kTile pixels
 constexpr int kBlock = 256;                // threads per CTA for the 1-D work kernels
-constexpr int kGrid = 148 * 4;             // fixed 1-D grid: 4 CTAs per B200 SM
+constexpr int kSMs = 148;                  // B200
+constexpr int kGrid = kSMs * 4;            // fixed 1-D grid: 4 CTAs per B200 SM
 constexpr float kThreshold = 1.0f / 8160.0f;   // hpp:1289, 2429, 2573
 constexpr uint32_t kNoRun = 0xffffffffu;
 
@@ -88,6 +89,10 @@ struct job_rec {
     uint32_t first_item, n_items;          // ... = K4 work items of this job
     // shadow plane (JOB_SHADOW): working rectangle in padded space + storage
     int32_t left, top, bw, bh;
+    // storage: pixel (left + c, top + r) is plane[r * pitch + skew + c]; pitch is a multiple of 32
+    // floats and skew puts canvas x = 0 (mod 32) on a 128-byte boundary, so that the raster, both
+    // blur sweeps and the compositor move whole aligned 128-byte lines
+    int32_t pitch, skew;
     uint64_t plane_offset;
     float w1, w2; int32_t radius;
     uint32_t opaque;                       // host: solid, alpha 1, source_over/copy, unclipped
@@ -101,7 +106,7 @@ struct comp_rec {
     int32_t tx0, ty0, tw, th, cx0, cy0, cx1, cy1;
     float alpha;                       // global_alpha
     float color[4];                    // solid colour, or the shadow tint
-    int32_t border, left, top, bw;     // shadow plane placement
+    int32_t border, left, top, bw;     // shadow plane placement: storage origin (left - skew, top), row pitch
     uint32_t plane_lo, plane_hi;       // plane offset (floats), 64 bit
     uint32_t brush_type, pad[4];
 };

@@ -32,6 +32,7 @@ struct device_frame {
     stroke_src *sources;   uint32_t n_static_sources;
     job_rec *jobs;
     comp_rec *comp;                                    // per job, built by k_job_tiles
+    uint32_t *blur_units;                              // [2][n_shadow_jobs + 1] prefix of blur sweep units (x, y)
     uint2 *job_box;  uint32_t *job_te;                 // compact per-job tile box + first tile entry
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
     int general_compositor;                            // frame needs gradients / patterns / masks / shadows / clips
@@ -59,7 +60,7 @@ struct device_frame {
     uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
     float *planes, *planes_tmp;  uint64_t cap_planes;
     uint32_t *shadow_jobs; uint32_t n_shadow_jobs;     // job indices with kind JOB_SHADOW
-    int max_shadow_pad, max_shadow_radius;
+    int max_shadow_pad, max_shadow_radius, min_shadow_radius;
     // scratch
     uint32_t *partials;                                // several kGrid-sized slices
     uint32_t *sort_hist;

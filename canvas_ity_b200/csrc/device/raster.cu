@@ -389,7 +389,9 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
                 int top = max(ly - b, 0), bottom = min(hy + b, full_h);
                 jr.left = left; jr.top = top;
                 jr.bw = max(right - left, 0); jr.bh = max(bottom - top, 0);
-                plane = (unsigned long long)jr.bw * (unsigned long long)jr.bh;
+                jr.skew = (left - b) & 31;                        // (left - skew - border) = 0 mod 32, also when negative
+                jr.pitch = (jr.skew + jr.bw + 31) & ~31;
+                plane = (unsigned long long)jr.pitch * (unsigned long long)jr.bh;
                 x0 = left; y0 = top; x1 = left + jr.bw; y1 = top + jr.bh;
                 // where the blurred plane lands on the canvas, hpp:2512-2514, 2535
                 jr.cx0 = max(left - b, 0); jr.cx1 = min(right - b, t.width);
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
             c.alpha = d.global_alpha;
             if (jr.kind == JOB_SHADOW) {
                 for (int k = 0; k < 4; ++k) c.color[k] = d.shadow_color[k];
-                c.border = jr.border; c.left = jr.left; c.top = jr.top; c.bw = jr.bw;
+                c.border = jr.border; c.left = jr.left - jr.skew; c.top = jr.top; c.bw = jr.pitch;
             } else if (jr.kind == JOB_MAIN) {
                 const brush_rec &b = f.brushes[d.brush];
                 c.brush_type = b.n_colors ? b.type : 0xffu;     // 0xff: empty brush paints nothing

@@ -4,12 +4,17 @@
 //                    canvas space): coverage * paint.alpha -> float plane
 //                    (hpp:2430-2452), coverage rebuilt from the sorted runs exactly
 //                    like the compositor does (tile_cov.cuh)
-//   k_blur_rows      the three extended-box passes (Gwosdek et al.) of one axis fused in shared
-//                    memory, zero outside the working rectangle (hpp:2453-2503).  Each output is
-//                      (w1+w2) * sum_{|d|<=r} s[i+d] + w1 * (s[i-r-1] + s[i+r+1])
-//                    which is what the reference's running sum maintains.
-//   k_transpose      32x32 tiled transpose so the column passes reuse the row kernel with
-//                    coalesced accesses: rows, transpose, rows, transpose back.
+//   k_blur_stream    the three extended-box passes (Gwosdek et al.) of one axis, zero outside the
+//                    working rectangle (hpp:2453-2503), as ONE streaming sweep: a thread owns one
+//                    line (a plane row for the x axis, a plane column for the y axis) and pushes
+//                    every sample through three cascaded running sums whose 2r+3-deep histories
+//                    live in shared memory.  The running sum is updated with the reference's own
+//                    four terms in the reference's order, so a line that is swept in one piece is
+//                    bit-identical to the reference.  One global read + one write per pixel and
+//                    axis (16 B per working pixel for the whole blur = the algorithmic figure).
+//   k_blur_rows      fallback for radii whose history does not fit (r > kStreamMaxRadius): the
+//   k_transpose      three passes per row in shared memory, each output a windowed sum, with
+//                    32x32 tiled transposes around the column passes.
 // The blurred plane is consumed by the tile compositor (composite.cu).
 #include "frame.cuh"
 #include "tile_cov.cuh"
@@ -107,21 +112,266 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     const cov_source cs = make_cov_source(f, sb);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *plane = f.planes + jr.plane_offset;
+    // a solid brush has one alpha for the whole plane (negative: evaluate the brush per pixel)
+    const float flat_alpha = br.type == CB200_BRUSH_COLOR ? (br.n_colors ? f.colors[br.first_color].w : 0.0f) : -1.0f;
     for (uint32_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
         int tx = jr.tx0 + int(tl % uint32_t(jr.tw)), ty = jr.ty0 + int(tl / uint32_t(jr.tw));
         uint32_t te = jr.te_base + tl;
         int x = tx * kTile + lane;
+        // row info of the whole tile in two coalesced loads; most rows have no run in the tile
+        const float carried = cs.backdrop[te * kTile + lane];
+        const uint32_t first = cs.first[te * kTile + lane];
         for (int k = 0; k < kTile / (kBlock / 32); ++k) {
             int ly = warp + k * (kBlock / 32), y = ty * kTile + ly;
-            float sum = tile_row_sum(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
+            float sum = __shfl_sync(0xffffffffu, carried, ly);
+            if (__shfl_sync(0xffffffffu, first, ly) != kNoRun) sum = tile_row_sum(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
             float cov = fminf(fabsf(sum), 1.0f);
             if (x < jr.left || x >= jr.left + jr.bw || y < jr.top || y >= jr.top + jr.bh) continue;
             float v = 0.0f;
             if (cov >= kThreshold) {
-                vec2 centre = v2(float(x) + 0.5f, float(y) + 0.5f) - v2(jr.off_x, jr.off_y);
-                v = cov * paint_alpha(f, br, d.inverse, centre);
+                if (flat_alpha >= 0.0f) v = cov * flat_alpha;
+                else {
+                    vec2 centre = v2(float(x) + 0.5f, float(y) + 0.5f) - v2(jr.off_x, jr.off_y);
+                    v = cov * paint_alpha(f, br, d.inverse, centre);
+                }
             }
-            plane[size_t(y - jr.top) * size_t(jr.bw) + size_t(x - jr.left)] = v;
+            plane[size_t(y - jr.top) * size_t(jr.pitch) + size_t(x - jr.left + jr.skew)] = v;
+        }
+    }
+}
+
+// ---- streaming blur ---------------------------------------------------------------------------
+constexpr int kStreamThreads = 128;        // lines in flight per CTA; every warp works on its own
+constexpr int kStreamMaxRadius = 30;       // history 3 x (2r+3) x 128 floats <= 95 KB
+constexpr int kStreamChunk = 1024;         // longer lines are swept in pieces (with a 3(r+1) run-in)
+
+struct stream_pass { float running, prev; };
+
+// Histories: ring[(slot * 3 + pass) * kStreamThreads + tid], slot in [0, 2r+3): the three passes of
+// one slot sit at constant offsets from one another, so a step needs two slot addresses in all.
+constexpr int kRingSlot = 3 * kStreamThreads;                      // floats per slot
+constexpr int kRingPass = kStreamThreads;                          // floats between passes
+
+// One sample `v` (index ik + r + 1 of this pass's input) enters; returns output ik of the pass.
+// `at` points at this thread's entry of the slot that holds the sample 2r+3 back (overwritten by
+// v), `at1` at the next older slot.  hpp:2463-2479: running -= w2 s[x-r-1]; running -= w1 s[x-r-2];
+// running += w2 s[x+r]; running += w1 s[x+r+1].
+__device__ __forceinline__ float stream_step(float *ring, int W, int slot, int slot1, stream_pass &ps, float v,
+                                             int ik, int start, int len, float w1, float w2, float w12)
+{
+    const float a = ring[slot * kRingSlot], b = ring[slot1 * kRingSlot];
+    ring[slot * kRingSlot] = v;
+    if (ik > start) {
+        float run = ps.running;
+        run -= w2 * b;
+        run -= w1 * a;
+        run += w2 * ps.prev;
+        run += w1 * v;
+        ps.running = run;
+    } else if (ik == start) {
+        // first output of the sweep: w1 s[r+1] + w12 (s[0] + ... + s[r]) at the head of a line
+        // (hpp:2460-2462; the history left of the line is zero), the full window mid-line
+        float run = w1 * v;
+        int at = slot1;
+        run += w1 * ring[at * kRingSlot];
+#pragma unroll 1
+        for (int j = W - 2; j >= 1; --j) {
+            at = at + 1 == W ? 0 : at + 1;
+            run += w12 * ring[at * kRingSlot];
+        }
+        ps.running = run;
+    }
+    ps.prev = v;
+    return (ik >= start && ik < len) ? ps.running : 0.0f;
+}
+
+// The same once every pass is under way and no pass has run off the end of the line.
+__device__ __forceinline__ float steady_step(float *at, float *at1, stream_pass &ps, float v, float w1, float w2)
+{
+    const float a = *at, b = *at1;
+    *at = v;
+    float run = ps.running;
+    run -= w2 * b;
+    run -= w1 * a;
+    run += w2 * ps.prev;
+    run += w1 * v;
+    ps.running = run;
+    ps.prev = v;
+    return run;
+}
+
+__device__ __forceinline__ uint32_t sweep_units(int len, int cross)
+{
+    if (len <= 0 || cross <= 0) return 0;
+    return uint32_t((cross + 31) / 32) * uint32_t((len + kStreamChunk - 1) / kStreamChunk);
+}
+
+// Prefix sums of every shadow job's sweep units (32 adjacent lines x one chunk), so that the
+// sweeps can deal all units of a frame to warps as they become free -- plane sizes differ by
+// orders of magnitude.  Also resets the two unit tickets.  One CTA.
+__global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
+{
+    __shared__ uint32_t sm[33];
+    if (f.hdr->overflow) return;
+    const uint32_t n = f.n_shadow_jobs;
+    uint32_t *along_x = f.blur_units, *along_y = f.blur_units + n + 1;
+    uint32_t carry_x = 0, carry_y = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t ux = 0, uy = 0;
+        if (i < n) {
+            const job_rec &jr = f.jobs[f.shadow_jobs[i]];
+            if (jr.radius <= kStreamMaxRadius) { ux = sweep_units(jr.bw, jr.bh); uy = sweep_units(jr.bh, jr.pitch); }
+        }
+        uint32_t total_x, total_y;
+        const uint32_t ex = block_exclusive_scan(ux, sm, total_x);
+        const uint32_t ey = block_exclusive_scan(uy, sm, total_y);
+        if (i < n) { along_x[i] = carry_x + ex; along_y[i] = carry_y + ey; }
+        carry_x += total_x; carry_y += total_y;
+    }
+    if (threadIdx.x == 0) {
+        along_x[n] = carry_x; along_y[n] = carry_y;
+        f.blur_units[2 * (n + 1)] = 0; f.blur_units[2 * (n + 1) + 1] = 0;
+    }
+}
+
+// Persistent grid of independent warps; each takes the next unit off a ticket counter.
+template <bool kAlongRows>
+__global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, const float *src_base, float *dst_base)
+{
+    extern __shared__ float blur_smem[];
+    if (f.hdr->overflow) return;
+    const uint32_t n_jobs = f.n_shadow_jobs;
+    const uint32_t *prefix = f.blur_units + (kAlongRows ? 0u : n_jobs + 1u);
+    uint32_t *ticket = f.blur_units + 2 * (n_jobs + 1) + (kAlongRows ? 0 : 1);
+    const uint32_t n_units = prefix[n_jobs];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // x sweep: one 32 x 32 staging tile per warp (skewed), then everybody's histories
+    float *tile = blur_smem + warp * 32 * 33;
+    float *ring1 = blur_smem + (kAlongRows ? kStreamThreads * 33 : 0) + tid;
+    for (;;) {
+        uint32_t global_unit = 0;
+        if (lane == 0) global_unit = atomicAdd(ticket, 1u);
+        global_unit = __shfl_sync(0xffffffffu, global_unit, 0);
+        if (global_unit >= n_units) break;
+        uint32_t lo = 0, hi = n_jobs;                               // last job whose prefix <= global_unit
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (prefix[mid] <= global_unit) lo = mid; else hi = mid;
+        }
+        const job_rec &jr = f.jobs[f.shadow_jobs[lo]];
+        const int r = jr.radius;
+        const int W = 2 * r + 3, p = r + 1;
+        // lines of the y sweep are storage columns, so that a warp always covers one aligned 128 B line
+        const int len = kAlongRows ? jr.bw : jr.bh, cross = kAlongRows ? jr.bh : jr.pitch;
+        const int pitch = jr.pitch, skew = jr.skew;
+        const float w1 = jr.w1, w2 = jr.w2, w12 = jr.w1 + jr.w2;
+        const float *src = src_base + jr.plane_offset;
+        float *dst = dst_base + jr.plane_offset;
+        float *ring2 = ring1 + kRingPass, *ring3 = ring2 + kRingPass;
+        const int n_strips = (cross + 31) / 32;
+        const int unit = int(global_unit - prefix[lo]);
+        const int strip = unit % n_strips, chunk = unit / n_strips;
+        const int line = strip * 32 + lane;
+        const bool active = kAlongRows ? line < cross : (line >= skew && line < skew + jr.bw);
+        const int y0 = chunk * kStreamChunk, y1 = min(len, y0 + kStreamChunk);
+        const int t_begin = chunk ? y0 - 3 * p : 0, t_last = y1 + 3 * p;
+        const int start1 = chunk ? y0 - 2 * p : 0, start2 = chunk ? y0 - p : 0, start3 = chunk ? y0 : 0;
+        // [t_steady, t_inside): every pass is past its first output and still inside the line, and
+        // every output lands in [y0, y1) -- the branch-free part of the sweep
+        const int t_steady = start3 + 3 * p + 1, t_inside = min(len, t_last);
+        for (int k = 0; k < 3 * W; ++k) ring1[k * kStreamThreads] = 0.0f;
+        stream_pass p1 = {0.0f, 0.0f}, p2 = {0.0f, 0.0f}, p3 = {0.0f, 0.0f};
+        int slot = 0;
+        auto push = [&](int t, float v) -> float {
+            const int slot1 = slot + 1 == W ? 0 : slot + 1;
+            float o1 = stream_step(ring1, W, slot, slot1, p1, v, t - p, start1, len, w1, w2, w12);
+            float o2 = stream_step(ring2, W, slot, slot1, p2, o1, t - 2 * p, start2, len, w1, w2, w12);
+            float o3 = stream_step(ring3, W, slot, slot1, p3, o2, t - 3 * p, start3, len, w1, w2, w12);
+            slot = slot1;
+            return o3;
+        };
+        auto push_steady = [&](float v) -> float {
+            const int slot1 = slot + 1 == W ? 0 : slot + 1;
+            float *at = ring1 + slot * kRingSlot, *at1 = ring1 + slot1 * kRingSlot;
+            float o1 = steady_step(at, at1, p1, v, w1, w2);
+            float o2 = steady_step(at + kRingPass, at1 + kRingPass, p2, o1, w1, w2);
+            float o3 = steady_step(at + 2 * kRingPass, at1 + 2 * kRingPass, p3, o2, w1, w2);
+            slot = slot1;
+            return o3;
+        };
+        if (kAlongRows) {
+            // lines are plane rows: stage 32 columns of the warp's 32 rows through a skewed tile so
+            // that global accesses stay coalesced; the next block is fetched while this one is swept
+            float *mine = tile + lane * 33;
+            const float *in = src + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane);
+            const int rows_here = min(32, cross - strip * 32);
+            float ahead[32];
+            auto fetch = [&](int tb) {
+                const int col = tb + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    ahead[q] = (q < rows_here && col >= 0 && col < len) ? in[ptrdiff_t(q) * pitch + tb] : 0.0f;
+            };
+            const int t_first = t_begin - ((t_begin + skew) & 31);      // blocks start on 128 B lines
+            fetch(t_first);
+            for (int tb = t_first; tb < t_last; tb += 32) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) tile[q * 33 + lane] = ahead[q];
+                if (tb + 32 < t_last) fetch(tb + 32);
+                __syncwarp();
+                if (active) {
+                    // [u_steady, u_tail) of this block is the branch-free stretch
+                    const int u_first = max(t_begin - tb, 0), u_last = min(t_last - tb, 32);
+                    const int u_steady = min(max(t_steady - tb, u_first), u_last), u_tail = max(min(t_inside - tb, u_last), u_steady);
+#pragma unroll 1
+                    for (int u = u_first; u < u_steady; ++u) mine[u] = push(tb + u, mine[u]);
+#pragma unroll 4
+                    for (int u = u_steady; u < u_tail; ++u) mine[u] = push_steady(mine[u]);
+#pragma unroll 1
+                    for (int u = u_tail; u < u_last; ++u) mine[u] = push(tb + u, mine[u]);
+                }
+                __syncwarp();
+                const int col = tb + lane - 3 * p;
+                if (col >= y0 && col < y1) {
+                    float *out = dst + size_t(strip * 32) * size_t(pitch) + size_t(skew + col);
+#pragma unroll 8
+                    for (int q = 0; q < rows_here; ++q) out[size_t(q) * size_t(pitch)] = tile[q * 33 + lane];
+                }
+                __syncwarp();
+            }
+        } else {
+            if (!active) continue;
+            constexpr int kAhead = 8;
+            const float *in = src + size_t(line);
+            float ahead[kAhead];
+            auto fetch = [&](int tb) {
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) ahead[u] = tb + u < len ? in[size_t(tb + u) * size_t(pitch)] : 0.0f;
+            };
+            fetch(t_begin);
+            for (int tb = t_begin; tb < t_last; tb += kAhead) {
+                float v[kAhead];
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) v[u] = ahead[u];
+                if (tb + kAhead < t_last) fetch(tb + kAhead);
+                if (tb >= t_steady && tb + kAhead <= t_inside) {
+                    float *out = dst + size_t(tb - 3 * p) * size_t(pitch) + size_t(line);
+#pragma unroll
+                    for (int u = 0; u < kAhead; ++u) out[u * pitch] = push_steady(v[u]);
+                } else {
+#pragma unroll 1
+                    for (int u = 0; u < kAhead; ++u) {
+                        if (tb + u >= t_last) break;
+                        float x = v[0];                              // v[u] without indexing registers
+#pragma unroll
+                        for (int k = 1; k < kAhead; ++k) x = u == k ? v[k] : x;
+                        const float o = push(tb + u, x);
+                        const int i3 = tb + u - 3 * p;
+                        if (i3 >= y0 && i3 < y1) dst[size_t(i3) * size_t(pitch) + size_t(line)] = o;
+                    }
+                }
+            }
         }
     }
 }
@@ -181,11 +431,13 @@ __global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const floa
     const job_rec &jr = f.jobs[f.shadow_jobs[blockIdx.y]];
     const int len = transposed ? jr.bh : jr.bw, rows = transposed ? jr.bw : jr.bh;
     const int r = jr.radius, pad = r + 1;
-    if (len <= 0 || rows <= 0) return;
+    if (len <= 0 || rows <= 0 || r <= kStreamMaxRadius) return;
     const int stride = sk(len + 2 * pad) + 1;
     const float w1 = jr.w1, w12 = jr.w1 + jr.w2;
-    const float *src = src_base + jr.plane_offset;
-    float *dst = dst_base + jr.plane_offset;
+    // upright planes are pitched (job_rec::pitch, skew); transposed ones are compact bw rows of bh
+    const size_t row_stride = transposed ? size_t(len) : size_t(jr.pitch);
+    const float *src = src_base + jr.plane_offset + (transposed ? 0 : jr.skew);
+    float *dst = dst_base + jr.plane_offset + (transposed ? 0 : jr.skew);
     constexpr int kWarpsPerCta = kBlock / 32;
     if (2 * stride * kWarpsPerCta <= smem_floats) {
         // short rows: every warp blurs its own row, eight rows per CTA in flight
@@ -195,7 +447,7 @@ __global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const floa
         for (int i = lane; i < 2 * stride; i += 32) buf0[i] = 0.0f;
         __syncwarp();
         for (int row = blockIdx.x * kWarpsPerCta + warp; row < rows; row += gridDim.x * kWarpsPerCta)
-            blur_one_row<32>(src + size_t(row) * size_t(len), dst + size_t(row) * size_t(len), len, r, w1, w12,
+            blur_one_row<32>(src + size_t(row) * row_stride, dst + size_t(row) * row_stride, len, r, w1, w12,
                              buf0, buf1, lane);
         return;
     }
@@ -204,7 +456,7 @@ __global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const floa
     for (int i = threadIdx.x; i < 2 * stride; i += kBlock) buf0[i] = 0.0f;
     __syncthreads();
     for (int row = blockIdx.x; row < rows; row += gridDim.x)
-        blur_one_row<kBlock>(src + size_t(row) * size_t(len), dst + size_t(row) * size_t(len), len, r, w1, w12,
+        blur_one_row<kBlock>(src + size_t(row) * row_stride, dst + size_t(row) * row_stride, len, r, w1, w12,
                              buf0, buf1, threadIdx.x);
 }
 
@@ -217,21 +469,23 @@ __global__ void __launch_bounds__(kBlock) k_transpose(device_frame f, const floa
     if (h->overflow) return;
     const job_rec &jr = f.jobs[f.shadow_jobs[blockIdx.y]];
     const int sw = back ? jr.bh : jr.bw, sh = back ? jr.bw : jr.bh;   // source is sh rows of sw
-    if (sw <= 0 || sh <= 0) return;
-    const float *src = src_base + jr.plane_offset;
-    float *dst = dst_base + jr.plane_offset;
+    if (sw <= 0 || sh <= 0 || jr.radius <= kStreamMaxRadius) return;
+    // the upright side is pitched, the transposed side compact
+    const size_t src_stride = back ? size_t(sw) : size_t(jr.pitch), dst_stride = back ? size_t(jr.pitch) : size_t(sh);
+    const float *src = src_base + jr.plane_offset + (back ? 0 : jr.skew);
+    float *dst = dst_base + jr.plane_offset + (back ? jr.skew : 0);
     const int tiles_x = (sw + 31) / 32, tiles_y = (sh + 31) / 32;
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;             // 32 x 8 threads
     for (int tl = blockIdx.x; tl < tiles_x * tiles_y; tl += gridDim.x) {
         const int x0 = (tl % tiles_x) * 32, y0 = (tl / tiles_x) * 32;
         for (int k = ly; k < 32; k += 8) {
             int x = x0 + lx, y = y0 + k;
-            tile[k][lx] = (x < sw && y < sh) ? src[size_t(y) * size_t(sw) + size_t(x)] : 0.0f;
+            tile[k][lx] = (x < sw && y < sh) ? src[size_t(y) * src_stride + size_t(x)] : 0.0f;
         }
         __syncthreads();
         for (int k = ly; k < 32; k += 8) {
             int x = y0 + lx, y = x0 + k;                                  // destination is sw rows of sh
-            if (x < sh && y < sw) dst[size_t(y) * size_t(sh) + size_t(x)] = tile[lx][k];
+            if (x < sh && y < sw) dst[size_t(y) * dst_stride + size_t(x)] = tile[lx][k];
         }
         __syncthreads();
     }
@@ -244,23 +498,36 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
     if (!f.n_shadow_jobs) return;
     dim3 grid(64, f.n_shadow_jobs);
     k_shadow_raster<<<grid, kBlock, 0, s>>>(f, sorted_buffer);
-    // rows -> transpose -> rows (= columns) -> transpose back; the result ends up in f.planes
     const int longest = std::max(t.width, t.height) + f.max_shadow_pad;
-    // room for one longest row (CTA mode) and for eight rows of up to 512 pixels (warp mode)
-    const int pad2 = 2 * (f.max_shadow_radius + 1);
-    auto skewed = [](int n) { return n + (n >> 5) + 1; };
-    const int smem_floats = std::max(2 * skewed(longest + pad2), 16 * skewed(std::min(longest, 512) + pad2));
-    const size_t smem_bytes = size_t(smem_floats) * sizeof(float);
-    static size_t configured = 0;
-    if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
-        cudaFuncSetAttribute(k_blur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
-        configured = smem_bytes;
+    if (f.min_shadow_radius <= kStreamMaxRadius) {
+        // x sweep planes -> planes_tmp, y sweep back into planes
+        const int w = 2 * std::min(f.max_shadow_radius, kStreamMaxRadius) + 3;
+        const size_t ring_bytes = size_t(3 * w * kStreamThreads) * sizeof(float);
+        const size_t row_bytes = ring_bytes + size_t(kStreamThreads * 33) * sizeof(float);
+        if (row_bytes > 48 * 1024) {                             // per device, so not cached in a static
+            cudaFuncSetAttribute(k_blur_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
+            cudaFuncSetAttribute(k_blur_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
+        }
+        auto resident = [](size_t smem) { return int(std::min<size_t>(16, (227 * 1024) / (smem + 1024))); };
+        k_blur_units<<<1, kBlock, 0, s>>>(f);
+        k_blur_stream<true><<<kSMs * resident(row_bytes), kStreamThreads, row_bytes, s>>>(f, f.planes, f.planes_tmp);
+        k_blur_stream<false><<<kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s>>>(f, f.planes_tmp, f.planes);
     }
-    dim3 rgrid(256, f.n_shadow_jobs), tgrid(128, f.n_shadow_jobs);
-    k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 0, smem_floats);
-    k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 0);
-    k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 1, smem_floats);
-    k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 1);
+    if (f.max_shadow_radius > kStreamMaxRadius) {
+        // rows -> transpose -> rows (= columns) -> transpose back; the result ends up in f.planes
+        // room for one longest row (CTA mode) and for eight rows of up to 512 pixels (warp mode)
+        const int pad2 = 2 * (f.max_shadow_radius + 1);
+        auto skewed = [](int n) { return n + (n >> 5) + 1; };
+        const int smem_floats = std::max(2 * skewed(longest + pad2), 16 * skewed(std::min(longest, 512) + pad2));
+        const size_t smem_bytes = size_t(smem_floats) * sizeof(float);
+        if (smem_bytes > 48 * 1024)
+            cudaFuncSetAttribute(k_blur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+        dim3 rgrid(256, f.n_shadow_jobs), tgrid(128, f.n_shadow_jobs);
+        k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 0, smem_floats);
+        k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 0);
+        k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 1, smem_floats);
+        k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 1);
+    }
 }
 
 }  // namespace cb200

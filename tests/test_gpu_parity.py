@@ -58,6 +58,37 @@ def test_tiger_shadow_config3_small(lib):
     assert nbad == 0, "%d floats off, max %.3g" % (nbad, worst)
 
 
+def _shadow_scene(width, height, blur, offset=(7.0, -5.0)):
+    from canvas_ity_b200.script import ScriptWriter
+    w = ScriptWriter()
+    w.floats("SET_SHADOW_COLOR", 0.1, 0.0, 0.3, 0.8)
+    w.floats("SET_SHADOW_OFFSET_X", offset[0]); w.floats("SET_SHADOW_OFFSET_Y", offset[1])
+    w.floats("SET_SHADOW_BLUR", blur)
+    w.raw("Bi4f", H.OP["SET_COLOR"], 0, 0.9, 0.5, 0.1, 0.7)
+    w.bare("BEGIN_PATH")
+    w.floats("MOVE_TO", 0.06 * width, 0.2 * height)
+    w.floats("BEZIER_CURVE_TO", 0.4 * width, -0.3 * height, 0.7 * width, 1.4 * height, 0.95 * width, 0.3 * height)
+    w.floats("LINE_TO", 0.5 * width, 0.93 * height)
+    w.bare("CLOSE_PATH"); w.bare("FILL")
+    w.raw("Bi4f", H.OP["SET_COLOR"], 1, 0.0, 0.6, 0.9, 1.0)
+    w.floats("SET_LINE_WIDTH", 0.02 * min(width, height))
+    w.bare("BEGIN_PATH"); w.floats("MOVE_TO", 0.1 * width, 0.8 * height)
+    w.floats("LINE_TO", 0.9 * width, 0.1 * height); w.bare("STROKE")
+    return w.take()
+
+
+@pytest.mark.parametrize("width,height,blur", [(1500, 200, 9.0), (200, 2300, 14.0), (300, 260, 90.0), (1200, 1100, 70.0),
+                                               (256, 256, 61.0), (256, 256, 63.0)],
+                         ids=["long_rows", "long_columns", "big_radius", "big_radius_long", "radius_30", "radius_31"])
+def test_shadow_blur_sweeps(lib, width, height, blur):
+    """Planes longer than one sweep chunk (1024) and radii either side of the streaming limit (30)."""
+    script = _shadow_scene(width, height, blur)
+    got = H.render_script(lib, script, width, height)
+    want = H.render_oracle(script, width, height)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "%d floats off, max %.3g" % (nbad, worst)
+
+
 def test_bands_are_bit_identical_to_the_whole(lib):
     """Scanline-band sharding: rendering rows [y0,y1) alone gives exactly the bytes and
     floats of the same rows of the full render."""
