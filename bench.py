@@ -42,6 +42,17 @@ SIZE = 4096
 ALGO_BYTES_PER_COMPOSITED_PIXEL = 32.0     # 16 B load + 16 B store of the float4 texel
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` capture
+    (profiles/*ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None if absent."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_traffic.json")), reverse=True):
+        entry = json.load(open(path)).get(kernel)
+        if entry:
+            return entry["dram_bytes_per_launch"]
+    return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -242,6 +253,56 @@ def main():
     check(lib.cb200_get_stats(cv, C.byref(stats)))
     launches = int(stats.kernel_launches - launches_before)
     composited = int(stats.composited_pixels)
+    stages_ms = {"geometry": stats.geometry_ms, "raster": stats.raster_ms, "sort": stats.sort_ms, "coverage": stats.coverage_ms,
+                 "composite": stats.composite_ms, "frame": stats.last_frame_ms}
+
+    # ---- the other passes of the north star, each against its own algorithmic bytes ----
+    passes = None
+    if not bands and rank == 0:
+        stage = {k: [] for k in ("sort", "coverage")}
+        for _ in range(5):
+            check(lib.cb200_frame_replay(cv, 1))
+            check(lib.cb200_get_stats(cv, C.byref(stats)))
+            stage["sort"].append(stats.sort_ms)
+            stage["coverage"].append(stats.coverage_ms)
+        runs = int(stats.raw_runs)
+        rb = []
+        dev_ptr = C.c_void_p()
+        for _ in range(6):                                      # sRGB + dither kernel alone, device to device
+            check(lib.cb200_read_rgba8_device(cv, C.byref(dev_ptr)))
+            check(lib.cb200_get_stats(cv, C.byref(stats)))
+            rb.append(stats.readback_ms)
+        peak_gbs = measured_hbm_peak()[0]
+        rb_ms = float(np.median(rb[1:]))
+        passes = {
+            "readback": {"kernel": "k_readback", "ms": rb_ms, "bytes_per_pixel": 20,
+                         "achieved_gbs": 20.0 * size * size / rb_ms / 1e6, "frac_of_hbm_peak": 20.0 * size * size / rb_ms / 1e6 / peak_gbs},
+            "sort": {"kernels": "k_sort_hist/scan/scatter", "keys": runs, "ms": float(np.median(stage["sort"])),
+                     "gkeys_per_s": runs / float(np.median(stage["sort"])) / 1e6},
+            "coverage": {"kernels": "k_rows/k_rows_long/k_tile_flags", "runs": runs, "ms": float(np.median(stage["coverage"])),
+                         "gruns_per_s": runs / float(np.median(stage["coverage"])) / 1e6},
+        }
+        # config 3 of BASELINE.json on the same canvas: global_alpha 0.9, shadow_blur 16, shadow alpha 0.5
+        shadow_script = H.tiger_script(size, size, global_alpha=0.9, shadow_blur=16.0, shadow_color=(0, 0, 0, 0.5))
+        shadow_frame = H.lower_script(shadow_script, size, size)[0]
+        check(lib.cb200_frame_upload(cv, C.byref(shadow_frame.frame)))
+        rows3 = []
+        for i in range(3 + 8):
+            check(lib.cb200_frame_replay(cv, 1))
+            check(lib.cb200_get_stats(cv, C.byref(stats)))
+            if i >= 3:
+                rows3.append((stats.last_frame_ms, stats.blur_ms, stats.shadow_raster_ms, stats.composite_ms))
+        f_ms, b_ms, r_ms, c_ms = [float(np.median(c)) for c in zip(*rows3)]
+        plane_px, comp_px = int(stats.shadow_pixels), int(stats.composited_pixels)
+        passes["config3_tiger_alpha0.9_shadow_blur16"] = {
+            "frames_per_s": 1e3 / f_ms, "frame_ms": f_ms, "shadow_plane_pixels": plane_px, "composited_pixels": comp_px,
+            "blur": {"kernels": "k_blur_stream<x>, k_blur_stream<y>", "ms": b_ms, "bytes_per_pixel": 16,
+                     "achieved_gbs": 16.0 * plane_px / b_ms / 1e6, "frac_of_hbm_peak": 16.0 * plane_px / b_ms / 1e6 / peak_gbs},
+            "shadow_raster": {"kernel": "k_shadow_raster", "ms": r_ms, "bytes_per_pixel": 4,
+                              "achieved_gbs": 4.0 * plane_px / r_ms / 1e6},
+            "composite": {"kernel": "k_composite<general>", "ms": c_ms, "bytes_per_pixel": 32,
+                          "achieved_gbs": 32.0 * comp_px / c_ms / 1e6, "frac_of_hbm_peak": 32.0 * comp_px / c_ms / 1e6 / peak_gbs},
+        }
 
     # ---- end-to-end arm through the public API with host buffers: `e2e` ----
     # Every frame: fresh canvas state (save/restore + cb200_clear), canvas-script replay on the host
@@ -327,16 +388,17 @@ def main():
                        "composited_mpix_per_s": composited * value / 1e6 / (1 if bands else world) * (1 if bands else world),
                        "canvas_mpix_per_s": size * size * value / 1e6},
             "roofline": {"bound": "hbm", "kernel": "k_composite", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic("k_composite"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": composited * ALGO_BYTES_PER_COMPOSITED_PIXEL,
                          "kernel_ms": comp_avg_s * 1e3,
                          "note": "algorithmic = 32 B x composited pixels (3.05x overdraw); the tile compositor keeps "
                                  "overlapping draws in registers, so DRAM traffic is about 1/3 of this and frac may exceed 1"},
-            "stages_ms": {"geometry": stats.geometry_ms, "raster": stats.raster_ms, "sort": stats.sort_ms,
-                          "composite": stats.composite_ms, "frame": stats.last_frame_ms},
+            "stages_ms": stages_ms,
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
+        if passes:
+            line["passes"] = passes
         if e2e:
             line["e2e"] = {"value": e2e["frames"] * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                            "d2h_bytes_per_step": e2e["d2h"], "in_flight": args.e2e_lanes,

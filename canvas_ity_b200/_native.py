@@ -15,7 +15,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("draws", "cubics", "line_points", "edges", "raw_runs", "tile_entries",
                                            "composited_pixels", "shadow_pixels", "kernel_launches")] + \
                [(n, C.c_float) for n in ("last_frame_ms", "composite_ms", "raster_ms", "sort_ms", "geometry_ms",
-                                         "readback_ms")]
+                                         "readback_ms", "coverage_ms", "shadow_raster_ms", "blur_ms")]
 
 
 class Frame(C.Structure):          # cb200_frame

@@ -134,7 +134,7 @@ struct cb200_canvas {
     bool pending = false;                     // a frame was launched and not yet verified
     bool resident = false;                    // staged frame came from cb200_frame_upload
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[10];
     std::vector<cudaEvent_t> chunk_events;
     cb200_stats stats;
     uint64_t launches = 0;
@@ -596,7 +596,8 @@ int run_frame(cb200_canvas *cv)
     launch_sort(f, s, sf.key_bits, &sorted);
     CK(cudaEventRecord(cv->ev[3], s));
     launch_rows(f, cv->target, sorted, s);
-    launch_shadow(f, cv->target, sorted, s);
+    CK(cudaEventRecord(cv->ev[8], s));
+    launch_shadow(f, cv->target, sorted, s, cv->ev[9]);
     CK(cudaEventRecord(cv->ev[4], s));
     launch_composite(f, cv->target, sorted, s);
     CK(cudaEventRecord(cv->ev[5], s));
@@ -604,7 +605,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
                     ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-                    (sf.shadow_jobs.empty() ? 0 : 5) + 1;
+                    (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1;
     cv->pending = true;
     CK(cudaGetLastError());
     return CB200_OK;
@@ -653,6 +654,9 @@ int finish_pending(cb200_canvas *cv)
             cudaEventElapsedTime(&ms, cv->ev[1], cv->ev[2]); st.raster_ms = ms;
             cudaEventElapsedTime(&ms, cv->ev[2], cv->ev[3]); st.sort_ms = ms;
             cudaEventElapsedTime(&ms, cv->ev[4], cv->ev[5]); st.composite_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[3], cv->ev[8]); st.coverage_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[8], cv->ev[9]); st.shadow_raster_ms = ms;
+            cudaEventElapsedTime(&ms, cv->ev[9], cv->ev[4]); st.blur_ms = ms;
             st.draws = seen.n_draws;
             st.cubics = seen.n_units - seen.n_subpaths;
             st.line_points = seen.n_line_points + seen.n_dash_points + seen.n_stroke_points;
@@ -660,7 +664,7 @@ int finish_pending(cb200_canvas *cv)
             st.raw_runs = seen.n_runs;
             st.tile_entries = seen.n_tile_entries;
             st.composited_pixels = seen.composited_pixels;
-            st.shadow_pixels = seen.plane_floats;
+            st.shadow_pixels = seen.shadow_working_pixels;
             st.kernel_launches = cv->launches;
             cv->pending = false;
             return CB200_OK;
@@ -735,7 +739,7 @@ int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, 
     if (err == cudaSuccess) err = cudaMalloc(&cv->fb, px * sizeof(float4));
     if (err == cudaSuccess) err = cudaMemsetAsync(cv->fb, 0, px * sizeof(float4), cv->stream);
     if (err == cudaSuccess) err = cudaMallocHost(&cv->pinned_hdr, sizeof(frame_header));
-    for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->ev[i]);
+    for (int i = 0; i < 10 && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->ev[i]);
     if (err != cudaSuccess) {
         std::string why = cudaGetErrorString(err);
         cb200_canvas_destroy(cv);
@@ -833,7 +837,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 10; ++i)
         if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
     for (cudaEvent_t e : cv->chunk_events) cudaEventDestroy(e);
     if (cv->stream) cudaStreamDestroy(cv->stream);
@@ -989,6 +993,11 @@ int cb200_read_rgba8_device(cb200_canvas *cv, void **device_ptr)
     if (rc != CB200_OK) return rc;
     rc = readback_to_device(cv, cv->width, cv->band_rows, 0, cv->band_y0);
     if (rc != CB200_OK) return rc;
+    CK(cudaEventRecord(cv->ev[6], cv->stream));
+    CK(cudaEventSynchronize(cv->ev[6]));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, cv->ev[7], cv->ev[6]);
+    cv->stats.readback_ms = ms;                           // the sRGB + dither kernel alone on this path
     *device_ptr = cv->rgba8.p;
     return CB200_OK;
 }

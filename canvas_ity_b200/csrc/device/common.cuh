@@ -132,7 +132,8 @@ struct frame_header {
     uint32_t n_runs;
     uint32_t n_tile_entries;
     uint32_t n_long_rows;                  // scanline segments handed to k_rows_long
-    uint64_t plane_floats;
+    uint64_t plane_floats;               // storage (pitched)
+    uint64_t shadow_working_pixels;      // sum of bw * bh: what the reference blurs (hpp:2426)
     uint32_t overflow;                     // bit set: which capacity was exceeded
     uint32_t sort_bits_x, sort_bits_y, sort_bits;
     unsigned long long composited_pixels, shadow_pixels;

@@ -91,7 +91,8 @@ void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffe
 // composite.cu
 void launch_composite(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
 // shadow.cu
-void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
+void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s,
+                   cudaEvent_t after_raster);
 // pixels.cu
 // dst / src are tightly packed RGBA8 device buffers of dst_w x dst_h pixels
 void launch_readback(const float4 *fb, int width, int band_y0, int band_rows, uint8_t *dst, int dst_w,

@@ -364,9 +364,9 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
 __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_target t)
 {
     __shared__ uint32_t sm[33];
-    __shared__ unsigned long long plane_carry;
+    __shared__ unsigned long long plane_carry, working_carry;
     frame_header *h = f.hdr;
-    if (threadIdx.x == 0) plane_carry = 0;
+    if (threadIdx.x == 0) { plane_carry = 0; working_carry = 0; }
     __syncthreads();
     uint32_t n = h->n_jobs, carry = 0;
     for (uint32_t base = 0; base < n; base += blockDim.x) {
@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
         // plane storage: order of allocation does not matter, only disjointness
         if (plane) {
             unsigned long long off = atomicAdd(&plane_carry, plane);
+            atomicAdd(&working_carry, (unsigned long long)f.jobs[j].bw * (unsigned long long)f.jobs[j].bh);
             f.jobs[j].plane_offset = off;
             f.comp[j].plane_lo = uint32_t(off); f.comp[j].plane_hi = uint32_t(off >> 32);
         }
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
     if (threadIdx.x == 0) {
         h->n_tile_entries = carry;
         h->plane_floats = plane_carry;
+        h->shadow_working_pixels = working_carry;
         if (carry > f.cap_tiles) atomicOr(&h->overflow, OVF_TILES);
         if (plane_carry > f.cap_planes) atomicOr(&h->overflow, OVF_PLANES);
     }

@@ -493,11 +493,13 @@ __global__ void __launch_bounds__(kBlock) k_transpose(device_frame f, const floa
 
 }  // namespace
 
-void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
+void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s,
+                   cudaEvent_t after_raster)
 {
-    if (!f.n_shadow_jobs) return;
+    if (!f.n_shadow_jobs) { cudaEventRecord(after_raster, s); return; }
     dim3 grid(64, f.n_shadow_jobs);
     k_shadow_raster<<<grid, kBlock, 0, s>>>(f, sorted_buffer);
+    cudaEventRecord(after_raster, s);
     const int longest = std::max(t.width, t.height) + f.max_shadow_pad;
     if (f.min_shadow_radius <= kStreamMaxRadius) {
         // x sweep planes -> planes_tmp, y sweep back into planes

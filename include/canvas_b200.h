@@ -191,6 +191,9 @@ typedef struct cb200_stats {
     float    last_frame_ms;        /* CUDA events on the canvas stream */
     float    composite_ms;         /* the tile compositor only */
     float    raster_ms, sort_ms, geometry_ms, readback_ms;
+    float    coverage_ms;          /* scanline walk: running sums + tile entries (after the sort) */
+    float    shadow_raster_ms;     /* coverage * alpha into the shadow planes */
+    float    blur_ms;              /* both blur sweeps */
 } cb200_stats;
 
 int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);
