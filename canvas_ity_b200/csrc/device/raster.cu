@@ -279,7 +279,11 @@ __global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
     for (uint32_t k = 0; k < ipt; ++k) {
         uint32_t it = first + k;
         if (it >= end) break;
-        while (it >= f.piece_row_off[slot] + f.piece_rows[slot]) ++slot;
+        if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) {
+            // usually the next slot; a band canvas has long stretches of pieces without rows
+            ++slot;
+            if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) slot = find_piece(f.piece_row_off, n_slots, it);
+        }
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
         uint32_t runs = uint32_t(w.inner) + 2;
@@ -314,7 +318,11 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
     for (uint32_t k = 0; k < ipt; ++k) {
         uint32_t it = first + k;
         if (it >= end) break;
-        while (it >= f.piece_row_off[slot] + f.piece_rows[slot]) ++slot;
+        if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) {
+            // usually the next slot; a band canvas has long stretches of pieces without rows
+            ++slot;
+            if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) slot = find_piece(f.piece_row_off, n_slots, it);
+        }
         uint32_t j = f.piece_job[slot];
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
