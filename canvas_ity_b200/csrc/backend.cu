@@ -109,7 +109,7 @@ struct cb200_canvas {
 
     // device work buffers
     dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
-        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, long_rows, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, te_flags, te_job,
+        half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, long_rows, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, row_piece, te_flags, te_job,
         te_first, partials, sort_hist;
     dev_buf<float2> pts;
     dev_buf<loop_span> loops;
@@ -407,6 +407,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->piece_rlo.reserve(3 * size_t(want_items)));
     CK(cv->piece_row_off.reserve(3 * size_t(want_items)));
     CK(cv->row_runs.reserve(want_rows));
+    CK(cv->row_piece.reserve(want_rows));
     CK(cv->keys0.reserve(want_runs));
     CK(cv->keys1.reserve(want_runs));
     CK(cv->vals0.reserve(want_runs));
@@ -554,7 +555,7 @@ int upload_frame(cb200_canvas *cv)
     f.pieces = cv->pieces.p; f.piece_job = cv->piece_job.p; f.piece_rows = cv->piece_rows.p;
     f.piece_rlo = cv->piece_rlo.p; f.piece_row_off = cv->piece_row_off.p;
     f.cap_items = cv->cap_items;
-    f.row_runs = cv->row_runs.p; f.cap_rows = cv->cap_rows;
+    f.row_runs = cv->row_runs.p; f.row_piece = cv->row_piece.p; f.cap_rows = cv->cap_rows;
     f.keys[0] = cv->keys0.p; f.keys[1] = cv->keys1.p; f.vals[0] = cv->vals0.p; f.vals[1] = cv->vals1.p;
     f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p; f.long_rows = cv->long_rows.p;
     f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
@@ -832,7 +833,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
     cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->half_last.release(); cv->visit_prev.release(); cv->visit_close.release(); cv->piece_job.release();
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
-    cv->row_runs.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
+    cv->row_runs.release(); cv->row_piece.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();

@@ -52,7 +52,7 @@ struct device_frame {
     float4 *pieces;        uint32_t *piece_job;  uint32_t *piece_rows;   // 3 per item
     uint32_t *piece_rlo, *piece_row_off;
     uint32_t cap_items;
-    uint32_t *row_runs;    uint32_t cap_rows;          // per (piece,row)
+    uint32_t *row_runs, *row_piece;  uint32_t cap_rows;   // per (piece,row): run count, piece slot
     uint64_t *keys[2];     float *vals[2];            uint32_t cap_runs;
     float *cumulative;
     uint32_t *long_rows;                               // segment heads too long for one thread

@@ -129,28 +129,51 @@ __global__ void __launch_bounds__(kBlock) k_job_items(device_frame f)
 // Sutherland-Hodgman uses (hpp:2220-2222); only meaningful when sa * sb < 0.
 __device__ __forceinline__ float cross_at(float sa, float sb) { return sa / (sa - sb); }
 
+// Work mapping of the four kernels below: a CTA owns a contiguous slice of the items in whole
+// tiles of kBlock, and thread t takes item `tile + t` -- neighbouring lanes read and write
+// neighbouring records, whatever the frame size (a batch frame has ~10^8 row items).  Count
+// kernels leave one total per CTA (-> exclusive bases by finish_partials), emit kernels scan
+// tile by tile on top of their CTA's base.
+__device__ __forceinline__ void tile_slice(uint32_t n, uint32_t &begin, uint32_t &end)
+{
+    uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + kBlock - 1) / kBlock * kBlock;
+    uint64_t b = uint64_t(per) * blockIdx.x;
+    begin = b < n ? uint32_t(b) : n;
+    end = b + per < n ? uint32_t(b + per) : n;
+}
+
+// Job of item `it`; the lanes of a warp hold consecutive items and `j` is the lane's previous
+// answer.  One binary search per warp (first lane's item), then a short walk.
+__device__ __forceinline__ uint32_t job_of_item(const device_frame &f, uint32_t n_jobs, uint32_t it, bool valid, uint32_t j)
+{
+    const bool stale = valid && !(it >= f.jobs[j].first_item && it < f.jobs[j].first_item + f.jobs[j].n_items);
+    if (!__any_sync(0xffffffffu, stale)) return j;
+    const uint32_t it0 = __shfl_sync(0xffffffffu, it, 0);
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (f.jobs[mid].first_item <= it0) lo = mid; else hi = mid;
+    }
+    if (valid)
+        while (it >= f.jobs[lo].first_item + f.jobs[lo].n_items) ++lo;
+    return lo;
+}
+
 __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target t)
 {
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
-    uint32_t n = h->overflow ? 0 : h->n_items, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    uint32_t j = 0;
-    if (first < end) {                                   // job of my first item
-        uint32_t lo = 0, hi = h->n_jobs;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (f.jobs[mid].first_item <= first) lo = mid; else hi = mid;
-        }
-        j = lo;
-    }
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t it = first + k;
+    uint32_t n = h->overflow ? 0 : h->n_items, begin, end;
+    tile_slice(n, begin, end);
+    const uint32_t n_jobs = h->n_jobs;
+    uint32_t sum = 0, j = 0;
+    for (uint32_t tile = begin; tile < end; tile += kBlock) {
+        const uint32_t it = tile + threadIdx.x;
         const bool valid = it < end;
         int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;     // pixel bounds of this item's pieces
+        j = job_of_item(f, n_jobs, it, valid, j);
         if (valid) {
-        while (it >= f.jobs[j].first_item + f.jobs[j].n_items) ++j;
         const job_rec &job = f.jobs[j];
         uint32_t p = job.first_point + (it - job.first_item);
         loop_span loop = f.loops[f.pt_loop[p]];
@@ -239,24 +262,23 @@ __global__ void __launch_bounds__(kBlock) k_scan_rows(device_frame f)
 {
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
-    uint32_t n = h->overflow ? 0 : h->n_items, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
-        uint32_t s = (first + k) * 3;
-        sum += f.piece_rows[s] + f.piece_rows[s + 1] + f.piece_rows[s + 2];
-    }
-    uint32_t total;
-    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[4 * kGrid + blockIdx.x];
-    for (uint32_t k = 0; k < ipt && first + k < end; ++k) {
-        uint32_t s = (first + k) * 3;
-        for (int m = 0; m < 3; ++m) { f.piece_row_off[s + m] = at; at += f.piece_rows[s + m]; }
+    uint32_t n = h->overflow ? 0 : h->n_items, begin, end;
+    tile_slice(n, begin, end);
+    uint32_t carry = f.partials[4 * kGrid + blockIdx.x];
+    for (uint32_t tile = begin; tile < end; tile += kBlock) {
+        const uint32_t it = tile + threadIdx.x, s = it * 3;
+        uint32_t r0 = 0, r1 = 0, r2 = 0;
+        if (it < end) { r0 = f.piece_rows[s]; r1 = f.piece_rows[s + 1]; r2 = f.piece_rows[s + 2]; }
+        uint32_t total;
+        const uint32_t at = carry + block_exclusive_scan(r0 + r1 + r2, sm, total);
+        if (it < end) { f.piece_row_off[s] = at; f.piece_row_off[s + 1] = at + r0; f.piece_row_off[s + 2] = at + r0 + r1; }
+        carry += total;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && h->n_row_items > f.cap_rows) atomicOr(&h->overflow, OVF_ROWS);
 }
 
-// Largest piece slot whose offset is <= item (slots with zero rows share offsets;
-// the walk below skips them).
+// Largest piece slot whose offset is <= item (slots without rows share their offset with the
+// next slot that has some, so this is the slot that contains the item).
 __device__ __forceinline__ uint32_t find_piece(const uint32_t *off, uint32_t n_slots, uint32_t item)
 {
     uint32_t lo = 0, hi = n_slots;
@@ -267,27 +289,43 @@ __device__ __forceinline__ uint32_t find_piece(const uint32_t *off, uint32_t n_s
     return lo;
 }
 
+// The same for a whole warp whose lanes hold consecutive items: one binary search (first lane's
+// item), one coalesced load of the next 32 offsets, five shuffles per lane; only lanes whose slot
+// lies beyond that window (long stretches of pieces without rows: band canvases) search again.
+__device__ __forceinline__ uint32_t piece_of_row_item(const uint32_t *off, uint32_t n_slots, uint32_t it, bool valid)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t s0 = find_piece(off, n_slots, __shfl_sync(0xffffffffu, it, 0));
+    const uint32_t mine = s0 + uint32_t(lane) < n_slots ? off[s0 + uint32_t(lane)] : 0xffffffffu;
+    uint32_t k = 0;
+#pragma unroll
+    for (uint32_t step = 16; step; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, mine, int(k + step));
+        if (v <= it) k += step;
+    }
+    uint32_t slot = s0 + k;
+    if (valid && k == 31 && s0 + 32 < n_slots && off[s0 + 32] <= it) slot = find_piece(off, n_slots, it);
+    return slot;
+}
+
 __global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
 {
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
-    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    uint32_t n_slots = h->n_items * 3;
-    uint32_t slot = first < end ? find_piece(f.piece_row_off, n_slots, first) : 0;
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t it = first + k;
-        if (it >= end) break;
-        if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) {
-            // usually the next slot; a band canvas has long stretches of pieces without rows
-            ++slot;
-            if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) slot = find_piece(f.piece_row_off, n_slots, it);
-        }
+    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end;
+    tile_slice(n, begin, end);
+    const uint32_t n_slots = h->n_items * 3;
+    uint32_t sum = 0;
+    for (uint32_t tile = begin; tile < end; tile += kBlock) {
+        const uint32_t it = tile + threadIdx.x;
+        const bool valid = it < end;
+        const uint32_t slot = piece_of_row_item(f.piece_row_off, n_slots, valid ? it : end - 1, valid);
+        if (!valid) continue;
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
         uint32_t runs = uint32_t(w.inner) + 2;
         f.row_runs[it] = runs;
+        f.row_piece[it] = slot;
         sum += runs;
     }
     uint32_t total;
@@ -304,25 +342,20 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&h->overflow, OVF_RUNS);
         return;
     }
-    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end, ipt;
-    block_slice(n, begin, end, ipt);
-    uint32_t first = begin + threadIdx.x * ipt, sum = 0;
-    for (uint32_t k = 0; k < ipt && first + k < end; ++k) sum += f.row_runs[first + k];
-    uint32_t total;
-    uint32_t at = block_exclusive_scan(sum, sm, total) + f.partials[5 * kGrid + blockIdx.x];
-    uint32_t n_slots = h->n_items * 3;
-    uint32_t slot = first < end ? find_piece(f.piece_row_off, n_slots, first) : 0;
+    uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end;
+    tile_slice(n, begin, end);
+    uint32_t carry = f.partials[5 * kGrid + blockIdx.x];
     const uint32_t bx = h->sort_bits_x, by = h->sort_bits_y;
     uint64_t *keys = f.keys[0];
     float *vals = f.vals[0];
-    for (uint32_t k = 0; k < ipt; ++k) {
-        uint32_t it = first + k;
-        if (it >= end) break;
-        if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) {
-            // usually the next slot; a band canvas has long stretches of pieces without rows
-            ++slot;
-            if (it >= f.piece_row_off[slot] + f.piece_rows[slot]) slot = find_piece(f.piece_row_off, n_slots, it);
-        }
+    for (uint32_t tile = begin; tile < end; tile += kBlock) {
+        const uint32_t it = tile + threadIdx.x;
+        const bool valid = it < end;
+        uint32_t total;
+        uint32_t at = carry + block_exclusive_scan(valid ? f.row_runs[it] : 0u, sm, total);
+        carry += total;
+        if (!valid) continue;
+        const uint32_t slot = f.row_piece[it];
         uint32_t j = f.piece_job[slot];
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
@@ -330,26 +363,26 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         bool shadow = f.jobs[j].kind == JOB_SHADOW;
         int lo_x = 0x7fffffff, hi_x = -1;
         vec2 cur = w.now;
-        float px = w.px, carry = 0.0f;
+        float px = w.px, carry_area = 0.0f;
         for (int c = 0; c < w.inner; ++c) {
             float gx = px + 1.0f;
             vec2 nx = v2(gx, edge_y_at(e, gx));
             float strip = clamp01((nx.y - cur.y) * e.ystep);
             float mid = (nx.x + cur.x) * 0.5f;
             float area = (mid - px) * strip;
-            float delta = (carry + strip - area) * e.sign;
+            float delta = (carry_area + strip - area) * e.sign;
             keys[at] = row_key | uint64_t(uint32_t(px));
             vals[at] = delta;
             ++at;
             if (delta != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
-            carry = area;
+            carry_area = area;
             cur = nx;
             px = gx;
         }
         float strip = clamp01((w.stop.y - cur.y) * e.ystep);
         float mid = (w.stop.x + cur.x) * 0.5f;
         float area = (mid - px) * strip;
-        float d0 = (carry + strip - area) * e.sign, d1 = area * e.sign;
+        float d0 = (carry_area + strip - area) * e.sign, d1 = area * e.sign;
         keys[at] = row_key | uint64_t(uint32_t(px));         vals[at] = d0; ++at;
         keys[at] = row_key | uint64_t(uint32_t(px + 1.0f));  vals[at] = d1; ++at;
         if (shadow) {

@@ -7,7 +7,7 @@
 // (the run count lives on the device):
 //   k_sort_hist     per-CTA digit histogram of its slice (digit-major table)
 //   k_sort_scan     one CTA per digit: exclusive scan across the CTAs + digit total
-//   k_sort_scatter  each CTA re-reads its slice in order, 256 keys per step;
+//   k_sort_scatter  each CTA re-reads its slice in order, 2048 keys (8 per thread) per step;
 //                   ranks are made stable with warp match + per-warp digit counts
 #include "frame.cuh"
 
@@ -59,6 +59,12 @@ __global__ void __launch_bounds__(kBlock) k_sort_scan(device_frame f)
     if (threadIdx.x == 0) f.sort_hist[kMaxRadix * kGrid + blockIdx.x] = carry;
 }
 
+// Keys per thread and step of the scatter: a CTA ranks 2048 keys between two barriers.  Warp w
+// owns keys [w * 256, (w + 1) * 256) of the step, lane l its keys k * 32 + l, so "warp, then k,
+// then lane" is input order and the ranks below are stable.
+constexpr int kSortKeys = 8;
+constexpr int kSortStep = kBlock * kSortKeys;
+
 __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift, int width)
 {
     __shared__ uint32_t base[kMaxRadix];             // next free global slot per digit for this CTA
@@ -86,15 +92,31 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
     const float *vin = f.vals[src];
     uint64_t *kout = f.keys[src ^ 1];
     float *vout = f.vals[src ^ 1];
-    for (uint32_t tile = begin; tile < end; tile += kBlock) {
-        uint32_t i = tile + threadIdx.x;
-        bool valid = i < end;
-        uint64_t key = valid ? kin[i] : 0;
-        float val = valid ? vin[i] : 0.0f;
-        uint32_t digit = valid ? uint32_t(key >> shift) & mask : kMaxRadix + uint32_t(lane);
-        uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) warp_count[warp][digit] = __popc(peers);
+    uint32_t *mine = warp_count[warp];
+    for (uint32_t step = begin; step < end; step += kSortStep) {
+        uint64_t key[kSortKeys];
+        float val[kSortKeys];
+        uint32_t rank[kSortKeys];                    // rank among the warp's keys of the same digit
+        const uint32_t first = step + uint32_t(warp) * (32 * kSortKeys) + uint32_t(lane);
+#pragma unroll
+        for (int k = 0; k < kSortKeys; ++k) {
+            const uint32_t i = first + uint32_t(k) * 32;
+            const bool valid = i < end;
+            key[k] = valid ? kin[i] : ~0ull;
+            val[k] = valid ? vin[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kSortKeys; ++k) {
+            const bool valid = first + uint32_t(k) * 32 < end;
+            const uint32_t digit = uint32_t(key[k] >> shift) & mask;
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : kMaxRadix + uint32_t(lane));
+            const uint32_t ahead = __popc(peers & ((1u << lane) - 1u));
+            const uint32_t seen = valid ? mine[digit] : 0;
+            rank[k] = seen + ahead;
+            __syncwarp();
+            if (valid && ahead == 0) mine[digit] = seen + __popc(peers);
+            __syncwarp();
+        }
         __syncthreads();
         // each digit: prefix over the warps, then advance the CTA base
         for (uint32_t d = threadIdx.x; d < radix; d += kBlock) {
@@ -108,10 +130,13 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
             base[d] = run;
         }
         __syncthreads();
-        if (valid) {
-            uint32_t dst = warp_count[warp][digit] + rank;
-            kout[dst] = key;
-            vout[dst] = val;
+#pragma unroll
+        for (int k = 0; k < kSortKeys; ++k) {
+            if (first + uint32_t(k) * 32 < end) {
+                const uint32_t dst = mine[uint32_t(key[k] >> shift) & mask] + rank[k];
+                kout[dst] = key[k];
+                vout[dst] = val[k];
+            }
         }
         __syncthreads();
         // prefixes (also of digits absent from a warp) must not leak into the next step

@@ -294,3 +294,45 @@ def config5_script(index, with_text=True):
         x, y = 192 * u(), 192 * u()
         w.floats("FILL_TEXT", x, y, 1.0e30); w.blob(text.encode())
     return w.take()
+
+
+# ------------------------------------------------------------------ config 4 ----
+
+def lcg_image(n, seed=12345):
+    """n x n RGBA8 image of SURVEY 8d config 4: bytes = high byte of s = s * 1664525 + 1013904223."""
+    s, out = seed, bytearray(n * n * 4)
+    for i in range(len(out)):
+        s = (s * 1664525 + 1013904223) & 0xffffffff
+        out[i] = s >> 24
+    return bytes(out)
+
+
+_lcg_cache = {}
+
+
+def config4_script(kind, op, size, image_size=None):
+    """Full-canvas fill of SURVEY 8d config 4: kind in solid / linear / radial / image under composite op."""
+    w = ScriptWriter()
+    W = float(size)
+    w.ints("SET_COMPOSITE", op)
+    if kind == "solid":
+        w.ints("SET_COLOR", 0); w.raw("4f", 0.2, 0.5, 0.9, 0.7)
+        w.floats("FILL_RECTANGLE", 0, 0, W, W)
+    elif kind == "linear":
+        w.ints("SET_LINEAR_GRADIENT", 0); w.raw("4f", 0.1 * W, 0.2 * W, 0.9 * W, 0.8 * W)
+        for o, c in ((0.0, (1, 0, 0, 1)), (0.5, (0, 1, 0, 0.5)), (1.0, (0, 0, 1, 1))):
+            w.ints("ADD_COLOR_STOP", 0); w.raw("5f", o, *c)
+        w.floats("FILL_RECTANGLE", 0, 0, W, W)
+    elif kind == "radial":
+        w.ints("SET_RADIAL_GRADIENT", 0); w.raw("6f", 0.4 * W, 0.4 * W, 0.05 * W, 0.5 * W, 0.5 * W, 0.5 * W)
+        for o, c in ((0.0, (1, 1, 0, 1)), (1.0, (0, 1, 1, 0.3))):
+            w.ints("ADD_COLOR_STOP", 0); w.raw("5f", o, *c)
+        w.floats("FILL_RECTANGLE", 0, 0, W, W)
+    elif kind == "image":
+        n = image_size or (256 if size <= 2048 else 1024)
+        if n not in _lcg_cache:
+            _lcg_cache[n] = lcg_image(n)
+        w.ints("DRAW_IMAGE", n, n, 4 * n); w.raw("4f", 0, 0, W, W); w.blob(_lcg_cache[n])
+    else:
+        raise ValueError(kind)
+    return w.take()

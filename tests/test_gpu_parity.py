@@ -89,6 +89,22 @@ def test_shadow_blur_sweeps(lib, width, height, blur):
     assert nbad == 0, "%d floats off, max %.3g" % (nbad, worst)
 
 
+@pytest.mark.parametrize("op", [2, 15, 10], ids=["source_copy", "exclusive_or", "lighter"])
+@pytest.mark.parametrize("kind", ["solid", "linear", "radial", "image"])
+def test_config4_full_canvas_fills(lib, kind, op):
+    """Config 4: gradient / bicubic-image fills of the whole canvas over a translucent
+    background under copy / xor / lighter, at a size the oracle finishes quickly."""
+    size = 768
+    from canvas_ity_b200.script import ScriptWriter
+    bg = ScriptWriter()
+    bg.ints("SET_COLOR", 0); bg.raw("4f", 0.9, 0.8, 0.1, 0.6); bg.floats("FILL_RECTANGLE", 0, 0, float(size), float(size))
+    script = bg.take() + H.config4_script(kind, op, size, image_size=64)
+    got = H.render_script(lib, script, size, size)
+    want = H.render_oracle(script, size, size)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "%s op %d: %d floats off, max %.3g" % (kind, op, nbad, worst)
+
+
 def test_bands_are_bit_identical_to_the_whole(lib):
     """Scanline-band sharding: rendering rows [y0,y1) alone gives exactly the bytes and
     floats of the same rows of the full render."""

@@ -67,3 +67,31 @@ def test_empty_and_degenerate_inputs():
     got = H.render_oracle(w.take(), 32, 32)
     # the clip of an empty path hides everything; nothing was drawn anyway
     assert not got["f32"].any()
+
+
+@pytest.mark.parametrize("kind", ["solid", "linear", "radial", "image"])
+def test_config4_scenes_oracle_vs_reference_build(kind):
+    """The benchmark's extra scenes are not among the reference's tests, so the
+    oracle is pinned on them against the reference build itself (only where oracle/_ref exists)."""
+    ref = H.reference_library()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    for op in (2, 15, 10, 14):
+        script = H.config4_script(kind, op, 320, image_size=32)
+        got = H.render_oracle(script, 320, 320)
+        want = H.render_script(ref, script, 320, 320)
+        nbad, worst = H.float_mismatch(got["f32"], want["f32"], tol=2.0e-6)
+        assert nbad == 0, "%s op %d: oracle differs from the reference build by %.3g" % (kind, op, worst)
+
+
+def test_config3_and_config5_scenes_oracle_vs_reference_build():
+    ref = H.reference_library()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    scenes = [("tiger shadow", H.tiger_script(200, 200, global_alpha=0.9, shadow_blur=16.0, shadow_color=(0, 0, 0, 0.5)), 200)]
+    scenes += [("config5 #%d" % i, H.config5_script(i), 256) for i in (0, 7)]
+    for name, script, size in scenes:
+        got = H.render_oracle(script, size, size)
+        want = H.render_script(ref, script, size, size)
+        nbad, worst = H.float_mismatch(got["f32"], want["f32"], tol=2.0e-6)
+        assert nbad == 0, "%s: oracle differs from the reference build by %.3g" % (name, worst)

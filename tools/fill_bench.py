@@ -13,45 +13,9 @@ SIZE = int(os.environ.get("FILL_SIZE", 8192))
 OPS = {"source_copy": 2, "exclusive_or": 15, "lighter": 10, "source_over": 14}
 
 
-def lcg_image(n):
-    s, out = 12345, np.empty(n * n * 4, np.uint8)
-    for i in range(out.size):
-        s = (s * 1664525 + 1013904223) & 0xffffffff
-        out[i] = s >> 24
-    return out.tobytes()
-
-
-def scene(kind, op):
-    w = ScriptWriter()
-    W = H_ = float(SIZE)
-    w.ints("SET_COMPOSITE", op)
-    if kind == "solid":
-        w.ints("SET_COLOR", 0); w.raw("4f", 0.2, 0.5, 0.9, 0.7)
-        w.floats("FILL_RECTANGLE", 0, 0, W, H_)
-    elif kind == "linear":
-        w.ints("SET_LINEAR_GRADIENT", 0); w.raw("4f", 0.1 * W, 0.2 * H_, 0.9 * W, 0.8 * H_)
-        for o, c in ((0.0, (1, 0, 0, 1)), (0.5, (0, 1, 0, 0.5)), (1.0, (0, 0, 1, 1))):
-            w.ints("ADD_COLOR_STOP", 0); w.raw("5f", o, *c)
-        w.floats("FILL_RECTANGLE", 0, 0, W, H_)
-    elif kind == "radial":
-        w.ints("SET_RADIAL_GRADIENT", 0); w.raw("6f", 0.4 * W, 0.4 * H_, 0.05 * W, 0.5 * W, 0.5 * H_, 0.5 * W)
-        for o, c in ((0.0, (1, 1, 0, 1)), (1.0, (0, 1, 1, 0.3))):
-            w.ints("ADD_COLOR_STOP", 0); w.raw("5f", o, *c)
-        w.floats("FILL_RECTANGLE", 0, 0, W, H_)
-    elif kind == "image":
-        n = 256 if SIZE <= 2048 else 1024
-        w.ints("DRAW_IMAGE", n, n, 4 * n); w.raw("4f", 0, 0, W, H_); w.blob(IMAGE[n])
-    return w.take()
-
-
-IMAGE = {}
-
-
 def main():
     lib = _native.load()
     peak = json.load(open(os.path.join(H.ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(H.ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    n = 256 if SIZE <= 2048 else 1024
-    IMAGE[n] = lcg_image(n)
     rows = []
     kinds = os.environ.get("FILL_KINDS", "solid,linear,radial,image").split(",")
     ops = {k: v for k, v in OPS.items() if k in os.environ.get("FILL_OPS", ",".join(OPS)).split(",")}
@@ -59,7 +23,7 @@ def main():
         for opname, op in ops.items():
             # background first so that the measured draw blends over real pixels
             bg = ScriptWriter(); bg.ints("SET_COLOR", 0); bg.raw("4f", 0.9, 0.8, 0.1, 0.6); bg.floats("FILL_RECTANGLE", 0, 0, float(SIZE), float(SIZE))
-            frame = H.lower_script(scene(kind, op), SIZE, SIZE)[0]
+            frame = H.lower_script(H.config4_script(kind, op, SIZE), SIZE, SIZE)[0]
             bgf = H.lower_script(bg.take(), SIZE, SIZE)[0]
             cv = C.c_void_p()
             assert lib.cb200_canvas_create(SIZE, SIZE, 0, C.byref(cv)) == 0
