@@ -8,7 +8,8 @@
 //   k_sort_hist     per-CTA digit histogram of its slice (digit-major table)
 //   k_sort_scan     one CTA per digit: exclusive scan across the CTAs + digit total
 //   k_sort_scatter  each CTA re-reads its slice in order, 2048 keys (8 per thread) per step;
-//                   ranks are made stable with warp match + per-warp digit counts
+//                   ranks are made stable with warp match + per-warp digit counts; the step is
+//                   regrouped by digit in shared memory before it is stored
 #include "frame.cuh"
 
 namespace cb200 {
@@ -68,16 +69,19 @@ constexpr int kSortStep = kBlock * kSortKeys;
 __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift, int width)
 {
     __shared__ uint32_t base[kMaxRadix];             // next free global slot per digit for this CTA
+    __shared__ uint32_t step_base[kMaxRadix];        // the same at the start of the current step
+    __shared__ uint32_t local_start[kMaxRadix];      // first slot of the digit in the staged step
     __shared__ uint32_t warp_count[kBlock / 32][kMaxRadix];
+    __shared__ uint64_t staged_key[kSortStep];       // the step's keys grouped by digit, input order within
+    __shared__ float staged_val[kSortStep];
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
     sort_slice(n, begin, end);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t radix = 1u << width, mask = radix - 1;
-    {   // global base of digit d = keys with a smaller digit + this digit's keys in earlier CTAs;
-        // thread t owns digits 2t and 2t+1
-        uint32_t d0 = 2 * threadIdx.x, d1 = d0 + 1;
+    const uint32_t d0 = 2 * threadIdx.x, d1 = d0 + 1;        // thread t owns digits 2t and 2t+1
+    {   // global base of digit d = keys with a smaller digit + this digit's keys in earlier CTAs
         uint32_t t0 = d0 < radix ? f.sort_hist[kMaxRadix * kGrid + d0] : 0;
         uint32_t t1 = d1 < radix ? f.sort_hist[kMaxRadix * kGrid + d1] : 0;
         uint32_t total;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
         float val[kSortKeys];
         uint32_t rank[kSortKeys];                    // rank among the warp's keys of the same digit
         const uint32_t first = step + uint32_t(warp) * (32 * kSortKeys) + uint32_t(lane);
+        const uint32_t in_step = min(end - step, uint32_t(kSortStep));
 #pragma unroll
         for (int k = 0; k < kSortKeys; ++k) {
             const uint32_t i = first + uint32_t(k) * 32;
@@ -118,9 +123,11 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
             __syncwarp();
         }
         __syncthreads();
-        // each digit: prefix over the warps, then advance the CTA base
-        for (uint32_t d = threadIdx.x; d < radix; d += kBlock) {
-            uint32_t run = base[d];
+        // each digit: prefix over the warps, advance the CTA base, count the step's keys
+        uint32_t c0 = 0, c1 = 0;
+        for (uint32_t d = d0; d <= d1 && d < radix; ++d) {
+            const uint32_t was = base[d];
+            uint32_t run = was;
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) {
                 uint32_t c = warp_count[w][d];
@@ -128,15 +135,33 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src
                 run += c;
             }
             base[d] = run;
+            step_base[d] = was;
+            (d == d0 ? c0 : c1) = run - was;
         }
+        uint32_t total;
+        const uint32_t before = block_exclusive_scan(c0 + c1, sm, total);     // barriers inside
+        if (d0 < radix) local_start[d0] = before;
+        if (d1 < radix) local_start[d1] = before + c0;
         __syncthreads();
+        // stage the step grouped by digit ...
 #pragma unroll
         for (int k = 0; k < kSortKeys; ++k) {
             if (first + uint32_t(k) * 32 < end) {
-                const uint32_t dst = mine[uint32_t(key[k] >> shift) & mask] + rank[k];
-                kout[dst] = key[k];
-                vout[dst] = val[k];
+                const uint32_t digit = uint32_t(key[k] >> shift) & mask;
+                const uint32_t slot = local_start[digit] + (mine[digit] + rank[k] - step_base[digit]);
+                staged_key[slot] = key[k];
+                staged_val[slot] = val[k];
             }
+        }
+        __syncthreads();
+        // ... so that neighbouring threads store neighbouring keys of one digit: whole sectors
+        // instead of one 8-byte fragment per key
+        for (uint32_t i = threadIdx.x; i < in_step; i += kBlock) {
+            const uint64_t kk = staged_key[i];
+            const uint32_t digit = uint32_t(kk >> shift) & mask;
+            const uint32_t dst = step_base[digit] + (i - local_start[digit]);
+            kout[dst] = kk;
+            vout[dst] = staged_val[i];
         }
         __syncthreads();
         // prefixes (also of digits absent from a warp) must not leak into the next step
