@@ -37,6 +37,10 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
         if (i > 0 && (keys[i - 1] >> bx) == row) continue;          // not a segment head
         uint32_t j = uint32_t(row >> by);
         if (j >= h->n_jobs) continue;
+        if (i + kShortRow < n && (keys[i + kShortRow] >> bx) == row) {   // sorted: the segment is longer than that
+            f.long_rows[atomicAdd(&h->n_long_rows, 1u)] = i;             // a whole warp takes it
+            continue;
+        }
         int y = int(row & ymask);
         const job_rec &jr = f.jobs[j];
         int ty = y / kTile - jr.ty0, ly = y % kTile;
@@ -48,9 +52,7 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
         float sum = 0.0f;
         uint32_t k = i;
         uint64_t key = keys[k];
-        bool too_long = false;
         for (;;) {
-            if (k - i >= kShortRow) { too_long = true; break; }
             int x = int(key & xmask);
             int c = x / kTile;
             if (binned && c > c_prev) {
@@ -77,10 +79,6 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
             if (!same_row) break;
             k = nk;
             key = nkey;
-        }
-        if (too_long) {                                              // redo by a whole warp
-            f.long_rows[atomicAdd(&h->n_long_rows, 1u)] = i;
-            continue;
         }
         // whatever is left over after the last run spills to the right edge
         if (binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
