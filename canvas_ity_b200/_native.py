@@ -83,6 +83,7 @@ SIGNATURES = {
     "cb200_debug_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_debug_runs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_last_error": (C.c_char_p, []),
+    "cb200_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_abi_version": (C.c_int, []),
     "cb200_device_count": (C.c_int, []),
     "cb200_struct_size": (C.c_int, [C.c_int]),

@@ -135,6 +135,7 @@ struct cb200_canvas {
     bool resident = false;                    // staged frame came from cb200_frame_upload
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
     cudaEvent_t ev[10];
+    bool stage_timing = true;          // cb200_set_stage_timing
     std::vector<cudaEvent_t> chunk_events;
     cb200_stats stats;
     uint64_t launches = 0;
@@ -586,19 +587,22 @@ int run_frame(cb200_canvas *cv)
     device_frame &f = cv->df;
     cudaStream_t s = cv->stream;
     CK(cudaMemsetAsync(cv->partials.p, 0, sizeof(uint32_t) * 8 * kGrid, s));
+    // Stage events sit between kernels and so cut the programmatic-dependent-launch chain there;
+    // with stage timing off only the frame and the compositor are bracketed.
+    const bool stages = cv->stage_timing;
     CK(cudaEventRecord(cv->ev[0], s));
     launch_flatten(f, uint32_t(sf.units.size()), s);
     launch_dash(f, s);
     launch_stroke(f, s);
-    CK(cudaEventRecord(cv->ev[1], s));
+    if (stages) CK(cudaEventRecord(cv->ev[1], s));
     launch_raster(f, cv->target, s);
-    CK(cudaEventRecord(cv->ev[2], s));
+    if (stages) CK(cudaEventRecord(cv->ev[2], s));
     int sorted = 0;
     launch_sort(f, s, sf.key_bits, &sorted);
-    CK(cudaEventRecord(cv->ev[3], s));
+    if (stages) CK(cudaEventRecord(cv->ev[3], s));
     launch_rows(f, cv->target, sorted, s);
-    CK(cudaEventRecord(cv->ev[8], s));
-    launch_shadow(f, cv->target, sorted, s, cv->ev[9]);
+    if (stages) CK(cudaEventRecord(cv->ev[8], s));
+    launch_shadow(f, cv->target, sorted, s, stages ? cv->ev[9] : nullptr);
     CK(cudaEventRecord(cv->ev[4], s));
     launch_composite(f, cv->target, sorted, s);
     CK(cudaEventRecord(cv->ev[5], s));
@@ -651,13 +655,16 @@ int finish_pending(cb200_canvas *cv)
             float ms = 0.0f;
             cb200_stats &st = cv->stats;
             cudaEventElapsedTime(&ms, cv->ev[0], cv->ev[5]); st.last_frame_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[0], cv->ev[1]); st.geometry_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[1], cv->ev[2]); st.raster_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[2], cv->ev[3]); st.sort_ms = ms;
             cudaEventElapsedTime(&ms, cv->ev[4], cv->ev[5]); st.composite_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[3], cv->ev[8]); st.coverage_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[8], cv->ev[9]); st.shadow_raster_ms = ms;
-            cudaEventElapsedTime(&ms, cv->ev[9], cv->ev[4]); st.blur_ms = ms;
+            st.geometry_ms = st.raster_ms = st.sort_ms = st.coverage_ms = st.shadow_raster_ms = st.blur_ms = 0.0f;
+            if (cv->stage_timing) {
+                cudaEventElapsedTime(&ms, cv->ev[0], cv->ev[1]); st.geometry_ms = ms;
+                cudaEventElapsedTime(&ms, cv->ev[1], cv->ev[2]); st.raster_ms = ms;
+                cudaEventElapsedTime(&ms, cv->ev[2], cv->ev[3]); st.sort_ms = ms;
+                cudaEventElapsedTime(&ms, cv->ev[3], cv->ev[8]); st.coverage_ms = ms;
+                cudaEventElapsedTime(&ms, cv->ev[8], cv->ev[9]); st.shadow_raster_ms = ms;
+                cudaEventElapsedTime(&ms, cv->ev[9], cv->ev[4]); st.blur_ms = ms;
+            }
             st.draws = seen.n_draws;
             st.cubics = seen.n_units - seen.n_subpaths;
             st.line_points = seen.n_line_points + seen.n_dash_points + seen.n_stroke_points;
@@ -687,6 +694,13 @@ int finish_pending(cb200_canvas *cv)
 // ------------------------------------------------------------------- C ABI ----
 
 extern "C" {
+
+int cb200_set_stage_timing(cb200_canvas *cv, int on)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    cv->stage_timing = on != 0;
+    return CB200_OK;
+}
 
 int cb200_abi_version(void) { return CB200_ABI_VERSION; }
 

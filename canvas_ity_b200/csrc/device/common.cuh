@@ -156,6 +156,29 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v)
     return v;
 }
 
+// Programmatic dependent launch: every kernel of a frame is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be placed while the previous
+// kernel drains, and starts with grid_dependency_wait() -- nothing written by an earlier kernel is
+// read before that returns (it returns once all preceding kernels have completed and flushed).
+__device__ __forceinline__ void grid_dependency_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+
 // Exclusive scan of one value per thread across the CTA; returns the exclusive
 // prefix and writes the CTA total to `total`.  `smem` needs 33 words.
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem, uint32_t &total)

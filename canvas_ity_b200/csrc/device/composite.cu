@@ -308,6 +308,7 @@ template <bool kGeneral>
 __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
+    grid_dependency_wait();
     __shared__ __align__(16) warp_scratch scratch[kTileWarps];
     frame_header *h = f.hdr;
     if (h->overflow) return;
@@ -518,8 +519,8 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     // overrides.
     int eager = f.n_opaque_jobs == 0;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
-    if (f.general_compositor) k_composite<true><<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
-    else k_composite<false><<<tiles, kCompBlock, 0, s>>>(f, t, sorted_buffer, tiles_x, ty0, eager);
+    if (f.general_compositor) launch_pdl(k_composite<true>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
+    else launch_pdl(k_composite<false>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
 }
 
 }  // namespace cb200

@@ -23,6 +23,7 @@ constexpr uint32_t kShortRow = 48;      // longer scanline segments go to the wa
 
 __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
 {
+    grid_dependency_wait();
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const uint32_t n = h->n_runs;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
 // the scan's association order), same bookkeeping as k_rows.
 __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
 {
+    grid_dependency_wait();
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const uint32_t n = h->n_runs, n_long = h->n_long_rows;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
 // culling (an opaque covered draw makes everything beneath it irrelevant).
 __global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_target t)
 {
+    grid_dependency_wait();
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const int lane = threadIdx.x & 31;
@@ -200,9 +203,9 @@ __global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_ta
 
 void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
 {
-    k_rows<<<kGrid, kBlock, 0, s>>>(f, sorted_buffer);
-    k_rows_long<<<kGrid, kBlock, 0, s>>>(f, sorted_buffer);
-    k_tile_flags<<<kGrid, kBlock, 0, s>>>(f, t);
+    launch_pdl(k_rows, kGrid, kBlock, 0, s, f, sorted_buffer);
+    launch_pdl(k_rows_long, kGrid, kBlock, 0, s, f, sorted_buffer);
+    launch_pdl(k_tile_flags, kGrid, kBlock, 0, s, f, t);
 }
 
 }  // namespace cb200

@@ -142,6 +142,7 @@ __device__ uint32_t warp_flatten(const device_frame &f, uint32_t u, uint32_t out
 
 __global__ void __launch_bounds__(kBlock) k_flatten_count(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     __shared__ uint32_t block_total;
     __shared__ float nodes[kWarps][kNodeWords * 32];
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kBlock) k_flatten_count(device_frame f)
 
 __global__ void __launch_bounds__(kBlock) k_flatten_emit(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     __shared__ float nodes[kWarps][kNodeWords * 32];
     uint32_t n = f.hdr->n_units, begin, end;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(kBlock) k_flatten_emit(device_frame f)
 // loops[s] = point span of subpath s in the K1 output
 __global__ void k_subpath_loops(device_frame f)
 {
+    grid_dependency_wait();
     uint32_t n = f.hdr->n_subpaths;
     if (f.hdr->overflow) return;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -259,6 +262,7 @@ struct dash_count_sink {
 
 __global__ void __launch_bounds__(kBlock) k_dash_count(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     uint32_t n = f.n_dash_items, begin, end, ipt;
     block_slice(n, begin, end, ipt);
@@ -316,6 +320,7 @@ struct dash_emit_sink {
 
 __global__ void __launch_bounds__(kBlock) k_dash_emit(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     uint32_t n = f.n_dash_items, begin, end, ipt;
     block_slice(n, begin, end, ipt);
@@ -633,6 +638,7 @@ __device__ __forceinline__ uint32_t n_halves(const device_frame &f)
 // units per half + in-kernel partial scan; total to hdr->n_stroke_units
 __global__ void __launch_bounds__(kBlock) k_stroke_plan(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
     uint32_t n = hd->overflow ? 0 : n_halves(f), begin, end, ipt;
@@ -654,6 +660,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_plan(device_frame f)
 // half_count (units per half) -> half_unit_off (exclusive), same slices as k_stroke_plan
 __global__ void __launch_bounds__(kBlock) k_stroke_plan_apply(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
     uint32_t n = hd->overflow ? 0 : n_halves(f), begin, end, ipt;
@@ -683,6 +690,7 @@ __device__ __forceinline__ uint32_t find_half(const uint32_t *off, uint32_t n, u
 // thread per visit: too-close mark and default link
 __global__ void __launch_bounds__(kBlock) k_stroke_visits(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *hd = f.hdr;
     uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
     block_slice(n, begin, end, ipt);
@@ -707,6 +715,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_visits(device_frame f)
 // warp per half: replay the greedy filter across marked stretches only
 __global__ void __launch_bounds__(kBlock) k_stroke_resolve(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *hd = f.hdr;
     if (hd->overflow) return;
     uint32_t nh = n_halves(f);
@@ -787,6 +796,7 @@ __device__ __forceinline__ void stroke_unit(const device_frame &f, const half_vi
 // points per unit
 __global__ void __launch_bounds__(kBlock) k_stroke_unit_count(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *hd = f.hdr;
     uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
     block_slice(n, begin, end, ipt);
@@ -809,6 +819,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_unit_count(device_frame f)
 // exact serial redo of dirty halves: all their points are booked on their first unit
 __global__ void __launch_bounds__(kBlock) k_stroke_fallback_count(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *hd = f.hdr;
     if (hd->overflow) return;
     uint32_t nh = n_halves(f);
@@ -824,6 +835,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_fallback_count(device_frame f
 // block sums of stroke_unit_pts -> partials -> total stroke points
 __global__ void __launch_bounds__(kBlock) k_stroke_unit_sums(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
     uint32_t n = hd->overflow ? 0 : hd->n_stroke_units, begin, end, ipt;
@@ -838,6 +850,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_unit_sums(device_frame f)
 
 __global__ void __launch_bounds__(kBlock) k_stroke_unit_emit(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *hd = f.hdr;
     uint32_t base = hd->n_line_points + hd->n_dash_points;
@@ -876,6 +889,7 @@ __global__ void __launch_bounds__(kBlock) k_stroke_unit_emit(device_frame f)
 // dirty halves written serially; loop table for all halves
 __global__ void __launch_bounds__(kBlock) k_stroke_finish(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *hd = f.hdr;
     if (hd->overflow) return;
     uint32_t nh = n_halves(f);
@@ -900,30 +914,30 @@ __global__ void __launch_bounds__(kBlock) k_stroke_finish(device_frame f)
 void launch_flatten(const device_frame &f, uint32_t n_units, cudaStream_t s)
 {
     if (!n_units) return;
-    k_flatten_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_flatten_emit<<<kGrid, kBlock, 0, s>>>(f);
-    k_subpath_loops<<<kGrid, kBlock, 0, s>>>(f);
+    launch_pdl(k_flatten_count, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_flatten_emit, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_subpath_loops, kGrid, kBlock, 0, s, f);
 }
 
 void launch_dash(const device_frame &f, cudaStream_t s)
 {
     if (!f.n_dash_items) return;
-    k_dash_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_dash_emit<<<kGrid, kBlock, 0, s>>>(f);
+    launch_pdl(k_dash_count, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_dash_emit, kGrid, kBlock, 0, s, f);
 }
 
 void launch_stroke(const device_frame &f, cudaStream_t s)
 {
     if (!f.n_static_sources && !f.n_dash_items) return;
-    k_stroke_plan<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_plan_apply<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_visits<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_resolve<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_unit_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_fallback_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_unit_sums<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_unit_emit<<<kGrid, kBlock, 0, s>>>(f);
-    k_stroke_finish<<<kGrid, kBlock, 0, s>>>(f);
+    launch_pdl(k_stroke_plan, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_plan_apply, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_visits, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_resolve, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_unit_count, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_fallback_count, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_unit_sums, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_unit_emit, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_stroke_finish, kGrid, kBlock, 0, s, f);
 }
 
 }  // namespace cb200

@@ -29,6 +29,7 @@ __constant__ float c_bayer[16] = {
 __global__ void __launch_bounds__(kBlock) k_readback(const float4 *fb, int width, int band_y0, int band_rows,
                                                       uchar4 *dst, int dst_w, int dst_h, int ox, int oy)
 {
+    grid_dependency_wait();
     size_t n = size_t(dst_w) * size_t(dst_h);
     size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -59,6 +60,7 @@ __device__ __forceinline__ float4 decode(uchar4 t)
 __global__ void __launch_bounds__(kBlock) k_upload(float4 *fb, int width, int band_y0, int band_rows,
                                                     const uchar4 *src, int src_w, int src_h, int ox, int oy)
 {
+    grid_dependency_wait();
     size_t n = size_t(src_w) * size_t(src_h);
     size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -70,12 +72,14 @@ __global__ void __launch_bounds__(kBlock) k_upload(float4 *fb, int width, int ba
 
 __global__ void __launch_bounds__(kBlock) k_texels(const uchar4 *src, float4 *dst, uint64_t n)
 {
+    grid_dependency_wait();
     uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = decode(src[i]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_fill(float *dst, float value, uint64_t n)
 {
+    grid_dependency_wait();
     uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
 }
@@ -94,7 +98,7 @@ void launch_readback(const float4 *fb, int width, int band_y0, int band_rows, ui
 {
     uint64_t n = uint64_t(dst_w) * uint64_t(dst_h);
     if (!n) return;
-    k_readback<<<grid_for(n), kBlock, 0, s>>>(fb, width, band_y0, band_rows, reinterpret_cast<uchar4 *>(dst),
+    launch_pdl(k_readback, grid_for(n), kBlock, 0, s, fb, width, band_y0, band_rows, reinterpret_cast<uchar4 *>(dst),
                                               dst_w, dst_h, x, y);
 }
 
@@ -103,20 +107,20 @@ void launch_upload(float4 *fb, int width, int band_y0, int band_rows, const uint
 {
     uint64_t n = uint64_t(src_w) * uint64_t(src_h);
     if (!n) return;
-    k_upload<<<grid_for(n), kBlock, 0, s>>>(fb, width, band_y0, band_rows, reinterpret_cast<const uchar4 *>(src),
+    launch_pdl(k_upload, grid_for(n), kBlock, 0, s, fb, width, band_y0, band_rows, reinterpret_cast<const uchar4 *>(src),
                                             src_w, src_h, x, y);
 }
 
 void launch_texel_convert(const uint8_t *src, float4 *dst, uint64_t n_texels, cudaStream_t s)
 {
     if (!n_texels) return;
-    k_texels<<<grid_for(n_texels), kBlock, 0, s>>>(reinterpret_cast<const uchar4 *>(src), dst, n_texels);
+    launch_pdl(k_texels, grid_for(n_texels), kBlock, 0, s, reinterpret_cast<const uchar4 *>(src), dst, n_texels);
 }
 
 void launch_fill_f32(float *dst, float value, uint64_t n, cudaStream_t s)
 {
     if (!n) return;
-    k_fill<<<grid_for(n), kBlock, 0, s>>>(dst, value, n);
+    launch_pdl(k_fill, grid_for(n), kBlock, 0, s, dst, value, n);
 }
 
 }  // namespace cb200

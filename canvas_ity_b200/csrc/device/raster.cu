@@ -81,6 +81,7 @@ __device__ __forceinline__ row_walk row_setup(const edge_walk &e, int r)
 
 __global__ void __launch_bounds__(kBlock) k_job_items(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->n_jobs, carry = 0;
@@ -162,6 +163,7 @@ __device__ __forceinline__ uint32_t job_of_item(const device_frame &f, uint32_t 
 
 __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target t)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_items, begin, end;
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
 // piece_rows (counts) -> piece_row_off (exclusive offsets), same slice mapping
 __global__ void __launch_bounds__(kBlock) k_scan_rows(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_items, begin, end;
@@ -310,6 +313,7 @@ __device__ __forceinline__ uint32_t piece_of_row_item(const uint32_t *off, uint3
 
 __global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_row_items, begin, end;
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
 
 __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     frame_header *h = f.hdr;
     if (h->n_runs > f.cap_runs) {
@@ -404,6 +409,7 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
 
 __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_target t)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     __shared__ unsigned long long plane_carry, working_carry;
     frame_header *h = f.hdr;
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
 // zero the per-(tile entry, row) coverage bookkeeping
 __global__ void k_clear_tiles(device_frame f)
 {
+    grid_dependency_wait();
     frame_header *h = f.hdr;
     if (h->overflow) return;
     uint64_t n = uint64_t(h->n_tile_entries) * kTile;
@@ -531,13 +538,13 @@ __global__ void k_clear_tiles(device_frame f)
 
 void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s)
 {
-    k_job_items<<<1, kBlock, 0, s>>>(f);
-    k_edges<<<kGrid, kBlock, 0, s>>>(f, t);
-    k_scan_rows<<<kGrid, kBlock, 0, s>>>(f);
-    k_row_count<<<kGrid, kBlock, 0, s>>>(f);
-    k_row_emit<<<kGrid, kBlock, 0, s>>>(f);
-    k_job_tiles<<<1, kBlock, 0, s>>>(f, t);
-    k_clear_tiles<<<kGrid, kBlock, 0, s>>>(f);
+    launch_pdl(k_job_items, 1, kBlock, 0, s, f);
+    launch_pdl(k_edges, kGrid, kBlock, 0, s, f, t);
+    launch_pdl(k_scan_rows, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_row_count, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_row_emit, kGrid, kBlock, 0, s, f);
+    launch_pdl(k_job_tiles, 1, kBlock, 0, s, f, t);
+    launch_pdl(k_clear_tiles, kGrid, kBlock, 0, s, f);
 }
 
 }  // namespace cb200

@@ -100,6 +100,7 @@ __device__ float paint_alpha(const device_frame &f, const brush_rec &b, const af
 // grid: (tile stride, shadow job)
 __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb)
 {
+    grid_dependency_wait();
     __shared__ float row_buf[kBlock / 32][kTile];
     frame_header *h = f.hdr;
     if (h->overflow) return;
@@ -211,6 +212,7 @@ __device__ __forceinline__ uint32_t sweep_units(int len, int cross)
 // orders of magnitude.  Also resets the two unit tickets.  One CTA.
 __global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     if (f.hdr->overflow) return;
     const uint32_t n = f.n_shadow_jobs;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
 template <bool kAlongRows>
 __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, const float *src_base, float *dst_base)
 {
+    grid_dependency_wait();
     extern __shared__ float blur_smem[];
     if (f.hdr->overflow) return;
     const uint32_t n_jobs = f.n_shadow_jobs;
@@ -425,6 +428,7 @@ __device__ __forceinline__ void blur_one_row(const float *in, float *out, int le
 __global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const float *src_base, float *dst_base,
                                                        int transposed, int smem_floats)
 {
+    grid_dependency_wait();
     extern __shared__ float blur_smem[];
     frame_header *h = f.hdr;
     if (h->overflow) return;
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(kBlock) k_blur_rows(device_frame f, const floa
 __global__ void __launch_bounds__(kBlock) k_transpose(device_frame f, const float *src_base, float *dst_base,
                                                        int back)
 {
+    grid_dependency_wait();
     __shared__ float tile[32][33];
     frame_header *h = f.hdr;
     if (h->overflow) return;
@@ -496,10 +501,10 @@ __global__ void __launch_bounds__(kBlock) k_transpose(device_frame f, const floa
 void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s,
                    cudaEvent_t after_raster)
 {
-    if (!f.n_shadow_jobs) { cudaEventRecord(after_raster, s); return; }
+    if (!f.n_shadow_jobs) { if (after_raster) cudaEventRecord(after_raster, s); return; }
     dim3 grid(64, f.n_shadow_jobs);
-    k_shadow_raster<<<grid, kBlock, 0, s>>>(f, sorted_buffer);
-    cudaEventRecord(after_raster, s);
+    launch_pdl(k_shadow_raster, grid, kBlock, 0, s, f, sorted_buffer);
+    if (after_raster) cudaEventRecord(after_raster, s);
     const int longest = std::max(t.width, t.height) + f.max_shadow_pad;
     if (f.min_shadow_radius <= kStreamMaxRadius) {
         // x sweep planes -> planes_tmp, y sweep back into planes
@@ -511,9 +516,9 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
             cudaFuncSetAttribute(k_blur_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
         }
         auto resident = [](size_t smem) { return int(std::min<size_t>(16, (227 * 1024) / (smem + 1024))); };
-        k_blur_units<<<1, kBlock, 0, s>>>(f);
-        k_blur_stream<true><<<kSMs * resident(row_bytes), kStreamThreads, row_bytes, s>>>(f, f.planes, f.planes_tmp);
-        k_blur_stream<false><<<kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s>>>(f, f.planes_tmp, f.planes);
+        launch_pdl(k_blur_units, 1, kBlock, 0, s, f);
+        launch_pdl(k_blur_stream<true>, kSMs * resident(row_bytes), kStreamThreads, row_bytes, s, f, f.planes, f.planes_tmp);
+        launch_pdl(k_blur_stream<false>, kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s, f, f.planes_tmp, f.planes);
     }
     if (f.max_shadow_radius > kStreamMaxRadius) {
         // rows -> transpose -> rows (= columns) -> transpose back; the result ends up in f.planes
@@ -525,10 +530,10 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
         if (smem_bytes > 48 * 1024)
             cudaFuncSetAttribute(k_blur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
         dim3 rgrid(256, f.n_shadow_jobs), tgrid(128, f.n_shadow_jobs);
-        k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 0, smem_floats);
-        k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 0);
-        k_blur_rows<<<rgrid, kBlock, smem_bytes, s>>>(f, f.planes, f.planes_tmp, 1, smem_floats);
-        k_transpose<<<tgrid, kBlock, 0, s>>>(f, f.planes_tmp, f.planes, 1);
+        launch_pdl(k_blur_rows, rgrid, kBlock, smem_bytes, s, f, f.planes, f.planes_tmp, 0, smem_floats);
+        launch_pdl(k_transpose, tgrid, kBlock, 0, s, f, f.planes_tmp, f.planes, 0);
+        launch_pdl(k_blur_rows, rgrid, kBlock, smem_bytes, s, f, f.planes, f.planes_tmp, 1, smem_floats);
+        launch_pdl(k_transpose, tgrid, kBlock, 0, s, f, f.planes_tmp, f.planes, 1);
     }
 }
 

@@ -29,6 +29,7 @@ __device__ __forceinline__ void sort_slice(uint32_t n, uint32_t &begin, uint32_t
 
 __global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, int shift, int width)
 {
+    grid_dependency_wait();
     __shared__ uint32_t bins[kMaxRadix];
     frame_header *h = f.hdr;
     uint32_t n = h->overflow ? 0 : h->n_runs, begin, end;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kBlock) k_sort_hist(device_frame f, int src, i
 // digit total to sort_hist[kMaxRadix * kGrid + digit].
 __global__ void __launch_bounds__(kBlock) k_sort_scan(device_frame f)
 {
+    grid_dependency_wait();
     __shared__ uint32_t sm[33];
     uint32_t *row = f.sort_hist + blockIdx.x * kGrid;
     uint32_t carry = 0;
@@ -68,6 +70,7 @@ constexpr int kSortStep = kBlock * kSortKeys;
 
 __global__ void __launch_bounds__(kBlock) k_sort_scatter(device_frame f, int src, int shift, int width)
 {
+    grid_dependency_wait();
     __shared__ uint32_t base[kMaxRadix];             // next free global slot per digit for this CTA
     __shared__ uint32_t step_base[kMaxRadix];        // the same at the start of the current step
     __shared__ uint32_t local_start[kMaxRadix];      // first slot of the digit in the staged step
@@ -185,9 +188,9 @@ void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *resul
     int width = (key_bits + passes - 1) / passes;      // <= 9
     int src = 0;
     for (int p = 0; p < passes; ++p) {
-        k_sort_hist<<<kGrid, kBlock, 0, s>>>(f, src, p * width, width);
-        k_sort_scan<<<1 << width, kBlock, 0, s>>>(f);
-        k_sort_scatter<<<kGrid, kBlock, 0, s>>>(f, src, p * width, width);
+        launch_pdl(k_sort_hist, kGrid, kBlock, 0, s, f, src, p * width, width);
+        launch_pdl(k_sort_scan, 1 << width, kBlock, 0, s, f);
+        launch_pdl(k_sort_scatter, kGrid, kBlock, 0, s, f, src, p * width, width);
         src ^= 1;
     }
     *result_buffer = src;

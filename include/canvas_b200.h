@@ -197,6 +197,9 @@ typedef struct cb200_stats {
 } cb200_stats;
 
 int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);
+/* Per-stage CUDA events (geometry/raster/sort/coverage/shadow) sit between kernels and cost a few
+ * microseconds per frame; off: only last_frame_ms and composite_ms are measured.  Default on. */
+int cb200_set_stage_timing(cb200_canvas *canvas, int on);
 
 /* Debug taps used by the parity tests: intermediate buffers of the last frame.
  * Each returns the element count (>= 0) and copies at most `capacity`. */
