@@ -136,6 +136,14 @@ struct cb200_canvas {
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
     cudaEvent_t ev[10];
     bool stage_timing = true;          // cb200_set_stage_timing
+    bool clear_pending = false;        // cb200_clear / replay(clear): folded into the next frame, or applied by settle()
+    bool inflight_clear = false;       // the frame in flight starts from a cleared canvas (kept for overflow re-runs)
+    bool replay_verified = false;      // the resident frame has completed once with the current capacities
+    // composite kernel times of the most recent frames (bench: roofline over the timed region)
+    static const int kCompRing = 256;
+    cudaEvent_t comp_ev[2 * kCompRing] = {};
+    uint64_t frames_run = 0, timer_frame0 = 0;
+    cudaEvent_t timer_ev[2] = {};
     std::vector<cudaEvent_t> chunk_events;
     cb200_stats stats;
     uint64_t launches = 0;
@@ -604,8 +612,13 @@ int run_frame(cb200_canvas *cv)
     if (stages) CK(cudaEventRecord(cv->ev[8], s));
     launch_shadow(f, cv->target, sorted, s, stages ? cv->ev[9] : nullptr);
     CK(cudaEventRecord(cv->ev[4], s));
+    const int ring = int(cv->frames_run % uint64_t(cb200_canvas::kCompRing));
+    CK(cudaEventRecord(cv->comp_ev[2 * ring], s));
+    cv->target.clear_first = cv->inflight_clear ? 1 : 0;
     launch_composite(f, cv->target, sorted, s);
+    CK(cudaEventRecord(cv->comp_ev[2 * ring + 1], s));
     CK(cudaEventRecord(cv->ev[5], s));
+    ++cv->frames_run;
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
@@ -675,6 +688,7 @@ int finish_pending(cb200_canvas *cv)
             st.shadow_pixels = seen.shadow_working_pixels;
             st.kernel_launches = cv->launches;
             cv->pending = false;
+            cv->replay_verified = cv->resident;
             return CB200_OK;
         }
         int rc = ensure_capacity(cv, cv->staged, &seen);
@@ -687,6 +701,28 @@ int finish_pending(cb200_canvas *cv)
     }
     cv->pending = false;
     return fail(CB200_ERR_OVERFLOW, "device work queues still overflow after regrowth");
+}
+
+// A new frame: a pending clear rides along (the compositor starts from transparent black and
+// writes every tile) instead of costing a separate pass over the framebuffer.
+int start_frame(cb200_canvas *cv)
+{
+    cv->inflight_clear = cv->clear_pending;
+    cv->clear_pending = false;
+    return run_frame(cv);
+}
+
+// Before anything outside a frame reads or writes pixels: finish the frame in flight and apply a
+// clear that no frame has absorbed.
+int settle(cb200_canvas *cv)
+{
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    if (cv->clear_pending) {
+        CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * fb_rows(cv), cv->stream));
+        cv->clear_pending = false;
+    }
+    return CB200_OK;
 }
 
 }  // namespace
@@ -755,6 +791,8 @@ int cb200_canvas_create_band(int width, int height, int band_y0, int band_rows, 
     if (err == cudaSuccess) err = cudaMemsetAsync(cv->fb, 0, px * sizeof(float4), cv->stream);
     if (err == cudaSuccess) err = cudaMallocHost(&cv->pinned_hdr, sizeof(frame_header));
     for (int i = 0; i < 10 && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->ev[i]);
+    for (int i = 0; i < 2 * cb200_canvas::kCompRing && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->comp_ev[i]);
+    for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaEventCreate(&cv->timer_ev[i]);
     if (err != cudaSuccess) {
         std::string why = cudaGetErrorString(err);
         cb200_canvas_destroy(cv);
@@ -789,7 +827,7 @@ int cb200_batch_submit(cb200_canvas *cv, const cb200_frame *const *frames, const
     if (rc != CB200_OK) return rc;
     rc = upload_frame(cv);
     if (rc != CB200_OK) return rc;
-    return run_frame(cv);
+    return start_frame(cv);
 }
 
 int cb200_batch_read_rgba8(cb200_canvas *cv, uint32_t canvas, uint8_t *dst, int width, int height, int stride,
@@ -799,7 +837,7 @@ int cb200_batch_read_rgba8(cb200_canvas *cv, uint32_t canvas, uint8_t *dst, int 
     if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
     if (width <= 0 || height <= 0) return CB200_OK;
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     size_t bytes = 4 * size_t(width) * size_t(height);
     CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
@@ -819,7 +857,7 @@ int cb200_batch_read_f32(cb200_canvas *cv, uint32_t canvas, float *dst)
     if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
     if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     const float4 *slot = cv->fb + size_t(canvas) * size_t(cv->n_canvases > 1 ? cv->slot_rows : 0) * size_t(cv->width);
     CK(cudaMemcpyAsync(dst, slot, sizeof(float4) * size_t(cv->width) * size_t(cv->height), cudaMemcpyDeviceToHost, cv->stream));
@@ -854,6 +892,8 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 10; ++i)
         if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
+    for (cudaEvent_t e : cv->comp_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : cv->timer_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : cv->chunk_events) cudaEventDestroy(e);
     if (cv->stream) cudaStreamDestroy(cv->stream);
     delete cv;
@@ -873,7 +913,7 @@ int cb200_submit(cb200_canvas *cv, const cb200_frame *frame)
     if (rc != CB200_OK) return rc;
     rc = upload_frame(cv);
     if (rc != CB200_OK) return rc;
-    return run_frame(cv);
+    return start_frame(cv);
 }
 
 int cb200_frame_upload(cb200_canvas *cv, const cb200_frame *frame)
@@ -889,6 +929,7 @@ int cb200_frame_upload(cb200_canvas *cv, const cb200_frame *frame)
     rc = upload_frame(cv);
     if (rc != CB200_OK) return rc;
     cv->resident = true;
+    cv->replay_verified = false;
     return CB200_OK;
 }
 
@@ -897,21 +938,56 @@ int cb200_frame_replay(cb200_canvas *cv, int clear)
     if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
     if (!cv->resident || !cv->staged.valid) return fail(CB200_ERR_BAD_ARG, "no frame uploaded");
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
-    if (rc != CB200_OK) return rc;
-    if (clear)
-        CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * fb_rows(cv), cv->stream));
+    // A frame that has already completed once with the present capacities cannot overflow, so
+    // its replays are queued back to back without waiting for the previous one's header.
+    if (!(cv->pending && cv->replay_verified)) {
+        int rc = finish_pending(cv);
+        if (rc != CB200_OK) return rc;
+    }
+    if (clear) cv->clear_pending = true;
     // the header is consumed by a run: restore it from its pristine twin (device to device)
     CK(cudaMemcpyAsync(cv->blob.p + cv->hdr_offset, cv->blob.p + cv->hdr_pristine_offset, sizeof(frame_header),
                        cudaMemcpyDeviceToDevice, cv->stream));
-    return run_frame(cv);
+    return start_frame(cv);
+}
+
+int cb200_timer_begin(cb200_canvas *cv)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    CK(cudaEventRecord(cv->timer_ev[0], cv->stream));
+    cv->timer_frame0 = cv->frames_run;
+    return CB200_OK;
+}
+
+int cb200_timer_end(cb200_canvas *cv, float *elapsed_ms, float *composite_ms, uint32_t *composite_frames)
+{
+    if (!cv || !elapsed_ms) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    CK(cudaEventRecord(cv->timer_ev[1], cv->stream));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaEventSynchronize(cv->timer_ev[1]));
+    CK(cudaEventElapsedTime(elapsed_ms, cv->timer_ev[0], cv->timer_ev[1]));
+    uint64_t first = cv->timer_frame0;
+    if (cv->frames_run - first > uint64_t(cb200_canvas::kCompRing)) first = cv->frames_run - cb200_canvas::kCompRing;
+    float sum = 0.0f;
+    for (uint64_t k = first; k < cv->frames_run; ++k) {
+        const int ring = int(k % uint64_t(cb200_canvas::kCompRing));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, cv->comp_ev[2 * ring], cv->comp_ev[2 * ring + 1]));
+        sum += ms;
+    }
+    if (composite_ms) *composite_ms = sum;
+    if (composite_frames) *composite_frames = uint32_t(cv->frames_run - first);
+    return CB200_OK;
 }
 
 int cb200_sync(cb200_canvas *cv)
 {
     if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     CK(cudaStreamSynchronize(cv->stream));
     return CB200_OK;
@@ -948,7 +1024,7 @@ int cb200_read_rgba8(cb200_canvas *cv, uint8_t *dst, int width, int height, int 
     if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
     if (width <= 0 || height <= 0) return CB200_OK;
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     rc = readback_to_device(cv, width, height, x, y);
     if (rc != CB200_OK) return rc;
@@ -1004,7 +1080,7 @@ int cb200_read_rgba8_device(cb200_canvas *cv, void **device_ptr)
 {
     if (!cv || !device_ptr) return fail(CB200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     rc = readback_to_device(cv, cv->width, cv->band_rows, 0, cv->band_y0);
     if (rc != CB200_OK) return rc;
@@ -1022,7 +1098,7 @@ int cb200_read_rgba8_into(cb200_canvas *cv, void *device_dst, int width, int hei
     if (!cv || !device_dst) return fail(CB200_ERR_BAD_ARG, "null argument");
     if (width <= 0 || height <= 0) return CB200_OK;
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     launch_readback(cv->fb, cv->width, cv->band_y0, cv->band_rows, static_cast<uint8_t *>(device_dst), width, height,
                     x, y, cv->stream);
@@ -1036,7 +1112,7 @@ int cb200_write_rgba8(cb200_canvas *cv, const uint8_t *src, int width, int heigh
     if (!cv || !src) return fail(CB200_ERR_BAD_ARG, "null argument");
     if (width <= 0 || height <= 0) return CB200_OK;
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     size_t bytes = 4 * size_t(width) * size_t(height);
     if (bytes > cv->pinned_rgba8_cap) {
@@ -1060,7 +1136,7 @@ int cb200_read_f32(cb200_canvas *cv, float *dst)
 {
     if (!cv || !dst) return fail(CB200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(cv->device));
-    int rc = finish_pending(cv);
+    int rc = settle(cv);
     if (rc != CB200_OK) return rc;
     CK(cudaMemcpyAsync(dst, cv->fb, sizeof(float4) * size_t(cv->width) * size_t(cv->band_rows),
                        cudaMemcpyDeviceToHost, cv->stream));
@@ -1104,8 +1180,7 @@ int cb200_clear(cb200_canvas *cv)
     CK(cudaSetDevice(cv->device));
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
-    CK(cudaMemsetAsync(cv->fb, 0, sizeof(float4) * size_t(cv->width) * fb_rows(cv), cv->stream));
-    CK(cudaStreamSynchronize(cv->stream));
+    cv->clear_pending = true;                    // absorbed by the next frame, or applied by the next pixel access
     for (auto &kv : cv->masks) cudaFree(kv.second);
     cv->masks.clear();
     return CB200_OK;

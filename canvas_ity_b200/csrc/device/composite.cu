@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(devi
         const int y = row0 + r;
         const bool live = x < t.width && y >= t.band_y0 && y < band_y1;
         live_mask |= uint32_t(live) << r;
-        px[r] = (live && eager_load) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        px[r] = (live && eager_load && !t.clear_first) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    bool loaded = eager_load != 0;
+    bool loaded = eager_load != 0 || t.clear_first != 0;
     const cov_source cs = make_cov_source(f, sb);
     const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
     uint32_t painted = 0;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(devi
         }
     }
     flush();
-    if (!touched) return;                                    // no job reaches these pixels: leave them alone
+    if (!touched && !t.clear_first) return;                  // no job reaches these pixels: leave them alone
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r)
         if (live_mask >> r & 1u) fb_at[size_t(r) * size_t(t.width)] = px[r];

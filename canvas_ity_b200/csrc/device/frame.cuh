@@ -75,6 +75,9 @@ struct canvas_target {
     // every job belongs to one canvas and works in that canvas' own coordinates
     int n_canvases, slot_rows;
     const uint2 *canvas_jobs;   // per canvas: first job, job count
+    // the frame starts from transparent black: the compositor never loads fb and also writes the
+    // tiles no job reaches (a clear folded into the frame instead of a separate 16 B/pixel memset)
+    int clear_first;
 };
 
 // geometry.cu

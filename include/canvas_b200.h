@@ -167,7 +167,8 @@ int cb200_write_rgba8(cb200_canvas *canvas, const uint8_t *src, int width,
 int cb200_read_f32(cb200_canvas *canvas, float *dst);
 /* Clip-mask slot as dense visibility, band_rows * width floats. */
 int cb200_read_mask(cb200_canvas *canvas, uint32_t slot, float *dst);
-/* Clear to transparent black and forget all mask slots. */
+/* Clear to transparent black and forget all mask slots.  The clear itself is deferred: the next
+ * frame absorbs it (its compositor starts from transparent black), any other pixel access applies it. */
 int cb200_clear(cb200_canvas *canvas);
 /* Clip-mask slots are immutable once written (clip() always writes a fresh
  * slot).  The host tells the back end which slots are still reachable (current
@@ -200,6 +201,12 @@ int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);
 /* Per-stage CUDA events (geometry/raster/sort/coverage/shadow) sit between kernels and cost a few
  * microseconds per frame; off: only last_frame_ms and composite_ms are measured.  Default on. */
 int cb200_set_stage_timing(cb200_canvas *canvas, int on);
+/* Device-side stopwatch on the canvas stream, for timing a run of frames without a host round
+ * trip per frame: _begin records an event, _end records another, waits for it and returns the
+ * elapsed milliseconds plus the summed duration of the tile compositor over the frames in
+ * between (the most recent 256 of them; *composite_frames says how many were summed). */
+int cb200_timer_begin(cb200_canvas *canvas);
+int cb200_timer_end(cb200_canvas *canvas, float *elapsed_ms, float *composite_ms, uint32_t *composite_frames);
 
 /* Debug taps used by the parity tests: intermediate buffers of the last frame.
  * Each returns the element count (>= 0) and copies at most `capacity`. */
