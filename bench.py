@@ -64,7 +64,8 @@ def measured_hbm_peak():
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe's line)."""
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
+        self.enabled = enabled
         self.rows, self.stop = [], threading.Event()
         self.cmd = ["nvidia-smi", "-i", str(index),
                     "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
@@ -73,6 +74,8 @@ class ClockSampler:
         self.proc = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
@@ -179,7 +182,9 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-lanes", type=int, default=4, help="canvases kept in flight by the end-to-end arm")
+    ap.add_argument("--e2e-lanes", type=int, default=0,
+                    help="canvases kept in flight per rank by the end-to-end arm (default: up to 4, one host thread each, "
+                         "as the host cores allow)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,6 +193,8 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if args.e2e_lanes <= 0:
+        args.e2e_lanes = max(2, min(4, (os.cpu_count() or 4) // max(1, world)))
 
     import torch
     import torch.distributed as dist
@@ -239,7 +246,7 @@ def main():
     check(lib.cb200_set_stage_timing(cv, 0))
     barrier()
     elapsed_ms, comp_sum_ms, comp_frames = C.c_float(), C.c_float(), C.c_uint32()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=rank == 0) as clocks:      # one nvidia-smi poller per job, not per rank
         t0 = time.perf_counter()
         check(lib.cb200_timer_begin(cv))                        # CUDA event on the canvas stream
         for _ in range(args.steps):

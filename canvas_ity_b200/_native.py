@@ -77,6 +77,8 @@ SIGNATURES = {
     "cb200_read_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cb200_clear": (C.c_int, [C.c_void_p]),
     "cb200_masks_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cb200_read_bgra8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cb200_framebuffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cb200_read_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cb200_read_rgba8_into": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4),
     "cb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -100,6 +102,7 @@ SIGNATURES = {
     "cv_is_point_in_path": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "cv_measure_text": (C.c_float, [C.c_void_p, C.c_char_p]),
     "cv_flush": (C.c_int, [C.c_void_p]),
+    "cv_write_tga": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cv_batch_create": (C.c_void_p, [C.c_int] * 4),
     "cv_batch_canvas": (C.c_void_p, [C.c_void_p, C.c_int]),
     "cv_batch_flush": (C.c_int, [C.c_void_p]),

@@ -52,6 +52,8 @@ class Canvas:
             self._h = self._lib.cv_create(self.width, self.height)
         if not self._h:
             raise RuntimeError("canvas_ity_b200: " + self._lib.cv_last_error().decode())
+        self._band = None if band is None else (int(band[0]), int(band[1]))
+        self._device_index = int(device or 0)
         self._w = ScriptWriter()
         self._state = {k: v[2] for k, v in _FIELDS.items()}
         self._stack = []
@@ -206,6 +208,45 @@ class Canvas:
         if rc != 0:
             raise RuntimeError(self._lib.cv_last_error().decode())
         return out
+
+    # -- beyond the reference API: the steps that follow get_image_data in its drivers, kept on the GPU --
+    def device_canvas(self):
+        """The cb200_canvas handle behind this canvas (None for tapped canvases)."""
+        return self._lib.cv_device(self._h)
+
+    def image_tensor(self, bgra=False):
+        """get_image_data straight into a CUDA tensor: (rows, width, 4) uint8, no host copy."""
+        import torch
+        self.flush()
+        rows = self.height if self._band is None else self._band[1]
+        y0 = 0 if self._band is None else self._band[0]
+        out = torch.empty((rows, self.width, 4), dtype=torch.uint8, device="cuda:%d" % self._device_index)
+        dev = self.device_canvas()
+        if self._lib.cb200_read_rgba8_into(dev, C.c_void_p(out.data_ptr()), self.width, rows, 0, y0) != 0 or \
+                self._lib.cb200_sync(dev) != 0:
+            raise RuntimeError(self._lib.cb200_last_error().decode())
+        return out[..., [2, 1, 0, 3]] if bgra else out
+
+    def framebuffer_tensor(self):
+        """Zero-copy torch view of the linear premultiplied float framebuffer, (rows, width, 4) float32.
+        Valid until the next draw call is flushed."""
+        import torch
+        self.flush()
+        ptr, rows, width = C.c_void_p(), C.c_int(), C.c_int()
+        if self._lib.cb200_framebuffer_device(self.device_canvas(), C.byref(ptr), C.byref(rows), C.byref(width)) != 0:
+            raise RuntimeError(self._lib.cb200_last_error().decode())
+
+        class _View:                                    # what torch.as_tensor needs to wrap foreign device memory
+            __cuda_array_interface__ = {"shape": (rows.value, width.value, 4), "typestr": "<f4", "data": (ptr.value, False),
+                                        "version": 2, "strides": None}
+        return torch.as_tensor(_View(), device="cuda:%d" % self._device_index)
+
+    def write_tga(self, path):
+        """The image file demos/tiger/tiger.cpp:4333-4345 writes: 18-byte header + top-down BGRA rows,
+        with the channel swap done by the readback kernel."""
+        self.flush()
+        if self._lib.cv_write_tga(self._h, str(path).encode()) != 0:
+            raise RuntimeError(self._lib.cv_last_error().decode())
 
     def put_image_data(self, image, width, height, stride, x, y):
         self._w.ints("PUT_IMAGE_DATA", width, height, stride, x, y)

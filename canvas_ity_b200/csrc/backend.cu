@@ -136,6 +136,7 @@ struct cb200_canvas {
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
     cudaEvent_t ev[10];
     bool stage_timing = true;          // cb200_set_stage_timing
+    bool read_bgra = false;            // channel order of the readback in progress (cb200_read_bgra8)
     bool clear_pending = false;        // cb200_clear / replay(clear): folded into the next frame, or applied by settle()
     bool inflight_clear = false;       // the frame in flight starts from a cleared canvas (kept for overflow re-runs)
     bool replay_verified = false;      // the resident frame has completed once with the current capacities
@@ -998,7 +999,8 @@ static int readback_to_device(cb200_canvas *cv, int width, int height, int x, in
     size_t bytes = 4 * size_t(width) * size_t(height);
     CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
     CK(cudaEventRecord(cv->ev[7], cv->stream));
-    launch_readback(cv->fb, cv->width, cv->band_y0, cv->band_rows, cv->rgba8.p, width, height, x, y, cv->stream);
+    launch_readback(cv->fb, cv->width, cv->band_y0, cv->band_rows, cv->rgba8.p, width, height, x, y, cv->stream,
+                    cv->read_bgra ? 1 : 0);
     ++cv->launches;
     return CB200_OK;
 }
@@ -1018,6 +1020,28 @@ void *cb200_host_alloc(size_t bytes)
 }
 
 void cb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int cb200_read_bgra8(cb200_canvas *cv, uint8_t *dst, int width, int height, int stride, int x, int y)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    cv->read_bgra = true;
+    int rc = cb200_read_rgba8(cv, dst, width, height, stride, x, y);
+    cv->read_bgra = false;
+    return rc;
+}
+
+int cb200_framebuffer_device(cb200_canvas *cv, void **device_ptr, int *rows, int *width)
+{
+    if (!cv || !device_ptr) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = settle(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaStreamSynchronize(cv->stream));
+    *device_ptr = cv->fb;
+    if (rows) *rows = int(fb_rows(cv));
+    if (width) *width = cv->width;
+    return CB200_OK;
+}
 
 int cb200_read_rgba8(cb200_canvas *cv, uint8_t *dst, int width, int height, int stride, int x, int y)
 {

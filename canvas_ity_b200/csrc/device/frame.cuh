@@ -99,7 +99,7 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
 // pixels.cu
 // dst / src are tightly packed RGBA8 device buffers of dst_w x dst_h pixels
 void launch_readback(const float4 *fb, int width, int band_y0, int band_rows, uint8_t *dst, int dst_w,
-                     int dst_h, int x, int y, cudaStream_t s);
+                     int dst_h, int x, int y, cudaStream_t s, int bgra = 0);
 void launch_upload(float4 *fb, int width, int band_y0, int band_rows, const uint8_t *src, int src_w,
                    int src_h, int x, int y, cudaStream_t s);
 void launch_texel_convert(const uint8_t *src, float4 *dst, uint64_t n_texels, cudaStream_t s);

@@ -5,6 +5,7 @@
 
 #include "../../../include/canvas_b200_api.h"
 
+#include <cstdio>
 #include <new>
 #include <vector>
 #include <stdexcept>
@@ -238,6 +239,33 @@ int cv_is_point_in_path(cv_canvas *canvas, float x, float y)
 float cv_measure_text(cv_canvas *canvas, const char *text)
 {
     return canvas ? front(canvas)->measure_text(text) : 0.0f;
+}
+
+int cv_write_tga(cv_canvas *canvas, const char *path)
+{
+    if (!canvas || !path) return CB200_ERR_BAD_ARG;
+    canvas_ity::canvas::host_state *s = front(canvas)->b200();
+    s->flush();
+    if (!s->device) { g_api_error = "cv_write_tga: tapped canvas has no device"; return CB200_ERR_NO_DEVICE; }
+    const int w = s->width, h = s->height;
+    if (w > 0xffff || h > 0xffff) { g_api_error = "cv_write_tga: TGA holds at most 65535 x 65535 pixels"; return CB200_ERR_BAD_ARG; }
+    const size_t bytes = size_t(w) * size_t(h) * 4;
+    uint8_t *pixels = static_cast<uint8_t *>(cb200_host_alloc(bytes));        // page-locked: one DMA, no bounce
+    if (!pixels) { g_api_error = "cv_write_tga: out of host memory"; return CB200_ERR_OOM; }
+    int rc = cb200_read_bgra8(s->device, pixels, w, h, 4 * w, 0, 0);
+    if (rc == CB200_OK) {
+        const unsigned char header[18] = { 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                           (unsigned char)(w & 255), (unsigned char)(w >> 8),
+                                           (unsigned char)(h & 255), (unsigned char)(h >> 8), 32, 40 };
+        FILE *f = fopen(path, "wb");
+        if (!f || fwrite(header, 1, sizeof header, f) != sizeof header || fwrite(pixels, 1, bytes, f) != bytes) {
+            g_api_error = std::string("cv_write_tga: cannot write ") + path;
+            rc = CB200_ERR_BAD_ARG;
+        }
+        if (f) fclose(f);
+    } else g_api_error = cb200_last_error();
+    cb200_host_free(pixels);
+    return rc;
 }
 
 int cv_flush(cv_canvas *canvas)

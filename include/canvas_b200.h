@@ -175,6 +175,14 @@ int cb200_clear(cb200_canvas *canvas);
  * mask + save stack); every other plane is freed. */
 int cb200_masks_keep(cb200_canvas *canvas, const uint32_t *slots, uint32_t n);
 
+/* cb200_read_rgba8 with the red and blue channels exchanged on the device (the order TGA and BMP
+ * files store; demos/tiger/tiger.cpp:4339 swaps them on the CPU after get_image_data). */
+int cb200_read_bgra8(cb200_canvas *canvas, uint8_t *dst, int width, int height, int stride, int x, int y);
+/* The linear premultiplied float4 framebuffer itself, in device memory (rows x width float4, rows
+ * = the band's rows, or all stacked slots of a batch): for zero-copy views from CUDA code or
+ * torch (__cuda_array_interface__).  Waits for queued work; valid until the next frame. */
+int cb200_framebuffer_device(cb200_canvas *canvas, void **device_ptr, int *rows, int *width);
+
 /* Readback without the host copy: runs the sRGB/dither kernel into a device
  * buffer owned by the canvas and returns its device pointer (for NCCL gathers
  * and device-resident timing). */

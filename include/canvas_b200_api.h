@@ -53,6 +53,11 @@ int   cv_put_image_data(cv_canvas *canvas, const uint8_t *image, int width, int 
 int   cv_is_point_in_path(cv_canvas *canvas, float x, float y);    /* :843 */
 float cv_measure_text(cv_canvas *canvas, const char *text);        /* :1025 */
 
+/* The file demos/tiger/tiger.cpp:4333-4345 writes after get_image_data: an uncompressed 32-bit TGA
+ * (18-byte header, top-down rows, BGRA).  Here the channel swap happens in the readback kernel
+ * (cb200_read_bgra8) and the rows go from the pinned staging buffer to the file. */
+int cv_write_tga(cv_canvas *canvas, const char *path);
+
 /* A batch of n independent width x height canvases rendered together on one GPU
  * (cb200_batch_*): cv_batch_canvas(i) is an ordinary front-end canvas whose draws
  * are queued in the batch; cv_batch_flush() lowers and submits all of them in one

@@ -13,8 +13,10 @@
 #include "../canvas_ity_b200/csrc/host/script.hpp"
 #include "../include/canvas_b200_api.h"
 
+#include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace {
 struct ns_tag {
@@ -66,6 +68,23 @@ int cv_put_image_data(cv_canvas *c, const uint8_t *image, int w, int h, int stri
 }
 int cv_is_point_in_path(cv_canvas *c, float x, float y) { return ref(c)->is_point_in_path(x, y); }
 float cv_measure_text(cv_canvas *c, const char *text) { return ref(c)->measure_text(text); }
+// what demos/tiger/tiger.cpp:4333-4345 does after rendering: get_image_data, swap R and B on the CPU, write
+int cv_write_tga(cv_canvas *c, const char *path)
+{
+    canvas_ity::canvas *r = ref(c);
+    const int w = r->size_x, h = r->size_y;
+    std::vector<unsigned char> image(size_t(w) * size_t(h) * 4);
+    r->get_image_data(image.data(), w, h, 4 * w, 0, 0);
+    for (size_t i = 0; i < image.size(); i += 4) { unsigned char t = image[i]; image[i] = image[i + 2]; image[i + 2] = t; }
+    const unsigned char header[18] = { 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, (unsigned char)(w & 255), (unsigned char)(w >> 8),
+                                       (unsigned char)(h & 255), (unsigned char)(h >> 8), 32, 40 };
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    fwrite(header, 1, sizeof header, f);
+    fwrite(image.data(), 1, image.size(), f);
+    fclose(f);
+    return 0;
+}
 int cv_flush(cv_canvas *) { return 0; }
 // batches are a back-end concept: the reference renders canvases one by one
 cv_batch *cv_batch_create(int, int, int, int) { return nullptr; }

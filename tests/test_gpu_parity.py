@@ -297,3 +297,91 @@ def test_batch_with_clip_masks_and_odd_size(lib):
             assert nbad == 0, "canvas %d: %d floats off (max %.3g)" % (i, nbad, worst)
     finally:
         lib.cv_batch_destroy(batch)
+
+
+def test_tga_writer_and_bgra_readback(lib, tmp_path):
+    """The step after get_image_data in demos/tiger (tiger.cpp:4333-4345): same file layout, the
+    channel swap done on the device; pixels within +-1 LSB of the reference's file."""
+    size = 200
+    script = H.tiger_script(size, size)
+    h = lib.cv_create(size, size)
+    try:
+        lib.cv_run_script(h, script, len(script), None, 0, None)
+        assert lib.cv_write_tga(h, str(tmp_path / "gpu.tga").encode()) == 0, lib.cv_last_error()
+        rgba = np.zeros((size, size, 4), np.uint8)
+        bgra = np.zeros((size, size, 4), np.uint8)
+        assert lib.cv_get_image_data(h, rgba.ctypes.data, size, size, 4 * size, 0, 0) == 0
+        assert lib.cb200_read_bgra8(lib.cv_device(h), bgra.ctypes.data, size, size, 4 * size, 0, 0) == 0
+    finally:
+        lib.cv_destroy(h)
+    assert np.array_equal(bgra, rgba[..., [2, 1, 0, 3]])
+    data = (tmp_path / "gpu.tga").read_bytes()
+    assert data[:18] == bytes([0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, size & 255, size >> 8, size & 255, size >> 8, 32, 40])
+    assert np.array_equal(np.frombuffer(data[18:], np.uint8).reshape(size, size, 4), bgra)
+    ref = H.reference_library()
+    if ref is not None:                                     # this container only: the reference build writes the file too
+        r = ref.cv_create(size, size)
+        ref.cv_run_script(r, script, len(script), None, 0, None)
+        assert ref.cv_write_tga(r, str(tmp_path / "ref.tga").encode()) == 0
+        ref.cv_destroy(r)
+        want = np.frombuffer((tmp_path / "ref.tga").read_bytes()[18:], np.uint8).reshape(size, size, 4)
+        assert H.rgba8_mismatch(bgra[..., [2, 1, 0, 3]], want[..., [2, 1, 0, 3]])[2] == 0
+    else:
+        assert H.rgba8_mismatch(rgba, H.render_oracle(script, size, size)["rgba8"])[2] == 0
+
+
+def test_torch_views_of_the_canvas(lib):
+    """framebuffer_tensor is a zero-copy view of the float framebuffer, image_tensor the readback on device."""
+    import torch
+    import canvas_ity_b200 as cb
+    c = cb.Canvas(96, 64)
+    c.set_color(cb.fill_style, 0.2, 0.6, 0.9, 0.5)
+    c.fill_rectangle(8, 8, 40, 30)
+    fb = c.framebuffer_tensor()
+    img = c.image_tensor()
+    assert fb.shape == (64, 96, 4) and fb.dtype == torch.float32 and fb.is_cuda
+    assert img.shape == (64, 96, 4) and img.dtype == torch.uint8 and img.is_cuda
+    assert np.array_equal(fb.cpu().numpy(), c.read_f32())
+    assert np.array_equal(img.cpu().numpy(), c.get_image_data())
+    assert np.array_equal(c.image_tensor(bgra=True).cpu().numpy(), c.get_image_data()[..., [2, 1, 0, 3]])
+    c.close()
+
+
+def test_clear_is_deferred_but_never_lost(lib):
+    """cb200_clear is folded into the next frame (or applied by the next pixel access): every order of
+    clear / draw / read / put must still behave like an immediate clear."""
+    size = 96
+    from canvas_ity_b200.script import ScriptWriter
+    def rect(x, y, colour):
+        w = ScriptWriter()
+        w.ints("SET_COLOR", 0); w.raw("4f", *colour)
+        w.floats("FILL_RECTANGLE", float(x), float(y), 30.0, 30.0)
+        return w.take()
+    a, b = rect(5, 5, (1, 0, 0, 1)), rect(50, 50, (0, 0, 1, 0.5))
+    h = lib.cv_create(size, size)
+    dev = lib.cv_device(h)
+    out = np.zeros((size, size, 4), np.uint8)
+    def read():
+        assert lib.cv_get_image_data(h, out.ctypes.data, size, size, 4 * size, 0, 0) == 0
+        return out.copy()
+    try:
+        lib.cv_run_script(h, a, len(a), None, 0, None)
+        first = read()
+        assert first[10, 10, 3] == 255 and first[60, 60, 3] == 0
+        assert lib.cb200_clear(dev) == 0                    # clear, then read: nothing left
+        assert not read().any()
+        lib.cv_run_script(h, a, len(a), None, 0, None); read()
+        assert lib.cb200_clear(dev) == 0                    # clear, then draw: only the new draw
+        lib.cv_run_script(h, b, len(b), None, 0, None)
+        second = read()
+        assert second[10, 10, 3] == 0 and second[60, 60, 3] > 100
+        assert lib.cb200_clear(dev) == 0                    # clear, then put_image_data: only the put
+        patch = np.full((4, 4, 4), 255, np.uint8)
+        assert lib.cv_put_image_data(h, patch.ctypes.data, 4, 4, 16, 70, 2) == 0
+        third = read()
+        assert third[3, 71, 3] == 255 and third[60, 60, 3] == 0 and third[10, 10, 3] == 0
+        lib.cv_run_script(h, a, len(a), None, 0, None)        # draw without a clear keeps what is there
+        fourth = read()
+        assert fourth[3, 71, 3] == 255 and fourth[10, 10, 3] == 255
+    finally:
+        lib.cv_destroy(h)
