@@ -541,7 +541,8 @@ int upload_frame(cb200_canvas *cv)
     f.general_compositor = 0;
     for (const job_rec &j : sf.jobs) {
         const draw_rec &d = sf.draws[j.draw];
-        if (j.kind != JOB_MAIN || d.mask_src || sf.brushes[d.brush].type != CB200_BRUSH_COLOR) f.general_compositor = 1;
+        if (j.kind != JOB_MAIN || d.mask_src) f.general_compositor = std::max(f.general_compositor, 1);
+        if (j.kind == JOB_MAIN && sf.brushes[d.brush].type != CB200_BRUSH_COLOR) f.general_compositor = 2;
     }
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);
     f.n_shadow_jobs = uint32_t(sf.shadow_jobs.size());

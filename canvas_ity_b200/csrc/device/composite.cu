@@ -179,34 +179,55 @@ struct staged_brush {
 };
 
 // Linear / radial gradient at a device-space pixel centre (hpp:2331-2376), from the staged copy.
-__device__ __noinline__ rgba paint_gradient(const staged_brush &sb, float x, float y)
+// Everything that does not depend on the pixel is gathered once per (job, warp).
+struct gradient_ctx {
+    affine inv;
+    float sx, sy, ax, ay, axis2, r0, dr;
+    uint32_t n;
+    bool linear;
+};
+
+__device__ __forceinline__ gradient_ctx make_gradient_ctx(const staged_brush &sb)
 {
+    gradient_ctx g;
     const brush_rec &b = sb.b;
-    vec2 p = apply(sb.inv, v2(x, y));
-    vec2 rel = p - v2(b.sx, b.sy), axis = v2(b.ex, b.ey) - v2(b.sx, b.sy);
-    float along = dot(rel, axis), axis2 = dot(axis, axis);
+    g.inv = sb.inv;
+    g.sx = b.sx; g.sy = b.sy;
+    vec2 axis = v2(b.ex, b.ey) - v2(b.sx, b.sy);
+    g.ax = axis.x; g.ay = axis.y;
+    g.axis2 = dot(axis, axis);
+    g.r0 = b.r0; g.dr = b.r1 - b.r0;
+    g.n = b.n_colors;
+    g.linear = b.type == CB200_BRUSH_LINEAR;
+    return g;
+}
+
+__device__ __forceinline__ rgba gradient_at(const gradient_ctx &g, const staged_brush &sb, float x, float y)
+{
+    vec2 p = apply(g.inv, v2(x, y));
+    vec2 rel = p - v2(g.sx, g.sy), axis = v2(g.ax, g.ay);
+    float along = dot(rel, axis);
     float t;
-    if (b.type == CB200_BRUSH_LINEAR) {
-        if (axis2 == 0.0f) return mk(0.0f, 0.0f, 0.0f, 0.0f);
-        t = along / axis2;
+    if (g.linear) {
+        if (g.axis2 == 0.0f) return mk(0.0f, 0.0f, 0.0f, 0.0f);
+        t = along / g.axis2;
     } else {
-        float dr = b.r1 - b.r0;
-        float qa = axis2 - dr * dr;
-        float qb = -2.0f * (along + b.r0 * dr);
-        float qc = dot(rel, rel) - b.r0 * b.r0;
+        float qa = g.axis2 - g.dr * g.dr;
+        float qb = -2.0f * (along + g.r0 * g.dr);
+        float qc = dot(rel, rel) - g.r0 * g.r0;
         float disc = qb * qb - 4.0f * qa * qc;
-        if (disc < 0.0f || (axis2 == 0.0f && dr == 0.0f)) return mk(0.0f, 0.0f, 0.0f, 0.0f);
+        if (disc < 0.0f || (g.axis2 == 0.0f && g.dr == 0.0f)) return mk(0.0f, 0.0f, 0.0f, 0.0f);
         float root = sqrtf(disc), inv2a = 1.0f / (2.0f * qa);
         float ta = (-qb - root) * inv2a, tb = (-qb + root) * inv2a;
-        if (b.r0 + dr * tb >= 0.0f) t = tb;
-        else if (b.r0 + dr * ta >= 0.0f) t = ta;
+        if (g.r0 + g.dr * tb >= 0.0f) t = tb;
+        else if (g.r0 + g.dr * ta >= 0.0f) t = ta;
         else return mk(0.0f, 0.0f, 0.0f, 0.0f);
     }
     uint32_t hi = 0;                                    // first stop strictly greater than t (NaN: none)
-    while (hi < b.n_colors && !(t < sb.stops[hi])) ++hi;
+    while (hi < g.n && !(t < sb.stops[hi])) ++hi;
     float4 c;
     if (hi == 0) c = sb.colors[0];
-    else if (hi == b.n_colors) c = sb.colors[b.n_colors - 1];
+    else if (hi == g.n) c = sb.colors[g.n - 1];
     else {
         float m = (t - sb.stops[hi - 1]) / (sb.stops[hi] - sb.stops[hi - 1]);
         float4 lo = sb.colors[hi - 1], up = sb.colors[hi];
@@ -214,6 +235,11 @@ __device__ __noinline__ rgba paint_gradient(const staged_brush &sb, float x, flo
                         lo.w + m * (up.w - lo.w));
     }
     return mk(c.x * c.w, c.y * c.w, c.z * c.w, c.w);
+}
+
+__device__ __noinline__ rgba paint_gradient(const staged_brush &sb, float x, float y)
+{
+    return gradient_at(make_gradient_ctx(sb), sb, x, y);
 }
 
 // Bicubic (Keys) pattern / image sample (hpp:2274-2330).  Same taps, weights and summation order as
@@ -301,13 +327,16 @@ struct warp_scratch {
 // One WARP owns 8 scanlines x 32 pixels of a tile (8 pixels per lane, in registers) and works
 // completely on its own: no block-wide barrier anywhere, so an SM keeps ~20 independent
 // tile-quarters in flight and their dependent loads (job table -> tile entry -> runs) overlap.
-// kGeneral = false is the lean build for frames that only hold unclipped solid-colour fills and
-// strokes without shadows (the tiger, most UI and plots): no gradient/pattern/mask/shadow code, so
-// no register spills on the hot path.  The host picks the variant per frame.
-template <bool kGeneral>
-__global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(device_frame f, canvas_target t, int sb,
+// Three builds of the same code, picked by the host per frame (device_frame::general_compositor):
+//   kMode 0  lean: frames that only hold unclipped solid-colour fills and strokes without shadows
+//            (the tiger, most UI and plots) -- no gradient/pattern/mask/shadow code, no spills
+//   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
+//   kMode 2  + gradients and patterns
+template <int kMode>
+__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 6 : 5) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
+    constexpr bool kGeneral = kMode >= 1, kPaint = kMode == 2;
     grid_dependency_wait();
     __shared__ __align__(16) warp_scratch scratch[kTileWarps];
     frame_header *h = f.hdr;
@@ -396,7 +425,7 @@ __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(devi
             float *mask_out = (kGeneral && c.kind == JOB_CLIP) ? t.mask_planes[c.mask_dst] : nullptr;
             const bool gradient = brush_type == CB200_BRUSH_LINEAR || brush_type == CB200_BRUSH_RADIAL;
             bool staged = false;
-            if (kGeneral && (gradient || brush_type == CB200_BRUSH_PATTERN) && c.kind == JOB_MAIN) {
+            if (kPaint && (gradient || brush_type == CB200_BRUSH_PATTERN) && c.kind == JOB_MAIN) {
                 // stage the brush: record (14 words), brush-space matrix (6 words), gradient stops
                 const brush_rec *gb = &f.brushes[c.brush];
                 const uint32_t n_stops = gradient ? gb->n_colors : 0;
@@ -425,6 +454,18 @@ __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(devi
                     ++painted;
                     blend(px[r], scale(cov * alpha, flat), op, 1.0f);
                 }
+            } else if (kPaint && staged && gradient && !mask && !mask_out) {
+                // unclipped gradient fill: the brush set-up is hoisted out of the pixel loop
+                const gradient_ctx g = make_gradient_ctx(ws.brush);
+#pragma unroll
+                for (int r = 0; r < kWarpRows; ++r) {
+                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, row0 + r, tile_x0, ws.row_buf);
+                    float cov = fminf(fabsf(sum), 1.0f);
+                    if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
+                    ++painted;
+                    rgba paint = gradient_at(g, ws.brush, float(x) + 0.5f, float(row0 + r) + 0.5f);
+                    blend(px[r], scale(cov * alpha, paint), op, 1.0f);
+                }
             } else if (kGeneral) {
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
@@ -441,6 +482,7 @@ __global__ void __launch_bounds__(kCompBlock, kGeneral ? 5 : 8) k_composite(devi
                     rgba paint;
                     if (brush_type == CB200_BRUSH_COLOR) paint = flat;
                     else if (brush_type == 0xffu) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (!kPaint) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);       // unreachable: the host picked mode 2
                     else if (staged && gradient) paint = paint_gradient(ws.brush, float(x) + 0.5f, float(y) + 0.5f);
                     else if (staged) paint = paint_pattern(f.texels, &ws.brush, float(x) + 0.5f, float(y) + 0.5f);
                     else paint = paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f);
@@ -519,8 +561,9 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     // overrides.
     int eager = f.n_opaque_jobs == 0;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
-    if (f.general_compositor) launch_pdl(k_composite<true>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
-    else launch_pdl(k_composite<false>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
+    if (f.general_compositor == 2) launch_pdl(k_composite<2>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
+    else if (f.general_compositor == 1) launch_pdl(k_composite<1>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
+    else launch_pdl(k_composite<0>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
 }
 
 }  // namespace cb200
