@@ -333,7 +333,7 @@ struct warp_scratch {
 //   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
 //   kMode 2  + gradients and patterns
 template <int kMode>
-__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 6 : 5) k_composite(device_frame f, canvas_target t, int sb,
+__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 5) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
     constexpr bool kGeneral = kMode >= 1, kPaint = kMode == 2;
