@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     const uint32_t j = f.shadow_jobs[blockIdx.y];
     const job_rec &jr = f.jobs[j];
     const uint32_t tiles = uint32_t(jr.tw) * uint32_t(jr.th);
-    if (blockIdx.x >= tiles) return;
+    if (blockIdx.x * (kBlock / 32) >= tiles) return;
     const draw_rec &d = f.draws[jr.draw];
     const brush_rec &br = f.brushes[d.brush];
     const cov_source cs = make_cov_source(f, sb);
@@ -115,19 +115,22 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     float *plane = f.planes + jr.plane_offset;
     // a solid brush has one alpha for the whole plane (negative: evaluate the brush per pixel)
     const float flat_alpha = br.type == CB200_BRUSH_COLOR ? (br.n_colors ? f.colors[br.first_color].w : 0.0f) : -1.0f;
-    for (uint32_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+    // one warp per tile: the tile set-up is paid once for 32 rows
+    for (uint32_t tl = blockIdx.x * (kBlock / 32) + warp; tl < tiles; tl += gridDim.x * (kBlock / 32)) {
         int tx = jr.tx0 + int(tl % uint32_t(jr.tw)), ty = jr.ty0 + int(tl / uint32_t(jr.tw));
         uint32_t te = jr.te_base + tl;
         int x = tx * kTile + lane;
+        const bool x_in = x >= jr.left && x < jr.left + jr.bw;
         // row info of the whole tile in two coalesced loads; most rows have no run in the tile
         const float carried = cs.backdrop[te * kTile + lane];
         const uint32_t first = cs.first[te * kTile + lane];
-        for (int k = 0; k < kTile / (kBlock / 32); ++k) {
-            int ly = warp + k * (kBlock / 32), y = ty * kTile + ly;
+        float *out = plane + ptrdiff_t(ty * kTile - jr.top) * ptrdiff_t(jr.pitch) + ptrdiff_t(x - jr.left + jr.skew);
+        const int ly0 = max(0, jr.top - ty * kTile), ly1 = min(kTile, jr.top + jr.bh - ty * kTile);
+        for (int ly = ly0; ly < ly1; ++ly) {
+            const int y = ty * kTile + ly;
             float sum = __shfl_sync(0xffffffffu, carried, ly);
             if (__shfl_sync(0xffffffffu, first, ly) != kNoRun) sum = tile_row_sum(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
             float cov = fminf(fabsf(sum), 1.0f);
-            if (x < jr.left || x >= jr.left + jr.bw || y < jr.top || y >= jr.top + jr.bh) continue;
             float v = 0.0f;
             if (cov >= kThreshold) {
                 if (flat_alpha >= 0.0f) v = cov * flat_alpha;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
                     v = cov * paint_alpha(f, br, d.inverse, centre);
                 }
             }
-            plane[size_t(y - jr.top) * size_t(jr.pitch) + size_t(x - jr.left + jr.skew)] = v;
+            if (x_in) out[ptrdiff_t(ly) * ptrdiff_t(jr.pitch)] = v;
         }
     }
 }
