@@ -21,40 +21,48 @@ namespace {
 
 constexpr uint32_t kShortRow = 48;      // longer scanline segments go to the warp-cooperative kernel
 
-__global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
+// One short scanline segment, walked by one thread from its first run `i`.
+__device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h, const uint64_t *keys, const float *delta,
+                                         uint32_t n, uint32_t i, uint32_t bx, uint32_t by)
 {
-    grid_dependency_wait();
-    frame_header *h = f.hdr;
-    if (h->overflow) return;
-    const uint32_t n = h->n_runs;
-    const uint32_t bx = h->sort_bits_x, by = h->sort_bits_y;
     const uint64_t xmask = (1ull << bx) - 1, ymask = (1ull << by) - 1;
-    const uint64_t *keys = f.keys[sb];
-    const float *delta = f.vals[sb];
     const float quiet_nan = __int_as_float(0x7fc00000);
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t row = keys[i] >> bx;
-        if (i > 0 && (keys[i - 1] >> bx) == row) continue;          // not a segment head
-        uint32_t j = uint32_t(row >> by);
-        if (j >= h->n_jobs) continue;
-        if (i + kShortRow < n && (keys[i + kShortRow] >> bx) == row) {   // sorted: the segment is longer than that
-            f.long_rows[atomicAdd(&h->n_long_rows, 1u)] = i;             // a whole warp takes it
-            continue;
+    uint64_t key = keys[i];
+    const uint64_t row = key >> bx;
+    uint32_t j = uint32_t(row >> by);
+    if (j >= h->n_jobs) return;
+    if (i + kShortRow < n && (keys[i + kShortRow] >> bx) == row) {   // sorted: the segment is longer than that
+        f.long_rows[atomicAdd(&h->n_long_rows, 1u)] = i;             // a whole warp takes it
+        return;
+    }
+    int y = int(row & ymask);
+    const job_rec &jr = f.jobs[j];
+    int ty = y / kTile - jr.ty0, ly = y % kTile;
+    bool binned = ty >= 0 && ty < jr.th && jr.tw > 0;
+    bool everywhere = jr.kind != JOB_MAIN || (~f.draws[jr.draw].op & 8u);
+    uint32_t te_row = jr.te_base + uint32_t(ty) * uint32_t(jr.tw);
+    int c_prev = jr.tx0 - 1;                                     // last tile column handled
+    const int c_end = jr.tx0 + jr.tw - 1;
+    float sum = 0.0f;
+    // runs are fetched four at a time (plus the key that follows them), so that the walk waits for
+    // memory once per batch instead of once per run; reading past the segment's end is harmless
+    constexpr int kBatch = 4;
+    bool more = true;
+    for (uint32_t k0 = i; more; k0 += kBatch) {
+        uint64_t kk[kBatch + 1];
+        float dd[kBatch];
+        kk[0] = key;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const uint32_t idx = k0 + uint32_t(u);
+            kk[u + 1] = idx + 1 < n ? keys[idx + 1] : ~0ull;
+            dd[u] = idx < n ? delta[idx] : 0.0f;
         }
-        int y = int(row & ymask);
-        const job_rec &jr = f.jobs[j];
-        int ty = y / kTile - jr.ty0, ly = y % kTile;
-        bool binned = ty >= 0 && ty < jr.th && jr.tw > 0;
-        bool everywhere = jr.kind != JOB_MAIN || (~f.draws[jr.draw].op & 8u);
-        uint32_t te_row = jr.te_base + uint32_t(ty) * uint32_t(jr.tw);
-        int c_prev = jr.tx0 - 1;                                     // last tile column handled
-        const int c_end = jr.tx0 + jr.tw - 1;
-        float sum = 0.0f;
-        uint32_t k = i;
-        uint64_t key = keys[k];
-        for (;;) {
-            int x = int(key & xmask);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (!more) break;
+            const uint32_t k = k0 + uint32_t(u);
+            int x = int(kk[u] & xmask);
             int c = x / kTile;
             if (binned && c > c_prev) {
                 int last = min(c, c_end);
@@ -72,23 +80,36 @@ __global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
                 }
                 c_prev = max(c_prev, last);
             }
-            sum += delta[k];
-            uint32_t nk = k + 1;
-            uint64_t nkey = nk < n ? keys[nk] : ~0ull;
-            bool same_row = (nkey >> bx) == row;
+            sum += dd[u];
+            const uint64_t nkey = kk[u + 1];
+            const bool same_row = (nkey >> bx) == row;
             f.cumulative[k] = (same_row && int(nkey & xmask) == x) ? quiet_nan : sum;
-            if (!same_row) break;
-            k = nk;
-            key = nkey;
+            more = same_row;
         }
-        // whatever is left over after the last run spills to the right edge
-        if (binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
-            for (int cc = c_prev + 1; cc <= c_end; ++cc) {
-                uint32_t te = te_row + uint32_t(cc - jr.tx0);
-                f.te_backdrop[te * kTile + ly] = sum;
-                { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
-            }
+        key = kk[kBatch];
     }
+    // whatever is left over after the last run spills to the right edge
+    if (binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
+        for (int cc = c_prev + 1; cc <= c_end; ++cc) {
+            uint32_t te = te_row + uint32_t(cc - jr.tx0);
+            f.te_backdrop[te * kTile + ly] = sum;
+            { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
+        }
+}
+
+// One thread per run; the ones that sit on the first run of a segment walk it.
+__global__ void __launch_bounds__(kBlock) k_rows(device_frame f, int sb)
+{
+    grid_dependency_wait();
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    const uint32_t n = h->n_runs;
+    const uint32_t bx = h->sort_bits_x, by = h->sort_bits_y;
+    const uint64_t *keys = f.keys[sb];
+    const float *delta = f.vals[sb];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (i == 0 || (keys[i - 1] >> bx) != (keys[i] >> bx)) walk_row(f, h, keys, delta, n, i, bx, by);
 }
 
 // Long scanline segments (thin, nearly horizontal shapes put thousands of runs on
