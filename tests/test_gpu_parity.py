@@ -151,6 +151,46 @@ def test_full_size_properties_4096(lib):
     assert np.abs(small - gold).mean() < 3.0
 
 
+def test_full_size_properties_config3_shadows_4096(lib):
+    """Config 3 (alpha 0.9, shadow_blur 16) at 4096^2: deterministic, a band equals the same rows of the
+    whole (shadow planes included), and the image downscales to the oracle's 512^2 render."""
+    size = 4096
+    kw = dict(global_alpha=0.9, shadow_blur=16.0, shadow_color=(0, 0, 0, 0.5))
+    script = H.tiger_script(size, size, **kw)
+    a = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
+    b = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
+    assert np.array_equal(a, b)
+    y0, rows = 2050, 130
+    h = lib.cv_create_band(size, size, 0, y0, rows)
+    try:
+        H._run(lib, h, script)
+        img = np.zeros((rows, size, 4), np.uint8)
+        lib.cv_get_image_data(h, img.ctypes.data, size, rows, 4 * size, 0, y0)
+    finally:
+        lib.cv_destroy(h)
+    assert np.array_equal(img, a[y0:y0 + rows])
+    # blur 16 at 4096 is blur 2 at 512: same picture up to resampling
+    small_script = H.tiger_script(512, 512, global_alpha=0.9, shadow_blur=2.0, shadow_color=(0, 0, 0, 0.5))
+    want = H.render_oracle(small_script, 512, 512)["rgba8"].astype(np.float32)
+    small = a.reshape(512, 8, 512, 8, 4).astype(np.float32).mean(axis=(1, 3))
+    assert np.abs(small - want).mean() < 4.0
+
+
+@pytest.mark.parametrize("kind", ["linear", "radial", "image"])
+def test_full_size_config4_fill_vs_oracle(lib, kind):
+    """Config 4 scenes are per-pixel independent, so the oracle can afford a 4096^2 canvas: float parity
+    of the whole framebuffer at a quarter of the benchmark's pixel count, same brush geometry."""
+    size = 4096
+    from canvas_ity_b200.script import ScriptWriter
+    bg = ScriptWriter()
+    bg.ints("SET_COLOR", 0); bg.raw("4f", 0.9, 0.8, 0.1, 0.6); bg.floats("FILL_RECTANGLE", 0, 0, float(size), float(size))
+    script = bg.take() + H.config4_script(kind, 15, size, image_size=256)
+    got = H.render_script(lib, script, size, size)
+    want = H.render_oracle(script, size, size)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "%s: %d floats off, max %.3g" % (kind, nbad, worst)
+
+
 def test_put_get_round_trip(lib):
     """put_image_data -> get_image_data is the identity on opaque pixels at any offset/stride."""
     rng = np.random.default_rng(7)
