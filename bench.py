@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="canvases replaying concurrently per GPU in the device-resident arm")
+    ap.add_argument("--lanes", type=int, default=8, help="canvases replaying concurrently per GPU in the device-resident arm")
     ap.add_argument("--e2e-lanes", type=int, default=0,
                     help="canvases kept in flight per rank by the end-to-end arm (default: up to 4, one host thread each, "
                          "as the host cores allow)")

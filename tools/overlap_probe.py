@@ -7,7 +7,7 @@ from canvas_ity_b200 import _native
 lib = _native.load()
 size = 4096
 frame = H.lower_script(H.tiger_script(size, size), size, size)[0]
-for lanes in (1, 2, 3, 4):
+for lanes in (1, 2, 4, 8):
     cvs = []
     for _ in range(lanes):
         cv = C.c_void_p()
