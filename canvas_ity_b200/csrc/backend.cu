@@ -117,7 +117,7 @@ struct cb200_canvas {
     dev_buf<float4> pieces, texels;
     dev_buf<comp_rec> comp;
     dev_buf<uint2> job_box;
-    dev_buf<uint32_t> job_te, blur_units;
+    dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -135,6 +135,7 @@ struct cb200_canvas {
     bool resident = false;                    // staged frame came from cb200_frame_upload
     size_t hdr_offset = 0, hdr_pristine_offset = 0;
     cudaEvent_t ev[10];
+    uint32_t row_stride = 0;  bool use_row_lists = false;
     bool stage_timing = true;          // cb200_set_stage_timing
     bool read_bgra = false;            // channel order of the readback in progress (cb200_read_bgra8)
     bool clear_pending = false;        // cb200_clear / replay(clear): folded into the next frame, or applied by settle()
@@ -435,6 +436,18 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->job_box.reserve(sf.jobs.size() + 1));
     CK(cv->job_te.reserve(sf.jobs.size() + 1));
     CK(cv->blur_units.reserve(2 * (sf.shadow_jobs.size() + 1) + 2));
+    {   // tile-row job lists: rows of the target x the largest job count of a canvas (skipped when huge)
+        uint32_t most = 0;
+        for (const uint2 &cj : sf.canvas_jobs) most = std::max(most, cj.y);
+        const size_t rows = cv->n_canvases > 1 ? size_t(cv->n_canvases) * size_t(cv->slot_rows / kTile)
+                                                : size_t((cv->band_y0 + cv->band_rows - 1) / kTile - cv->band_y0 / kTile + 1);
+        cv->row_stride = (most + 31u) & ~31u;
+        cv->use_row_lists = most > 32 && rows * cv->row_stride <= (size_t(1) << 25);
+        if (cv->use_row_lists) {
+            CK(cv->row_jobs.reserve(rows * cv->row_stride));
+            CK(cv->row_job_count.reserve(rows));
+        }
+    }
     CK(cv->sort_hist.reserve(512 * kGrid + 512));
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
@@ -536,6 +549,7 @@ int upload_frame(cb200_canvas *cv)
     f.n_static_sources = uint32_t(sf.sources.size());
     f.jobs = reinterpret_cast<job_rec *>(b + o_jobs);
     f.comp = cv->comp.p; f.job_box = cv->job_box.p; f.job_te = cv->job_te.p; f.blur_units = cv->blur_units.p;
+    f.row_jobs = cv->use_row_lists ? cv->row_jobs.p : nullptr; f.row_job_count = cv->row_job_count.p; f.row_stride = cv->row_stride;
     f.n_opaque_jobs = 0;
     for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
     f.general_compositor = 0;
@@ -625,7 +639,7 @@ int run_frame(cb200_canvas *cv)
     CK(cudaEventRecord(cv->ev[6], s));
     cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
                     ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-                    (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1;
+                    (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
     cv->pending = true;
     CK(cudaGetLastError());
     return CB200_OK;
@@ -889,7 +903,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->row_piece.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
-    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->keys0.release(); cv->keys1.release();
+    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
     for (int i = 0; i < 10; ++i)

@@ -498,8 +498,11 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
     // 32 candidates per step.  Occlusion culling: a job that paints this whole tile with an opaque
     // solid colour (covered tile entry, source_over/copy, alpha 1, unclipped -- then cov = vis = 1
     // replaces the pixel exactly) voids everything collected or painted before it.
-    for (uint32_t base = job_begin; base < job_end; base += 32) {
-        const uint32_t j = base + uint32_t(lane);
+    const uint32_t *row_list = f.row_jobs ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
+    const uint32_t n_candidates = row_list ? f.row_job_count[ty - tile_y0] : job_end - job_begin;
+    for (uint32_t base = 0; base < n_candidates; base += 32) {
+        const uint32_t at = base + uint32_t(lane);
+        const uint32_t j = at < n_candidates ? (row_list ? row_list[at] : job_begin + at) : job_end;
         uint32_t te = 0;
         bool hit = false, cover = false;
         if (j < job_end) {
@@ -547,6 +550,40 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
     if (lane == 0 && painted) atomicAdd(&h->composited_pixels, (unsigned long long)painted);
 }
 
+// One warp per tile row of the target: the ordered list of jobs whose composite box reaches the row.
+__global__ void __launch_bounds__(kBlock) k_row_lists(device_frame f, canvas_target t, int tile_y0, int n_rows)
+{
+    grid_dependency_wait();
+    if (f.hdr->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const int row = int((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_rows) return;
+    const int ty = tile_y0 + row;
+    int canvas = 0, ty_local = ty;
+    if (t.n_canvases > 1) {
+        const int slot_tiles = t.slot_rows / kTile;
+        canvas = ty / slot_tiles;
+        ty_local = ty - canvas * slot_tiles;
+    }
+    const uint2 range = t.canvas_jobs[canvas];
+    uint32_t *list = f.row_jobs + size_t(row) * f.row_stride;
+    uint32_t n = 0;
+    for (uint32_t base = range.x; base < range.x + range.y; base += 32) {
+        const uint32_t j = base + uint32_t(lane);
+        bool in = false;
+        if (j < range.x + range.y) {
+            const uint2 box = f.job_box[j];
+            const int by0 = int((box.x >> 11) & 0x7ffu), by1 = int((box.y >> 1) & 0x7ffu);
+            const int bx0 = int(box.x & 0x7ffu), bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10);
+            in = bx1 >= bx0 && ty_local >= by0 && ty_local <= by1;
+        }
+        const uint32_t votes = __ballot_sync(0xffffffffu, in);
+        if (in) list[n + __popc(votes & ((1u << lane) - 1u))] = j;
+        n += __popc(votes);
+    }
+    if (lane == 0) f.row_job_count[row] = n;
+}
+
 }  // namespace
 
 void launch_composite(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s)
@@ -561,6 +598,10 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     // overrides.
     int eager = f.n_opaque_jobs == 0;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
+    if (f.row_jobs) {
+        const int n_rows = ty1 - ty0 + 1;
+        launch_pdl(k_row_lists, (n_rows * 32 + kBlock - 1) / kBlock, kBlock, 0, s, f, t, ty0, n_rows);
+    }
     if (f.general_compositor == 2) launch_pdl(k_composite<2>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
     else if (f.general_compositor == 1) launch_pdl(k_composite<1>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
     else launch_pdl(k_composite<0>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);

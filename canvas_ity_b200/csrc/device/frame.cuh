@@ -32,6 +32,9 @@ struct device_frame {
     stroke_src *sources;   uint32_t n_static_sources;
     job_rec *jobs;
     comp_rec *comp;                                    // per job, built by k_job_tiles
+    // per tile row of the target: the jobs (in order) whose composite box reaches that row, so the
+    // compositor scans ~1/5 of the job table on a picture like the tiger; null = scan the canvas' range
+    uint32_t *row_jobs, *row_job_count;  uint32_t row_stride;
     uint32_t *blur_units;                              // [2][n_shadow_jobs + 1] prefix of blur sweep units (x, y)
     uint2 *job_box;  uint32_t *job_te;                 // compact per-job tile box + first tile entry
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
