@@ -332,7 +332,9 @@ struct warp_scratch {
 //            (the tiger, most UI and plots) -- no gradient/pattern/mask/shadow code, no spills
 //   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
 //   kMode 2  + gradients and patterns
-template <int kMode>
+// kLists: the job search walks the tile row's job list (frames with many jobs) instead of the
+// canvas' whole job range (a handful of jobs: the plain loop is leaner).
+template <int kMode, bool kLists>
 __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 5) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
@@ -498,11 +500,12 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
     // 32 candidates per step.  Occlusion culling: a job that paints this whole tile with an opaque
     // solid colour (covered tile entry, source_over/copy, alpha 1, unclipped -- then cov = vis = 1
     // replaces the pixel exactly) voids everything collected or painted before it.
-    const uint32_t *row_list = f.row_jobs ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
-    const uint32_t n_candidates = row_list ? f.row_job_count[ty - tile_y0] : job_end - job_begin;
-    for (uint32_t base = 0; base < n_candidates; base += 32) {
+    const uint32_t *row_list = kLists ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
+    const uint32_t search_begin = kLists ? 0u : job_begin;
+    const uint32_t search_end = kLists ? f.row_job_count[ty - tile_y0] : job_end;
+    for (uint32_t base = search_begin; base < search_end; base += 32) {
         const uint32_t at = base + uint32_t(lane);
-        const uint32_t j = at < n_candidates ? (row_list ? row_list[at] : job_begin + at) : job_end;
+        const uint32_t j = kLists ? (at < search_end ? row_list[at] : job_end) : at;
         uint32_t te = 0;
         bool hit = false, cover = false;
         if (j < job_end) {
@@ -602,9 +605,16 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
         const int n_rows = ty1 - ty0 + 1;
         launch_pdl(k_row_lists, (n_rows * 32 + kBlock - 1) / kBlock, kBlock, 0, s, f, t, ty0, n_rows);
     }
-    if (f.general_compositor == 2) launch_pdl(k_composite<2>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
-    else if (f.general_compositor == 1) launch_pdl(k_composite<1>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
-    else launch_pdl(k_composite<0>, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager);
+    auto go = [&](auto kernel) { launch_pdl(kernel, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager); };
+    if (f.row_jobs) {
+        if (f.general_compositor == 2) go(k_composite<2, true>);
+        else if (f.general_compositor == 1) go(k_composite<1, true>);
+        else go(k_composite<0, true>);
+    } else {
+        if (f.general_compositor == 2) go(k_composite<2, false>);
+        else if (f.general_compositor == 1) go(k_composite<1, false>);
+        else go(k_composite<0, false>);
+    }
 }
 
 }  // namespace cb200
