@@ -331,14 +331,15 @@ struct warp_scratch {
 //   kMode 0  lean: frames that only hold unclipped solid-colour fills and strokes without shadows
 //            (the tiger, most UI and plots) -- no gradient/pattern/mask/shadow code, no spills
 //   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
-//   kMode 2  + gradients and patterns
+//   kMode 2  lean + unclipped gradient brushes with at most kStagedStops stops (full-canvas gradient fills)
+//   kMode 3  everything: masks, shadows, gradients, patterns
 // kLists: the job search walks the tile row's job list (frames with many jobs) instead of the
 // canvas' whole job range (a handful of jobs: the plain loop is leaner).
 template <int kMode, bool kLists>
-__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 5) k_composite(device_frame f, canvas_target t, int sb,
+__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5) k_composite(device_frame f, canvas_target t, int sb,
                                                           int tiles_x, int tile_y0, int eager_load)
 {
-    constexpr bool kGeneral = kMode >= 1, kPaint = kMode == 2;
+    constexpr bool kGeneral = kMode == 1 || kMode == 3, kPaint = kMode >= 2, kPattern = kMode == 3;
     grid_dependency_wait();
     __shared__ __align__(16) warp_scratch scratch[kTileWarps];
     frame_header *h = f.hdr;
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
             float *mask_out = (kGeneral && c.kind == JOB_CLIP) ? t.mask_planes[c.mask_dst] : nullptr;
             const bool gradient = brush_type == CB200_BRUSH_LINEAR || brush_type == CB200_BRUSH_RADIAL;
             bool staged = false;
-            if (kPaint && (gradient || brush_type == CB200_BRUSH_PATTERN) && c.kind == JOB_MAIN) {
+            if (kPaint && (gradient || (kPattern && brush_type == CB200_BRUSH_PATTERN)) && c.kind == JOB_MAIN) {
                 // stage the brush: record (14 words), brush-space matrix (6 words), gradient stops
                 const brush_rec *gb = &f.brushes[c.brush];
                 const uint32_t n_stops = gradient ? gb->n_colors : 0;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
             }
             const float *back_row = ws.back + warp * kWarpRows;
             const uint32_t *first_row = ws.first + warp * kWarpRows;
-            if (!kGeneral || (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR)) {
+            if ((!kGeneral && !kPaint) || (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR)) {
                 // the common case -- unclipped solid colour -- carries no per-row address arithmetic
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? 8 : kMode == 1 ? 7 : 
                     rgba paint;
                     if (brush_type == CB200_BRUSH_COLOR) paint = flat;
                     else if (brush_type == 0xffu) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
-                    else if (!kPaint) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);       // unreachable: the host picked mode 2
+                    else if (!kPattern) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);     // unreachable: the host picked mode 3
                     else if (staged && gradient) paint = paint_gradient(ws.brush, float(x) + 0.5f, float(y) + 0.5f);
                     else if (staged) paint = paint_pattern(f.texels, &ws.brush, float(x) + 0.5f, float(y) + 0.5f);
                     else paint = paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f);
@@ -607,11 +608,13 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     }
     auto go = [&](auto kernel) { launch_pdl(kernel, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager); };
     if (f.row_jobs) {
-        if (f.general_compositor == 2) go(k_composite<2, true>);
+        if (f.general_compositor == 3) go(k_composite<3, true>);
+        else if (f.general_compositor == 2) go(k_composite<2, true>);
         else if (f.general_compositor == 1) go(k_composite<1, true>);
         else go(k_composite<0, true>);
     } else {
-        if (f.general_compositor == 2) go(k_composite<2, false>);
+        if (f.general_compositor == 3) go(k_composite<3, false>);
+        else if (f.general_compositor == 2) go(k_composite<2, false>);
         else if (f.general_compositor == 1) go(k_composite<1, false>);
         else go(k_composite<0, false>);
     }

@@ -38,7 +38,7 @@ struct device_frame {
     uint32_t *blur_units;                              // [2][n_shadow_jobs + 1] prefix of blur sweep units (x, y)
     uint2 *job_box;  uint32_t *job_te;                 // compact per-job tile box + first tile entry
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
-    int general_compositor;                            // 0 lean, 1 + masks / shadows / clips, 2 + gradients / patterns
+    int general_compositor;                            // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything
     float4 *texels;
     // geometry
     uint32_t *unit_count, *unit_offset;               // n_units + 1
