@@ -105,29 +105,41 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ reference arm ----
 
+def cpu_renderer(size):
+    """(kind, frame) -- `frame()` renders one whole tiger frame on the calling CPU thread: the
+    unmodified reference from oracle/_ref when it was built (kind "reference"), else the oracle port
+    fed with the frame lowered once by the front end (kind "port").  Draw calls only, fresh canvas per
+    frame: the timed region of demos/tiger/tiger.cpp:104-4323."""
+    from tests import harness as H
+    script = H.tiger_script(size, size)
+    lib = H.reference_library(fast=True) or H.reference_library()
+    if lib is not None:
+        def frame():
+            h = lib.cv_create(size, size)
+            lib.cv_run_script(h, script, len(script), None, 0, None)
+            lib.cv_destroy(h)
+        return "reference", frame
+    orc = H.oracle_library()
+    lowered = H.lower_script(script, size, size)
+
+    def frame():
+        o = orc.oracle_canvas_create(size, size)
+        for f in lowered:
+            orc.oracle_submit(o, C.byref(f.frame))
+        orc.oracle_canvas_destroy(o)
+    return "port", frame
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU renderer on the same call stream, all host threads, bounded sample."""
     if rank != 0:
         return
-    from tests import harness as H
-    lib = H.reference_library(fast=True) or H.reference_library()
-    if lib is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
-        return
-    script = H.tiger_script(SIZE, SIZE)
+    size = args.size
+    kind, frame = cpu_renderer(size)
     threads = os.cpu_count() or 1
 
-    def frames(count, out, slot):
-        t0 = time.perf_counter()
-        for _ in range(count):
-            h = lib.cv_create(SIZE, SIZE)           # fresh canvas per frame, as tiger.cpp does
-            lib.cv_run_script(h, script, len(script), None, 0, None)
-            lib.cv_destroy(h)
-        out[slot] = time.perf_counter() - t0
-
-    def step(per_thread):
-        out = [0.0] * threads
-        ts = [threading.Thread(target=frames, args=(per_thread, out, i)) for i in range(threads)]
+    def step():
+        ts = [threading.Thread(target=frame) for _ in range(threads)]
         t0 = time.perf_counter()
         [t.start() for t in ts]
         [t.join() for t in ts]
@@ -135,42 +147,36 @@ def run_reference(args, rank, world):
 
     # one step = one frame per host thread (ctypes releases the GIL): a bounded sample of the workload
     for _ in range(min(args.warmup, 1)):
-        step(1)
+        step()
     steps = max(1, min(args.steps, 4))
-    t = sum(step(1) for _ in range(steps))
+    t = sum(step() for _ in range(steps))
     fps = steps * threads / t
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tiger_4096 (demos/tiger call stream fit to 4096x4096, source_over, no shadow)",
+            "config": {"workload": "tiger_%d (demos/tiger call stream fit to %dx%d, source_over, no shadow)" % (size, size, size),
                        "frames_per_step": threads},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": "%d steps x %d concurrent frames (one per host thread), draw calls only" % (steps, threads)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(script, budget_s=20.0):
-    """Single-thread reference frames for about `budget_s` seconds (what one frame costs the reference)."""
-    from tests import harness as H
-    lib = H.reference_library(fast=True) or H.reference_library()
-    kind = "reference"
-    if lib is None:
-        return None
+def cpu_baseline_sample(size, budget_s=20.0):
+    """Single-thread CPU frames for about `budget_s` seconds (what one frame costs the reference)."""
+    kind, frame = cpu_renderer(size)
     n, t0 = 0, time.perf_counter()
     best = 1e30
     while True:
         t1 = time.perf_counter()
-        h = lib.cv_create(SIZE, SIZE)
-        lib.cv_run_script(h, script, len(script), None, 0, None)
-        lib.cv_destroy(h)
+        frame()
         best = min(best, time.perf_counter() - t1)
         n += 1
         if time.perf_counter() - t0 > budget_s or n >= 24:
             break
     return {"value": 1.0 / best, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "%d whole 4096x4096 tiger frames on one host thread (the reference is single-threaded), best-of" % n}
+            "sample": "%d whole %dx%d tiger frames on one host thread (the reference is single-threaded), best-of" % (n, size, size)}
 
 
 # ------------------------------------------------------------------------ our arm ----
@@ -465,7 +471,7 @@ def main():
                            "note": "in_flight canvases, one host thread each, so that one canvas' D2H overlaps the others' kernels; "
                                    "serial_value = one canvas, one thread"}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(script)
+            line["cpu_baseline"] = cpu_baseline_sample(size)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
