@@ -26,11 +26,14 @@ class Frame(C.Structure):          # cb200_frame
                 ("colors", C.c_void_p), ("stops", C.c_void_p), ("n_colors", C.c_uint32),
                 ("dashes", C.c_void_p), ("n_dashes", C.c_uint32),
                 ("images", C.c_void_p), ("n_images", C.c_uint32),
-                ("texels", C.c_void_p), ("texel_bytes", C.c_uint64)]
+                ("texels", C.c_void_p), ("texel_bytes", C.c_uint64),
+                ("atlases", C.c_void_p), ("n_atlases", C.c_uint32),
+                ("glyphs", C.c_void_p), ("n_glyphs", C.c_uint32), ("n_glyph_points", C.c_uint32)]
 
 
 FRAME_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Frame))
 SIZEOF_DRAW, SIZEOF_SUBPATH, SIZEOF_BRUSH, SIZEOF_IMAGE = 140, 16, 48, 16
+SIZEOF_GLYPH_SEG, SIZEOF_GLYPH_OUTLINE, SIZEOF_GLYPH_ATLAS, SIZEOF_GLYPH_INST = 16, 24, 56, 36
 
 
 class OwnedFrame:
@@ -44,7 +47,10 @@ class OwnedFrame:
             "points": grab(f.points, f.n_points * 8), "brushes": grab(f.brushes, f.n_brushes * SIZEOF_BRUSH),
             "colors": grab(f.colors, f.n_colors * 16), "stops": grab(f.stops, f.n_colors * 4),
             "dashes": grab(f.dashes, f.n_dashes * 4), "images": grab(f.images, f.n_images * SIZEOF_IMAGE),
-            "texels": grab(f.texels, f.texel_bytes)}
+            "texels": grab(f.texels, f.texel_bytes),
+            # atlas snapshots are copied by value; the arrays they point at live as long as the process
+            "atlases": grab(f.atlases, f.n_atlases * SIZEOF_GLYPH_ATLAS),
+            "glyphs": grab(f.glyphs, f.n_glyphs * SIZEOF_GLYPH_INST)}
         self.frame = Frame()
         for name, _ in Frame._fields_:
             if name in self.parts:
@@ -53,6 +59,8 @@ class OwnedFrame:
                 setattr(self.frame, name, getattr(f, name))
         self.n_draws = f.n_draws
         self.n_points = f.n_points
+        self.n_glyphs = f.n_glyphs
+        self.n_glyph_points = f.n_glyph_points
         self.upload_bytes = sum(len(p) for p in self.parts.values())
 
 # name -> (restype, argtypes); every symbol the two headers declare
@@ -102,6 +110,7 @@ SIGNATURES = {
     "cv_is_point_in_path": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "cv_measure_text": (C.c_float, [C.c_void_p, C.c_char_p]),
     "cv_flush": (C.c_int, [C.c_void_p]),
+    "cv_set_text_instancing": (C.c_int, [C.c_void_p, C.c_int]),
     "cv_write_tga": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cv_batch_create": (C.c_void_p, [C.c_int] * 4),
     "cv_batch_canvas": (C.c_void_p, [C.c_void_p, C.c_int]),

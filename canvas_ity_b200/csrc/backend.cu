@@ -77,6 +77,11 @@ struct staged_frame {
     std::vector<uint8_t> texels_u8;
     std::vector<float *> mask_table;
     std::vector<uint2> canvas_jobs;              // per canvas: first job, job count
+    // glyph instances: expanded on the device into the point pool right after the uploaded points
+    std::vector<glyph_inst_rec> glyph_insts;
+    std::vector<cb200_glyph_atlas> atlas_views;  // distinct atlases (by id) the instances refer to
+    std::vector<atlas_dev> atlas_table;          // device arrays of each, filled by upload_frame
+    uint32_t n_glyph_points = 0;
     uint64_t n_texels = 0;
     int key_bits = 0, bits_x = 0, bits_y = 0;
     uint32_t n_dash_subpath_cap = 0;
@@ -127,6 +132,13 @@ struct cb200_canvas {
     uint32_t cap_pts = 0, cap_items = 0, cap_rows = 0, cap_runs = 0, cap_tiles = 0, cap_sources = 0,
              cap_dash_subpaths = 0;
     uint64_t cap_planes = 0;
+
+    // device mirrors of the glyph atlases seen so far (append-only, keyed by atlas id)
+    struct atlas_mirror {
+        dev_buf<cb200_glyph_outline> outlines; dev_buf<cb200_glyph_seg> segs; dev_buf<float2> points;
+        uint32_t n_outlines = 0, n_segs = 0, n_points = 0;
+    };
+    std::map<uint64_t, atlas_mirror> atlases;
 
     staged_frame staged;
     device_frame df;
@@ -198,11 +210,36 @@ int stage_frames(cb200_canvas *cv, const cb200_frame *const *frames, const uint3
         sf.draws.resize(draw_base + in->n_draws);
         sf.subpaths.resize(sub_base + in->n_subpaths);
         sf.draw_src.resize(draw_base + in->n_draws, make_uint2(0, 0));
+        // glyph instances: rebase onto the shared instance region and the batch-wide atlas list
+        const uint32_t glyph_pt_base = sf.n_glyph_points;
+        if (in->n_glyphs && (!in->glyphs || !in->atlases)) return fail(CB200_ERR_BAD_ARG, "frame.glyphs / atlases is null");
+        std::vector<uint32_t> atlas_slot(in->n_atlases);
+        for (uint32_t a = 0; a < in->n_atlases; ++a) {
+            uint32_t slot = 0;
+            while (slot < sf.atlas_views.size() && sf.atlas_views[slot].id != in->atlases[a].id) ++slot;
+            if (slot == sf.atlas_views.size()) sf.atlas_views.push_back(in->atlases[a]);
+            else if (in->atlases[a].n_outlines > sf.atlas_views[slot].n_outlines) sf.atlas_views[slot] = in->atlases[a];   // the later snapshot
+            atlas_slot[a] = slot;
+        }
+        for (uint32_t g = 0; g < in->n_glyphs; ++g) {
+            const cb200_glyph_inst &gi = in->glyphs[g];
+            if (gi.atlas >= in->n_atlases || gi.outline >= in->atlases[gi.atlas].n_outlines)
+                return fail(CB200_ERR_BAD_ARG, "glyph instance refers to an unknown outline");
+            const cb200_glyph_outline &o = in->atlases[gi.atlas].outlines[gi.outline];
+            if (uint64_t(gi.first_point) + o.out_points > in->n_glyph_points)
+                return fail(CB200_ERR_BAD_ARG, "glyph instance points out of range");
+            glyph_inst_rec r = { atlas_slot[gi.atlas], gi.outline, glyph_pt_base + gi.first_point, 0, to_affine(gi.m) };
+            sf.glyph_insts.push_back(r);
+        }
+        sf.n_glyph_points += in->n_glyph_points;
         for (uint32_t s = 0; s < in->n_subpaths; ++s) {
             const cb200_subpath &sp = in->subpaths[s];
-            if (uint64_t(sp.first_point) + 1 + 3ull * sp.n_cubics > in->n_points)
+            if (uint64_t(sp.first_point) + 1 + 3ull * sp.n_cubics > (sp.instanced ? in->n_glyph_points : in->n_points))
                 return fail(CB200_ERR_BAD_ARG, "subpath points out of range");
-            subpath_rec r = { pt_base + sp.first_point, sp.n_cubics, sp.closed, 0xffffffffu, 0 };
+            // instanced subpaths: bit 31 marks "relative to the instance region" until every frame's
+            // uploaded points are counted (fixed up below)
+            subpath_rec r = { sp.instanced ? (0x80000000u | (glyph_pt_base + sp.first_point)) : pt_base + sp.first_point,
+                              sp.n_cubics, sp.closed, 0xffffffffu, 0 };
             sf.subpaths[sub_base + s] = r;
         }
         std::map<uint32_t, uint32_t> *slots = cv->n_canvases > 1 ? &cv->batch_masks[canvas] : nullptr;
@@ -337,6 +374,12 @@ int stage_frames(cb200_canvas *cv, const cb200_frame *const *frames, const uint3
         }
     }
     if (cv->n_canvases == 1) sf.canvas_jobs[0] = make_uint2(0, uint32_t(sf.jobs.size()));
+    // the instance region follows ALL uploaded points
+    const uint32_t uploaded_points = uint32_t(sf.points.size() / 2);
+    if (uint64_t(uploaded_points) + sf.n_glyph_points >= 0x80000000ull) return fail(CB200_ERR_BAD_ARG, "too many path points");
+    for (subpath_rec &sp : sf.subpaths)
+        if (sp.first_point & 0x80000000u) sp.first_point = uploaded_points + (sp.first_point & 0x7fffffffu);
+    for (glyph_inst_rec &g : sf.glyph_insts) g.first_point += uploaded_points;
     // sort key layout: job | y | x   (y, x local to the job's canvas)
     sf.bits_x = bits_for(uint32_t(cv->width + max_pad + 1));
     sf.bits_y = bits_for(uint32_t(cv->height + max_pad + 1));
@@ -488,6 +531,45 @@ int upload_frame(cb200_canvas *cv)
         if (d.mask_src && !sf.mask_table[d.mask_src])
             return fail(CB200_ERR_BAD_ARG, "draw reads a clip-mask slot that was never written");
 
+    // glyph atlases: extend the device mirrors to cover what this frame's instances refer to
+    sf.atlas_table.assign(sf.atlas_views.size(), atlas_dev());
+    for (size_t a = 0; a < sf.atlas_views.size(); ++a) {
+        const cb200_glyph_atlas &v = sf.atlas_views[a];
+        cb200_canvas::atlas_mirror &m = cv->atlases[v.id];
+        if (v.n_outlines > m.n_outlines || v.n_segs > m.n_segs || v.n_points > m.n_points) {
+            for (uint32_t o = m.n_outlines; o < v.n_outlines; ++o) {      // new outlines: check them once
+                const cb200_glyph_outline &ol = v.outlines[o];
+                if (uint64_t(ol.first_point) + ol.n_points > v.n_points || uint64_t(ol.first_seg) + ol.n_segs > v.n_segs ||
+                    ol.out_points != ol.n_contours + 3 * ol.n_segs)
+                    return fail(CB200_ERR_BAD_ARG, "glyph outline out of range");
+                for (uint32_t k = 0; k < ol.n_segs; ++k) {
+                    const cb200_glyph_seg &sg = v.segs[ol.first_seg + k];
+                    const uint32_t top = std::max(std::max(uint32_t(sg.from_a), uint32_t(sg.from_b)),
+                                                  std::max(std::max(uint32_t(sg.to_a), uint32_t(sg.to_b)), uint32_t(sg.ctrl)));
+                    if (top >= ol.n_points || sg.out < 1 || uint64_t(sg.out) + 3 > ol.out_points)
+                        return fail(CB200_ERR_BAD_ARG, "glyph piece out of range");
+                }
+            }
+            // a buffer that has to grow is re-created (cudaFree waits for frames in flight), then refilled
+            const bool regrow = v.n_outlines > m.outlines.cap || v.n_segs > m.segs.cap || v.n_points > m.points.cap;
+            if (regrow) {
+                CK(m.outlines.reserve(std::max<size_t>(64, 2 * size_t(v.n_outlines))));
+                CK(m.segs.reserve(std::max<size_t>(1024, 2 * size_t(v.n_segs))));
+                CK(m.points.reserve(std::max<size_t>(1024, 2 * size_t(v.n_points))));
+                m.n_outlines = m.n_segs = m.n_points = 0;
+            }
+            CK(cudaMemcpyAsync(m.outlines.p + m.n_outlines, v.outlines + m.n_outlines,
+                               sizeof(cb200_glyph_outline) * (v.n_outlines - m.n_outlines), cudaMemcpyHostToDevice, cv->stream));
+            CK(cudaMemcpyAsync(m.segs.p + m.n_segs, v.segs + m.n_segs, sizeof(cb200_glyph_seg) * (v.n_segs - m.n_segs),
+                               cudaMemcpyHostToDevice, cv->stream));
+            CK(cudaMemcpyAsync(m.points.p + m.n_points, v.points + 2 * size_t(m.n_points),
+                               sizeof(float2) * (v.n_points - m.n_points), cudaMemcpyHostToDevice, cv->stream));
+            m.n_outlines = v.n_outlines; m.n_segs = v.n_segs; m.n_points = v.n_points;
+        }
+        atlas_dev d = { m.outlines.p, m.segs.p, m.points.p };
+        sf.atlas_table[a] = d;
+    }
+
     std::vector<std::pair<size_t, std::pair<const void *, size_t> > > plan;
     size_t at = 0;
     std::vector<frame_header> hdr(1);
@@ -504,7 +586,7 @@ int upload_frame(cb200_canvas *cv)
     cv->hdr_offset = place(plan, at, hdr);
     cv->hdr_pristine_offset = place(plan, at, hdr);
     size_t o_draws = place(plan, at, sf.draws), o_sub = place(plan, at, sf.subpaths);
-    size_t o_units = place(plan, at, sf.units), o_points = place(plan, at, sf.points);
+    size_t o_units = place(plan, at, sf.units);
     size_t o_brushes = place(plan, at, sf.brushes), o_colors = place(plan, at, sf.colors);
     size_t o_stops = place(plan, at, sf.stops), o_dashes = place(plan, at, sf.dashes);
     size_t o_ditems = place(plan, at, sf.dash_items), o_dsrc = place(plan, at, sf.draw_src);
@@ -512,6 +594,11 @@ int upload_frame(cb200_canvas *cv)
     size_t o_masks = place(plan, at, sf.mask_table), o_tex = place(plan, at, sf.texels_u8);
     size_t o_cjobs = place(plan, at, sf.canvas_jobs);
     size_t o_src = place(plan, at, sf.sources);
+    size_t o_ginst = place(plan, at, sf.glyph_insts), o_atlas = place(plan, at, sf.atlas_table);
+    // points go last: the glyph-instance region follows them in the device blob and is never uploaded
+    size_t o_points = place(plan, at, sf.points);
+    const size_t upload_bytes = at;
+    at = align_up(o_points + (sf.points.size() / 2 + size_t(sf.n_glyph_points)) * sizeof(float2) + 16, 256);
 
     if (at > cv->pinned_cap) {
         if (cv->pinned) cudaFreeHost(cv->pinned);
@@ -524,7 +611,7 @@ int upload_frame(cb200_canvas *cv)
     CK(cv->blob.reserve(cv->pinned_cap));
     for (auto &pl : plan)
         if (pl.second.second) memcpy(cv->pinned + pl.first, pl.second.first, pl.second.second);
-    CK(cudaMemcpyAsync(cv->blob.p, cv->pinned, at, cudaMemcpyHostToDevice, cv->stream));
+    CK(cudaMemcpyAsync(cv->blob.p, cv->pinned, upload_bytes, cudaMemcpyHostToDevice, cv->stream));
     // static stroke sources live in the growable device array K2 appends to
     if (!sf.sources.empty())
         CK(cudaMemcpyAsync(cv->sources.p, cv->blob.p + o_src, sf.sources.size() * sizeof(stroke_src),
@@ -538,6 +625,9 @@ int upload_frame(cb200_canvas *cv)
     f.subpaths = reinterpret_cast<subpath_rec *>(b + o_sub);
     f.units = reinterpret_cast<unit_rec *>(b + o_units);
     f.in_points = reinterpret_cast<float2 *>(b + o_points);
+    f.glyph_insts = reinterpret_cast<glyph_inst_rec *>(b + o_ginst);
+    f.n_glyph_insts = uint32_t(sf.glyph_insts.size());
+    f.atlas_table = reinterpret_cast<atlas_dev *>(b + o_atlas);
     f.brushes = reinterpret_cast<brush_rec *>(b + o_brushes);
     f.colors = reinterpret_cast<float4 *>(b + o_colors);
     f.stops = reinterpret_cast<float *>(b + o_stops);
@@ -624,6 +714,7 @@ int run_frame(cb200_canvas *cv)
     // with stage timing off only the frame and the compositor are bracketed.
     const bool stages = cv->stage_timing;
     CK(cudaEventRecord(cv->ev[0], s));
+    launch_glyphs(f, s);
     launch_flatten(f, uint32_t(sf.units.size()), s);
     launch_dash(f, s);
     launch_stroke(f, s);
@@ -646,7 +737,7 @@ int run_frame(cb200_canvas *cv)
     ++cv->frames_run;
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(cv->ev[6], s));
-    cv->launches += (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
+    cv->launches += (sf.glyph_insts.empty() ? 0 : 1) + (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
                     ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
                     (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
     cv->pending = true;
@@ -773,6 +864,10 @@ int cb200_struct_size(int which)
     case 2: return int(sizeof(cb200_brush));
     case 3: return int(sizeof(cb200_image));
     case 4: return int(sizeof(cb200_frame));
+    case 5: return int(sizeof(cb200_glyph_seg));
+    case 6: return int(sizeof(cb200_glyph_outline));
+    case 7: return int(sizeof(cb200_glyph_atlas));
+    case 8: return int(sizeof(cb200_glyph_inst));
     default: return -1;
     }
 }

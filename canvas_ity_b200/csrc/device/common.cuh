@@ -59,6 +59,18 @@ struct subpath_rec {
     uint32_t first_unit;
 };
 
+// One glyph of a text draw: a cached outline (atlas arrays in device memory) placed by `m`; K0
+// writes its control points to in_points[first_point ...] (include/canvas_b200.h, cb200_glyph_inst).
+struct glyph_inst_rec {
+    uint32_t atlas, outline, first_point, reserved;
+    affine m;
+};
+struct atlas_dev {
+    const cb200_glyph_outline *outlines;
+    const cb200_glyph_seg *segs;
+    const float2 *points;
+};
+
 // A flatten unit: unit 0 of a subpath re-emits its start point, unit k>0
 // flattens cubic k-1.
 struct unit_rec { uint32_t subpath, index; };

@@ -23,7 +23,9 @@ struct device_frame {
     draw_rec *draws;
     subpath_rec *subpaths;
     unit_rec *units;
-    float2 *in_points;
+    float2 *in_points;                                 // uploaded points, then the glyph-instance region
+    glyph_inst_rec *glyph_insts;  uint32_t n_glyph_insts;
+    atlas_dev *atlas_table;
     brush_rec *brushes;
     float4 *colors;  float *stops;
     float *dashes;
@@ -84,6 +86,7 @@ struct canvas_target {
 };
 
 // geometry.cu
+void launch_glyphs(const device_frame &f, cudaStream_t s);
 void launch_flatten(const device_frame &f, uint32_t n_units, cudaStream_t s);
 void launch_dash(const device_frame &f, cudaStream_t s);
 void launch_stroke(const device_frame &f, cudaStream_t s);

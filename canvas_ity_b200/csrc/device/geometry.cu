@@ -22,6 +22,42 @@ namespace {
 
 __device__ __forceinline__ vec2 ld(const float2 *p, uint32_t i) { float2 v = p[i]; return v2(v.x, v.y); }
 
+// ------------------------------------------------------------------- K0 ----
+// Glyph instances -> device-space cubics (device-side text).  One warp per instance,
+// one lane per piece of the cached outline.  Per piece this is the arithmetic of the host lowering
+// (canvas_front.cpp lower_glyph, which restates add_glyph hpp:1533-1696): transform the font-unit
+// points it refers to, take the implied midpoints, degree-elevate the quadratic -- same products
+// in the same order without FMA, so the points equal the uploaded ones bit for bit.
+__global__ void __launch_bounds__(kBlock) k_glyph_instances(device_frame f)
+{
+    grid_dependency_wait();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (kBlock / 32);
+    for (uint32_t g = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); g < f.n_glyph_insts; g += warps) {
+        const glyph_inst_rec gi = f.glyph_insts[g];
+        const atlas_dev at = f.atlas_table[gi.atlas];
+        const cb200_glyph_outline o = at.outlines[gi.outline];
+        const float2 *src = at.points + o.first_point;
+        float2 *dst = f.in_points + gi.first_point;
+        auto point = [&](uint32_t k) { const float2 u = src[k]; return apply(gi.m, v2(u.x, u.y)); };
+        auto end_point = [&](uint32_t a, uint32_t b) { return a == b ? point(a) : mix(point(a), point(b), 0.5f); };
+        for (uint32_t k = lane; k < o.n_segs; k += 32) {
+            const cb200_glyph_seg sg = at.segs[o.first_seg + k];
+            const vec2 from = end_point(sg.from_a, sg.from_b), to = end_point(sg.to_a, sg.to_b);
+            vec2 c1 = from, c2 = to;                                   // straight: (from, to, to)
+            if (!(sg.flags & CB200_SEG_LINE)) {
+                const vec2 c = point(sg.ctrl);
+                c1 = mix(from, c, 2.0f / 3.0f);
+                c2 = mix(to, c, 2.0f / 3.0f);
+            }
+            if (sg.flags & CB200_SEG_FIRST) dst[sg.out - 1] = make_float2(from.x, from.y);
+            dst[sg.out] = make_float2(c1.x, c1.y);
+            dst[sg.out + 1] = make_float2(c2.x, c2.y);
+            dst[sg.out + 2] = make_float2(to.x, to.y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------- K1 ----
 
 struct point_sink {
@@ -910,6 +946,13 @@ __global__ void __launch_bounds__(kBlock) k_stroke_finish(device_frame f)
 }
 
 }  // namespace
+
+void launch_glyphs(const device_frame &f, cudaStream_t s)
+{
+    if (!f.n_glyph_insts) return;
+    const uint32_t ctas = (f.n_glyph_insts + kBlock / 32 - 1) / (kBlock / 32);
+    launch_pdl(k_glyph_instances, std::min<uint32_t>(ctas, 8 * kSMs), kBlock, 0, s, f);
+}
 
 void launch_flatten(const device_frame &f, uint32_t n_units, cudaStream_t s)
 {

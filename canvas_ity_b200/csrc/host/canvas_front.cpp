@@ -14,7 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <map>
+#include <mutex>
 #include <stdexcept>
+#include <unordered_map>
 
 namespace canvas_ity {
 
@@ -377,10 +381,13 @@ void canvas::rectangle(float x, float y, float w, float h)
 
 // ------------------------------------------------------- frame builder ----
 
+static cb200_glyph_atlas atlas_snapshot(glyph_cache &cache);   // defined with glyph_cache below
+
 void canvas::host_state::reset_frame()
 {
     draws.clear(); subpaths.clear(); points.clear(); brushes.clear();
     colors.clear(); stops.clear(); dashes.clear(); images.clear(); texels.clear();
+    glyphs.clear(); frame_atlases.clear(); n_glyph_points = 0;
     cached_brush_serial[0] = cached_brush_serial[1] = cached_brush_serial[2] = 0;
 }
 
@@ -398,6 +405,11 @@ void canvas::host_state::flush()
     f.dashes = dashes.data();     f.n_dashes = uint32_t(dashes.size());
     f.images = images.data();     f.n_images = uint32_t(images.size());
     f.texels = texels.data();     f.texel_bytes = texels.size();
+    std::vector<cb200_glyph_atlas> atlas_views;            // snapshots: everything the queued instances refer to
+    for (size_t i = 0; i < frame_atlases.size(); ++i) atlas_views.push_back(atlas_snapshot(*frame_atlases[i]));
+    f.atlases = atlas_views.data(); f.n_atlases = uint32_t(atlas_views.size());
+    f.glyphs = glyphs.data();       f.n_glyphs = uint32_t(glyphs.size());
+    f.n_glyph_points = n_glyph_points;
     if (tap.frame)
         tap.frame(tap.user, &f);
     else if (device) {
@@ -712,6 +724,212 @@ struct ttf {
 };
 }
 
+// ---- glyph outline cache (include/canvas_b200.h, "glyph outline cache") ----------------
+//
+// One cache per distinct font (shared by content between canvases).  A glyph is parsed on first
+// use into a transform-independent outline -- the contour walk of add_glyph (hpp:1533-1696) run
+// once with SYMBOLIC points -- and appended to the atlas the back end mirrors in device memory.
+// Arrays grow by generations that are never freed, so a snapshot handed to a frame (and any deep
+// copy of that frame) stays valid while other canvases keep adding glyphs.
+template <class T>
+struct stable_array {
+    T *data = nullptr;
+    size_t size = 0, cap = 0;
+    std::vector<std::unique_ptr<T[]> > generations;
+    void push(const T &v)
+    {
+        if (size == cap) {
+            size_t grown = cap ? cap * 2 : 256;
+            std::unique_ptr<T[]> g(new T[grown]);
+            for (size_t i = 0; i < size; ++i) g[i] = data[i];
+            data = g.get();
+            cap = grown;
+            generations.push_back(std::move(g));
+        }
+        data[size++] = v;
+    }
+};
+
+struct glyph_cache {
+    struct component { int glyph; float a, b, c, d, e, f; };
+    struct contour { uint32_t out_first, n_cubics; };
+    struct entry {
+        enum kind_t { EMPTY, SIMPLE, COMPOSITE, HOST_ONLY } kind = EMPTY;
+        uint32_t outline = 0, out_points = 0;
+        std::vector<contour> contours;       // SIMPLE: one closed subpath each
+        std::vector<component> parts;        // COMPOSITE: child glyph + its 2x3 placement
+    };
+
+    std::mutex lock;
+    uint64_t id = 0;
+    std::vector<uint8_t> key;                // the font bytes (font_state::data) this cache is for
+    stable_array<cb200_glyph_outline> outlines;
+    stable_array<cb200_glyph_seg> segs;
+    stable_array<float> points;
+    std::unordered_map<int, std::unique_ptr<entry> > glyphs;   // entries are immutable once built
+
+    const entry &lookup(const font_state &f, int glyph)
+    {
+        std::lock_guard<std::mutex> hold(lock);
+        std::unique_ptr<entry> &slot = glyphs[glyph];
+        if (!slot) { slot.reset(new entry); build(f, glyph, *slot); }
+        return *slot;
+    }
+    cb200_glyph_atlas snapshot()
+    {
+        std::lock_guard<std::mutex> hold(lock);
+        cb200_glyph_atlas a;
+        memset(&a, 0, sizeof a);
+        a.id = id;
+        a.outlines = outlines.data; a.n_outlines = uint32_t(outlines.size);
+        a.segs = segs.data;         a.n_segs = uint32_t(segs.size);
+        a.points = points.data;     a.n_points = uint32_t(points.size / 2);
+        return a;
+    }
+    static std::shared_ptr<glyph_cache> for_font(const std::vector<uint8_t> &data)
+    {
+        static std::mutex registry_lock;
+        static std::multimap<uint64_t, std::shared_ptr<glyph_cache> > registry;   // kept for the life of the process
+        static std::atomic<uint64_t> next_id(1);
+        uint64_t h = 1469598103934665603ull;                                       // FNV-1a
+        for (size_t i = 0; i < data.size(); ++i) h = (h ^ data[i]) * 1099511628211ull;
+        std::lock_guard<std::mutex> hold(registry_lock);
+        auto range = registry.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it)
+            if (it->second->key == data) return it->second;
+        std::shared_ptr<glyph_cache> fresh(new glyph_cache);
+        fresh->id = next_id++;
+        fresh->key = data;
+        registry.insert(std::make_pair(h, fresh));
+        return fresh;
+    }
+
+private:
+    struct ep { uint16_t a, b; };            // P[a], or mix(P[a], P[b], 0.5) when a != b
+    void build(const font_state &f, int glyph, entry &e);
+};
+
+static cb200_glyph_atlas atlas_snapshot(glyph_cache &cache) { return cache.snapshot(); }
+
+// The contour walk of lower_glyph() below with point INDICES in place of transformed points.
+void glyph_cache::build(const font_state &f, int glyph, entry &e)
+{
+    ttf r = { f.data };
+    bool long_loca = r.u16(f.head + 50) != 0;
+    int at = f.glyf + (long_loca ? r.s32(f.loca + glyph * 4) : r.u16(f.loca + glyph * 2) * 2);
+    int stop = f.glyf + (long_loca ? r.s32(f.loca + glyph * 4 + 4)
+                                   : r.u16(f.loca + glyph * 2 + 2) * 2);
+    if (at == stop) return;                              // empty glyph (space)
+    int contours = r.s16(at);
+    if (contours < 0) {                                  // composite glyph: the parts and their placement
+        e.kind = entry::COMPOSITE;
+        at += 10;
+        for (;;) {
+            int flags = r.u16(at), part = r.u16(at + 2);
+            if (!(flags & 2)) return;                    // point matching unsupported
+            component c;
+            c.glyph = part;
+            c.e = float(flags & 1 ? r.s16(at + 4) : r.s8(at + 4));
+            c.f = float(flags & 1 ? r.s16(at + 6) : r.s8(at + 5));
+            at += flags & 1 ? 8 : 6;
+            c.a = flags & 200 ? float(r.s16(at)) / 16384.0f : 1.0f;
+            c.b = flags & 128 ? float(r.s16(at + 2)) / 16384.0f : 0.0f;
+            c.c = flags & 128 ? float(r.s16(at + 4)) / 16384.0f : 0.0f;
+            c.d = flags & 8 ? c.a : flags & 64 ? float(r.s16(at + 2)) / 16384.0f :
+                  flags & 128 ? float(r.s16(at + 6)) / 16384.0f : 1.0f;
+            at += flags & 8 ? 2 : flags & 64 ? 4 : flags & 128 ? 8 : 0;
+            e.parts.push_back(c);
+            if (!(flags & 32)) return;                   // no more components
+        }
+    }
+    int hmetrics = r.u16(f.hhea + 34);
+    int lsb = glyph < hmetrics ? r.s16(f.hmtx + glyph * 4 + 2)
+                               : r.s16(f.hmtx + hmetrics * 2 + glyph * 2);
+    int x_min = r.s16(at + 2);
+    int n_points = contours ? r.u16(at + 8 + contours * 2) + 1 : 0;
+    e.kind = entry::HOST_ONLY;                           // until the whole outline is known to be expressible
+    if (contours == 0 || n_points > 65535) return;
+    int flag_at = at + 12 + contours * 2 + r.u16(at + 10 + contours * 2);
+    int flag_bytes = 0, x_bytes = 0;
+    for (int i = 0; i < n_points;) {
+        int fl = r.u8(flag_at + flag_bytes++);
+        int rep = fl & 8 ? r.u8(flag_at + flag_bytes++) + 1 : 1;
+        x_bytes += rep * (fl & 2 ? 1 : fl & 16 ? 0 : 2);
+        i += rep;
+    }
+    int x_at = flag_at + flag_bytes, y_at = x_at + x_bytes;
+    int x = lsb - x_min, y = 0, fl = 0, rep = 0, i = 0;
+    std::vector<float> pts;
+    std::vector<cb200_glyph_seg> pieces;
+    uint32_t out = 0;                                    // next output point of the instance
+    ep start = {0, 0}, last = {0, 0};
+    bool first_piece = false;
+    auto begin = [&](ep p) { start = last = p; first_piece = true; ++out; };
+    auto piece = [&](uint16_t ctrl, ep to, bool straight) {
+        cb200_glyph_seg sg = { last.a, last.b, to.a, to.b, ctrl,
+                               uint16_t((straight ? CB200_SEG_LINE : 0) | (first_piece ? CB200_SEG_FIRST : 0)), out };
+        pieces.push_back(sg);
+        out += 3;
+        last = to;
+        first_piece = false;
+    };
+    for (int c = 0; c < contours; ++c) {
+        int first_index = i, last_index = r.u16(at + 10 + c * 2);
+        if (last_index < first_index || last_index >= n_points) return;     // malformed: host lowering keeps its behaviour
+        uint16_t begin_idx = 0, prev_idx = 0;
+        bool begin_on = false, prev_on = false, started = false;
+        contour ct = { out, 0 };
+        size_t pieces_before = pieces.size();
+        for (; i <= last_index; ++i) {
+            if (rep) --rep;
+            else {
+                fl = r.u8(flag_at++);
+                if (fl & 8) rep = r.u8(flag_at++);
+            }
+            if (fl & 2) x += r.u8(x_at) * (fl & 16 ? 1 : -1);
+            else if (!(fl & 16)) x += r.s16(x_at);
+            if (fl & 4) y += r.u8(y_at) * (fl & 32 ? 1 : -1);
+            else if (!(fl & 32)) y += r.s16(y_at);
+            x_at += fl & 2 ? 1 : fl & 16 ? 0 : 2;
+            y_at += fl & 4 ? 1 : fl & 32 ? 0 : 2;
+            pts.push_back(float(x));
+            pts.push_back(float(y));
+            uint16_t idx = uint16_t(i);
+            bool on = (fl & 1) != 0;
+            if (i == first_index) {
+                begin_idx = idx;
+                begin_on = on;
+                if (on) { ep p = { idx, idx }; begin(p); started = true; }
+            } else {
+                ep to = { on ? idx : prev_idx, idx };                // implied on-curve midpoint
+                if (!started) { begin(to); started = true; }
+                else if (prev_on && on) piece(0, to, true);
+                else if (!prev_on || on) piece(prev_idx, to, false);  // quadratic around the previous point
+            }
+            prev_idx = idx;
+            prev_on = on;
+        }
+        if (!started) { ep p = { begin_idx, begin_idx }; begin(p); }
+        if (begin_on != prev_on) piece(prev_on ? begin_idx : prev_idx, start, false);
+        else if (!begin_on && !prev_on) {
+            ep half = { begin_idx, prev_idx };
+            piece(prev_idx, half, false);
+            piece(begin_idx, start, false);
+        }
+        piece(0, start, true);                                       // explicit closing point
+        ct.n_cubics = uint32_t(pieces.size() - pieces_before);
+        e.contours.push_back(ct);
+    }
+    cb200_glyph_outline o = { uint32_t(points.size / 2), uint32_t(n_points), uint32_t(segs.size),
+                              uint32_t(pieces.size()), uint32_t(contours), out };
+    for (size_t k = 0; k < pts.size(); ++k) points.push(pts[k]);
+    for (size_t k = 0; k < pieces.size(); ++k) segs.push(pieces[k]);
+    e.outline = uint32_t(outlines.size);
+    e.out_points = out;
+    outlines.push(o);
+    e.kind = entry::SIMPLE;
+}
+
 bool canvas::set_font(unsigned char const *font, int bytes, float size)
 {
     font_state &f = self->face;
@@ -746,6 +964,7 @@ bool canvas::set_font(unsigned char const *font, int bytes, float size)
             f.data.clear();
             return false;
         }
+        f.cache = glyph_cache::for_font(f.data);
     }
     if (f.data.empty()) return false;
     ttf r = { f.data };
@@ -913,6 +1132,36 @@ static void lower_glyph(outline_builder &ob, const font_state &f, int glyph, con
     }
 }
 
+// One glyph as instance records: the cached outline(s) + this draw's matrix; the device writes the
+// control points lower_glyph() would have produced (bit for bit) into the frame's point pool.
+static void instance_glyph(canvas::host_state *s, outline_builder &ob, const font_state &f, int glyph,
+                           const affine &m)
+{
+    const glyph_cache::entry &e = f.cache->lookup(f, glyph);
+    if (e.kind == glyph_cache::entry::EMPTY) return;
+    if (e.kind == glyph_cache::entry::HOST_ONLY) { lower_glyph(ob, f, glyph, m); return; }
+    if (e.kind == glyph_cache::entry::COMPOSITE) {
+        for (size_t k = 0; k < e.parts.size(); ++k) {
+            const glyph_cache::component &p = e.parts[k];
+            affine child = { m.a * p.a + m.c * p.b, m.b * p.a + m.d * p.b,
+                             m.a * p.c + m.c * p.d, m.b * p.c + m.d * p.d,
+                             m.a * p.e + m.c * p.f + m.e, m.b * p.e + m.d * p.f + m.f };
+            instance_glyph(s, ob, f, p.glyph, child);
+        }
+        return;
+    }
+    uint32_t atlas = 0;
+    while (atlas < s->frame_atlases.size() && s->frame_atlases[atlas] != f.cache) ++atlas;
+    if (atlas == s->frame_atlases.size()) s->frame_atlases.push_back(f.cache);
+    cb200_glyph_inst gi = { atlas, e.outline, s->n_glyph_points, { m.a, m.b, m.c, m.d, m.e, m.f } };
+    s->glyphs.push_back(gi);
+    for (size_t c = 0; c < e.contours.size(); ++c) {
+        cb200_subpath sp = { gi.first_point + e.contours[c].out_first, e.contours[c].n_cubics, 1u, 1u };
+        s->subpaths.push_back(sp);
+    }
+    s->n_glyph_points += e.out_points;
+}
+
 // Text layout (hpp:1793-1846): alignment, baseline, max-width squeeze, then one
 // font-units -> device matrix per glyph.
 static void lower_text(canvas &cv, canvas::host_state *s, outline_builder &ob,
@@ -941,7 +1190,8 @@ static void lower_text(canvas &cv, canvas::host_state *s, outline_builder &ob,
         affine g = { m.a * sx + m.c * 0.0f, m.b * sx + m.d * 0.0f,
                      m.a * 0.0f + m.c * -sy, m.b * 0.0f + m.d * -sy,
                      m.a * e + m.c * py + m.e, m.b * e + m.d * py + m.f };
-        lower_glyph(ob, f, glyph, g);
+        if (s->instanced_text && f.cache) instance_glyph(s, ob, f, glyph, g);
+        else lower_glyph(ob, f, glyph, g);
         pen += advance_of(f, glyph);
     }
 }

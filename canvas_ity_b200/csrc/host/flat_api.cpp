@@ -33,13 +33,15 @@ struct owned_frame {                   // deep copy of a lowered frame (the tap'
     std::vector<cb200_draw> draws; std::vector<cb200_subpath> subpaths; std::vector<float> points;
     std::vector<cb200_brush> brushes; std::vector<float> colors, stops, dashes;
     std::vector<cb200_image> images; std::vector<uint8_t> texels;
+    std::vector<cb200_glyph_atlas> atlases; std::vector<cb200_glyph_inst> glyphs;   // atlas arrays live for the process
     cb200_frame view;
     explicit owned_frame(const cb200_frame &f)
         : draws(f.draws, f.draws + f.n_draws), subpaths(f.subpaths, f.subpaths + f.n_subpaths),
           points(f.points, f.points + 2 * size_t(f.n_points)), brushes(f.brushes, f.brushes + f.n_brushes),
           colors(f.colors, f.colors + 4 * size_t(f.n_colors)), stops(f.stops, f.stops + f.n_colors),
           dashes(f.dashes, f.dashes + f.n_dashes), images(f.images, f.images + f.n_images),
-          texels(f.texels, f.texels + f.texel_bytes)
+          texels(f.texels, f.texels + f.texel_bytes), atlases(f.atlases, f.atlases + f.n_atlases),
+          glyphs(f.glyphs, f.glyphs + f.n_glyphs)
     {
         view = f;
     }
@@ -48,6 +50,7 @@ struct owned_frame {                   // deep copy of a lowered frame (the tap'
         view.draws = draws.data(); view.subpaths = subpaths.data(); view.points = points.data();
         view.brushes = brushes.data(); view.colors = colors.data(); view.stops = stops.data();
         view.dashes = dashes.data(); view.images = images.data(); view.texels = texels.data();
+        view.atlases = atlases.data(); view.glyphs = glyphs.data();
         return &view;
     }
 };
@@ -266,6 +269,13 @@ int cv_write_tga(cv_canvas *canvas, const char *path)
     } else g_api_error = cb200_last_error();
     cb200_host_free(pixels);
     return rc;
+}
+
+int cv_set_text_instancing(cv_canvas *canvas, int on)
+{
+    if (!canvas) return CB200_ERR_BAD_ARG;
+    front(canvas)->b200()->instanced_text = on != 0;
+    return CB200_OK;
 }
 
 int cv_flush(cv_canvas *canvas)

@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -35,10 +36,13 @@ struct brush_state {
     uint64_t serial = 0;             // bumped on every mutation (frame-level dedup)
 };
 
+struct glyph_cache;                  // parsed outlines of one font (canvas_front.cpp), shared by content
+
 struct font_state {
     std::vector<uint8_t> data;       // table directory + the 8 tables we use
     int cmap = 0, glyf = 0, head = 0, hhea = 0, hmtx = 0, loca = 0, maxp = 0, os_2 = 0;
     float scale = 0;
+    std::shared_ptr<glyph_cache> cache;
 };
 
 struct path_state {
@@ -98,6 +102,10 @@ struct canvas::host_state {
     std::vector<float> colors, stops, dashes;
     std::vector<cb200_image> images;
     std::vector<uint8_t> texels;
+    std::vector<std::shared_ptr<glyph_cache> > frame_atlases;   // fonts the queued text draws refer to
+    std::vector<cb200_glyph_inst> glyphs;
+    uint32_t n_glyph_points = 0;
+    bool instanced_text = true;      // false: lower glyph outlines on the host (A/B parity tests)
     uint64_t cached_brush_serial[3] = {0, 0, 0};
     uint32_t cached_brush_index[3] = {0, 0, 0};
     size_t max_queued_draws = 1u << 16;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CB200_ABI_VERSION 1
+#define CB200_ABI_VERSION 2
 
 typedef enum cb200_status {
     CB200_OK = 0,
@@ -56,7 +56,9 @@ typedef struct cb200_subpath {
     uint32_t first_point;   /* index into cb200_frame.points (xy pairs) */
     uint32_t n_cubics;      /* subpath owns 1 + 3 * n_cubics points */
     uint32_t closed;        /* subpath_data.closed, hpp:169 */
-    uint32_t reserved;
+    uint32_t instanced;     /* 1: first_point counts from the start of the frame's glyph-instance
+                               region (the points the device expands from cb200_frame.glyphs),
+                               which follows points[n_points - 1]; 0: an uploaded point */
 } cb200_subpath;
 
 /* paint_brush (hpp:162-165) flattened.  Colours: solid = 1 premultiplied
@@ -100,6 +102,55 @@ typedef struct cb200_draw {
     uint32_t reserved;
 } cb200_draw;
 
+/* ---- glyph outline cache (device-side text; fill_text hpp:3276, stroke_text hpp:3286) ----
+ *
+ * The reference re-parses a glyph's TrueType outline on every draw (add_glyph, hpp:1533-1696,
+ * text_to_lines hpp:1793-1846).  Here the front end parses each glyph ONCE into a transform-
+ * independent outline -- font-unit points plus a list of pieces that refer to them -- which the
+ * back end keeps in device memory; a text draw then uploads one cb200_glyph_inst (outline id +
+ * 2x3 matrix) per glyph and a kernel writes its device-space cubics straight into the frame's
+ * point pool.  The arithmetic per piece is exactly what the host lowering does (same products,
+ * same order, no FMA), so an instanced glyph is bit-identical to an uploaded one.
+ *
+ * End points are symbolic pairs (a, b): the transformed outline point P[a] when a == b, else
+ * mix(P[a], P[b], 0.5), the on-curve point TrueType implies between two off-curve points.
+ * A curved piece is the quadratic (from, P[ctrl], to), degree-elevated to the cubic
+ * (mix(from, C, 2/3), mix(to, C, 2/3), to); a straight piece is the cubic (from, to, to). */
+enum { CB200_SEG_LINE = 1,     /* straight piece; ctrl unused */
+       CB200_SEG_FIRST = 2 };  /* first piece of a contour: `from` is also stored at out - 1 */
+typedef struct cb200_glyph_seg {
+    uint16_t from_a, from_b;
+    uint16_t to_a, to_b;
+    uint16_t ctrl;
+    uint16_t flags;
+    uint32_t out;           /* the piece's three control points land at out, out + 1, out + 2,
+                               counted from the instance's first point */
+} cb200_glyph_seg;
+
+typedef struct cb200_glyph_outline {
+    uint32_t first_point, n_points;   /* into cb200_glyph_atlas.points */
+    uint32_t first_seg, n_segs;       /* into cb200_glyph_atlas.segs, contour by contour */
+    uint32_t n_contours;              /* an instance is n_contours closed subpaths ... */
+    uint32_t out_points;              /* ... of out_points points in all (n_contours + 3 * n_segs) */
+} cb200_glyph_outline;
+
+/* All outlines cached for one font so far.  Append-only: entries never change once published and
+ * ids are never reused, so a device copy is extended, never invalidated; the arrays a snapshot
+ * points at stay valid for the life of the process. */
+typedef struct cb200_glyph_atlas {
+    uint64_t id;
+    const cb200_glyph_outline *outlines;  uint32_t n_outlines;
+    const cb200_glyph_seg     *segs;      uint32_t n_segs;
+    const float               *points;    uint32_t n_points;   /* xy pairs, font units */
+} cb200_glyph_atlas;
+
+typedef struct cb200_glyph_inst {
+    uint32_t atlas;         /* index into cb200_frame.atlases */
+    uint32_t outline;
+    uint32_t first_point;   /* first output point, counted from the start of the instance region */
+    float    m[6];          /* font units -> device space (affine_matrix a..f) */
+} cb200_glyph_inst;
+
 typedef struct cb200_frame {
     const cb200_draw    *draws;     uint32_t n_draws;
     const cb200_subpath *subpaths;  uint32_t n_subpaths;
@@ -110,6 +161,11 @@ typedef struct cb200_frame {
     const float         *dashes;    uint32_t n_dashes;
     const cb200_image   *images;    uint32_t n_images;
     const uint8_t       *texels;    uint64_t texel_bytes;
+    /* glyph instances (may all be zero): expanded on the device into n_glyph_points points that
+     * instanced subpaths refer to */
+    const cb200_glyph_atlas *atlases;  uint32_t n_atlases;
+    const cb200_glyph_inst  *glyphs;   uint32_t n_glyphs;
+    uint32_t n_glyph_points;
 } cb200_frame;
 
 /* ---- canvases --------------------------------------------------------------- */
@@ -225,7 +281,8 @@ int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative
 
 const char *cb200_last_error(void);
 int cb200_abi_version(void);
-/* sizeof of the ABI records, for bindings that mirror them: 0 draw, 1 subpath, 2 brush, 3 image, 4 frame */
+/* sizeof of the ABI records, for bindings that mirror them: 0 draw, 1 subpath, 2 brush, 3 image, 4 frame,
+ * 5 glyph_seg, 6 glyph_outline, 7 glyph_atlas, 8 glyph_inst */
 int cb200_struct_size(int which);
 int cb200_device_count(void);
 

@@ -72,6 +72,13 @@ int cv_batch_read_f32(cv_batch *batch, int index, float *dst);
 cb200_canvas *cv_batch_device(cv_batch *batch);
 void cv_batch_destroy(cv_batch *batch);
 
+/* Text draws normally upload one glyph instance (cached outline id + matrix) per glyph and the
+ * device expands it (cb200_glyph_inst); on = 0 makes the front end lower glyph outlines to path
+ * points on the host instead, as the reference does per draw (hpp:1533-1696).  Both give the same
+ * pixels bit for bit -- the switch exists for the A/B parity tests and for measuring the difference.
+ * No-op on the reference build. */
+int cv_set_text_instancing(cv_canvas *canvas, int on);
+
 /* Flush queued draws (no-op on the reference build). */
 int cv_flush(cv_canvas *canvas);
 /* Linear premultiplied float framebuffer, rows * width * 4 floats. */

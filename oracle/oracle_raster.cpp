@@ -793,10 +793,58 @@ void *oracle_canvas_create(int width, int height)
 
 void oracle_canvas_destroy(void *canvas) { delete static_cast<Canvas *>(canvas); }
 
+// Glyph instances (cb200_glyph_inst): what the reference's add_glyph (hpp:1533-1696) emits for
+// one glyph under the matrix of text_to_lines (hpp:1793-1846), from the parsed outline: on-curve
+// points as they are, the implied midpoint between two off-curve points, quadratic pieces around
+// an off-curve point (kept as degree-elevated cubics for flatten()), straight pieces as (from, to, to).
+static void expand_glyphs(const cb200_frame *f, std::vector<float> &pts)
+{
+    pts.assign(f->points, f->points + 2 * size_t(f->n_points));
+    pts.resize(2 * (size_t(f->n_points) + f->n_glyph_points), 0.0f);
+    float *region = pts.data() + 2 * size_t(f->n_points);
+    for (uint32_t g = 0; g < f->n_glyphs; ++g) {
+        const cb200_glyph_inst &gi = f->glyphs[g];
+        const cb200_glyph_atlas &at = f->atlases[gi.atlas];
+        const cb200_glyph_outline &o = at.outlines[gi.outline];
+        const M m = mat(gi.m);
+        float *dst = region + 2 * size_t(gi.first_point);
+        auto point = [&](uint32_t k) { const float *u = at.points + 2 * size_t(o.first_point + k); return xf(m, mk(u[0], u[1])); };
+        auto end_point = [&](uint32_t a, uint32_t b) { return a == b ? point(a) : between(point(a), point(b), 0.5f); };
+        auto put = [&](uint32_t slot, P p) { dst[2 * size_t(slot)] = p.x; dst[2 * size_t(slot) + 1] = p.y; };
+        for (uint32_t k = 0; k < o.n_segs; ++k) {
+            const cb200_glyph_seg &sg = at.segs[o.first_seg + k];
+            P from = end_point(sg.from_a, sg.from_b), to = end_point(sg.to_a, sg.to_b);
+            P c1 = from, c2 = to;
+            if (!(sg.flags & CB200_SEG_LINE)) {
+                P c = point(sg.ctrl);
+                c1 = between(from, c, 2.0f / 3.0f);
+                c2 = between(to, c, 2.0f / 3.0f);
+            }
+            if (sg.flags & CB200_SEG_FIRST) put(sg.out - 1, from);
+            put(sg.out, c1);
+            put(sg.out + 1, c2);
+            put(sg.out + 2, to);
+        }
+    }
+}
+
 void oracle_submit(void *canvas, const cb200_frame *frame)
 {
     Canvas &cv = *static_cast<Canvas *>(canvas);
-    for (uint32_t i = 0; i < frame->n_draws; ++i) run_draw(cv, frame, frame->draws[i]);
+    cb200_frame local = *frame;
+    std::vector<float> pts;
+    std::vector<cb200_subpath> subs;
+    if (frame->n_glyphs) {                       // text drawn as glyph instances: expand them first
+        expand_glyphs(frame, pts);
+        subs.assign(frame->subpaths, frame->subpaths + frame->n_subpaths);
+        for (size_t i = 0; i < subs.size(); ++i)
+            if (subs[i].instanced) { subs[i].first_point += frame->n_points; subs[i].instanced = 0; }
+        local.points = pts.data();
+        local.n_points = frame->n_points + frame->n_glyph_points;
+        local.subpaths = subs.data();
+        local.n_glyphs = 0;
+    }
+    for (uint32_t i = 0; i < local.n_draws; ++i) run_draw(cv, &local, local.draws[i]);
 }
 
 // get_image_data, hpp:3348-3381.

@@ -85,6 +85,7 @@ int cv_write_tga(cv_canvas *c, const char *path)
     fclose(f);
     return 0;
 }
+int cv_set_text_instancing(cv_canvas *, int) { return 0; }
 int cv_flush(cv_canvas *) { return 0; }
 // batches are a back-end concept: the reference renders canvases one by one
 cv_batch *cv_batch_create(int, int, int, int) { return nullptr; }

@@ -126,12 +126,14 @@ def _run(lib, handle, script):
     return [tuple(q[i * 4:i * 4 + 3]) for i in range(min(nq.value, 8192))]
 
 
-def render_script(lib, script, width, height, want_f32=True):
+def render_script(lib, script, width, height, want_f32=True, instanced_text=True):
     """Replay `script` through a flat-API library (product or reference)."""
     h = lib.cv_create(width, height)
     if not h:
         raise RuntimeError(lib.cv_last_error().decode())
     try:
+        if not instanced_text:
+            lib.cv_set_text_instancing(h, 0)
         queries = _run(lib, h, script)
         out = {"queries": queries}
         img = np.zeros((height, width, 4), np.uint8)
@@ -148,7 +150,7 @@ def render_script(lib, script, width, height, want_f32=True):
         lib.cv_destroy(h)
 
 
-def render_oracle(script, width, height):
+def render_oracle(script, width, height, instanced_text=True):
     """Front-end lowering (product library, no device touched) -> oracle."""
     prod, orc = product_library(), oracle_library()
     o = orc.oracle_canvas_create(width, height)
@@ -156,6 +158,8 @@ def render_oracle(script, width, height):
     h = prod.cv_create_tapped(width, height, addr(orc.oracle_tap_frame), addr(orc.oracle_tap_read),
                               addr(orc.oracle_tap_write), o)
     try:
+        if not instanced_text:
+            prod.cv_set_text_instancing(h, 0)
         queries = _run(prod, h, script)
         prod.cv_flush(h)
         f = np.zeros((height, width, 4), np.float32)
@@ -168,7 +172,7 @@ def render_oracle(script, width, height):
         orc.oracle_canvas_destroy(o)
 
 
-def lower_script(script, width, height):
+def lower_script(script, width, height, instanced_text=True):
     """Run `script` through the front end only and return the lowered frames it would submit
     (deep copies), plus the upload size.  No device is touched."""
     prod = product_library()
@@ -180,6 +184,8 @@ def lower_script(script, width, height):
 
     h = prod.cv_create_tapped(width, height, C.cast(on_frame, C.c_void_p), None, None, None)
     try:
+        if not instanced_text:
+            prod.cv_set_text_instancing(h, 0)
         _run(prod, h, script)
         prod.cv_flush(h)
     finally:

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(header):
 
 def test_abi_version_and_backend_name():
     lib = _native.load()
-    assert lib.cb200_abi_version() == 1
+    assert lib.cb200_abi_version() == 2
     assert lib.cv_backend_name() == b"b200"
 
 
@@ -83,6 +83,10 @@ def test_record_sizes_match_the_python_mirror():
     assert lib.cb200_struct_size(2) == _native.SIZEOF_BRUSH
     assert lib.cb200_struct_size(3) == _native.SIZEOF_IMAGE
     assert lib.cb200_struct_size(4) == C.sizeof(_native.Frame)
+    assert lib.cb200_struct_size(5) == _native.SIZEOF_GLYPH_SEG
+    assert lib.cb200_struct_size(6) == _native.SIZEOF_GLYPH_OUTLINE
+    assert lib.cb200_struct_size(7) == _native.SIZEOF_GLYPH_ATLAS
+    assert lib.cb200_struct_size(8) == _native.SIZEOF_GLYPH_INST
 
 
 def test_lowering_of_the_tiger_is_one_frame_of_305_draws():
