@@ -85,6 +85,7 @@ SIGNATURES = {
     "cb200_read_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cb200_clear": (C.c_int, [C.c_void_p]),
     "cb200_masks_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cb200_hit_test": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)]),
     "cb200_read_bgra8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb200_framebuffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cb200_read_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -109,6 +110,8 @@ SIGNATURES = {
     "cv_put_image_data": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
     "cv_is_point_in_path": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "cv_measure_text": (C.c_float, [C.c_void_p, C.c_char_p]),
+    "cv_points_in_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cv_path_edges": (C.c_long, [C.c_void_p, C.c_void_p, C.c_long]),
     "cv_flush": (C.c_int, [C.c_void_p]),
     "cv_set_text_instancing": (C.c_int, [C.c_void_p, C.c_int]),
     "cv_write_tga": (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -133,6 +133,8 @@ struct cb200_canvas {
              cap_dash_subpaths = 0;
     uint64_t cap_planes = 0;
 
+    // bulk hit testing (cb200_hit_test)
+    dev_buf<float4> hit_edges;  dev_buf<float2> hit_queries;  dev_buf<int2> hit_acc;  dev_buf<uint8_t> hit_inside;
     // device mirrors of the glyph atlases seen so far (append-only, keyed by atlas id)
     struct atlas_mirror {
         dev_buf<cb200_glyph_outline> outlines; dev_buf<cb200_glyph_seg> segs; dev_buf<float2> points;
@@ -1010,6 +1012,8 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
+    cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();
+    for (auto &kv : cv->atlases) { kv.second.outlines.release(); kv.second.segs.release(); kv.second.points.release(); }
     for (int i = 0; i < 10; ++i)
         if (cv->ev[i]) cudaEventDestroy(cv->ev[i]);
     for (cudaEvent_t e : cv->comp_ev) if (e) cudaEventDestroy(e);
@@ -1298,6 +1302,36 @@ int cb200_read_mask(cb200_canvas *cv, uint32_t slot, float *dst)
     if (!cv->masks.count(slot)) return fail(CB200_ERR_BAD_ARG, "no such mask slot");
     CK(cudaMemcpyAsync(dst, cv->masks[slot], sizeof(float) * n, cudaMemcpyDeviceToHost, cv->stream));
     CK(cudaStreamSynchronize(cv->stream));
+    return CB200_OK;
+}
+
+int cb200_hit_test(cb200_canvas *cv, const float *edges, uint32_t n_edges, const float *queries,
+                   uint32_t n_queries, uint8_t *inside, float *kernel_ms)
+{
+    if (!cv || (n_edges && !edges) || (n_queries && (!queries || !inside))) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    if (kernel_ms) *kernel_ms = 0.0f;
+    if (!n_queries) return CB200_OK;
+    CK(cv->hit_edges.reserve(std::max<size_t>(n_edges, 1)));
+    CK(cv->hit_queries.reserve(n_queries));
+    CK(cv->hit_acc.reserve(n_queries));
+    CK(cv->hit_inside.reserve(n_queries));
+    cudaStream_t s = cv->stream;
+    if (n_edges) CK(cudaMemcpyAsync(cv->hit_edges.p, edges, sizeof(float4) * size_t(n_edges), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(cv->hit_queries.p, queries, sizeof(float2) * size_t(n_queries), cudaMemcpyHostToDevice, s));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (kernel_ms) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, s)); }
+    launch_hit_test(cv->hit_edges.p, n_edges, cv->hit_queries.p, n_queries, cv->hit_acc.p, cv->hit_inside.p, s);
+    cv->launches += 2;
+    if (kernel_ms) CK(cudaEventRecord(t1, s));
+    CK(cudaMemcpyAsync(inside, cv->hit_inside.p, n_queries, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (kernel_ms) {
+        CK(cudaEventElapsedTime(kernel_ms, t0, t1));
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+    }
     return CB200_OK;
 }
 

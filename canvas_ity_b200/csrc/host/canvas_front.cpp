@@ -675,11 +675,12 @@ void canvas::draw_image(unsigned char const *image, int width, int height, int s
     self->inverse = keep_i;
 }
 
-bool canvas::is_point_in_path(float x, float y)
+// The current path flattened for hit testing (path_to_lines( false ), hpp:3105 / 1495-1524) as
+// edges (from, to), every subpath's closing edge included -- with the same routine the device's
+// K1 uses (geom.cuh), in the reference's point order.
+void flattened_path_edges(const canvas::host_state *self, std::vector<float> &edges)
 {
-    // Synchronous query: flatten on the host with the same routine the device
-    // uses (geom.cuh) and count signed crossings (hpp:3101-3132).
-    int winding = 0;
+    edges.clear();
     size_t at = 0;
     std::vector<vec2> poly;
     for (size_t i = 0; i < self->path.subs.size(); ++i) {
@@ -695,14 +696,27 @@ bool canvas::is_point_in_path(float x, float y)
         at += sub.count;
         for (size_t k = 0; k < poly.size(); ++k) {
             vec2 a = poly[k], b = poly[k + 1 < poly.size() ? k + 1 : 0];
-            if ((a.y < y && y <= b.y) || (b.y < y && y <= a.y)) {
-                float side = dot(perp(b - a), v2(x, y) - a);
-                if (side == 0.0f) return true;           // on an edge
-                winding += side > 0.0f ? 1 : -1;
-            } else if (a.y == y && y == b.y &&
-                       ((a.x <= x && x <= b.x) || (b.x <= x && x <= a.x)))
-                return true;                             // on a horizontal edge
+            edges.push_back(a.x); edges.push_back(a.y); edges.push_back(b.x); edges.push_back(b.y);
         }
+    }
+}
+
+bool canvas::is_point_in_path(float x, float y)
+{
+    // Synchronous single-point query: count signed crossings on the host (hpp:3101-3132).  Many
+    // points at once go to the device instead (cv_points_in_path / cb200_hit_test).
+    std::vector<float> edges;
+    flattened_path_edges(self, edges);
+    int winding = 0;
+    for (size_t k = 0; k < edges.size(); k += 4) {
+        vec2 a = v2(edges[k], edges[k + 1]), b = v2(edges[k + 2], edges[k + 3]);
+        if ((a.y < y && y <= b.y) || (b.y < y && y <= a.y)) {
+            float side = dot(perp(b - a), v2(x, y) - a);
+            if (side == 0.0f) return true;               // on an edge
+            winding += side > 0.0f ? 1 : -1;
+        } else if (a.y == y && y == b.y &&
+                   ((a.x <= x && x <= b.x) || (b.x <= x && x <= a.x)))
+            return true;                                 // on a horizontal edge
     }
     return winding != 0;
 }

@@ -6,6 +6,8 @@
 #include "../../../include/canvas_b200_api.h"
 
 #include <cstdio>
+#include <cstring>
+#include <algorithm>
 #include <new>
 #include <vector>
 #include <stdexcept>
@@ -242,6 +244,28 @@ int cv_is_point_in_path(cv_canvas *canvas, float x, float y)
 float cv_measure_text(cv_canvas *canvas, const char *text)
 {
     return canvas ? front(canvas)->measure_text(text) : 0.0f;
+}
+
+int cv_points_in_path(cv_canvas *canvas, const float *xy, int n, uint8_t *inside)
+{
+    if (!canvas || n < 0 || (n && (!xy || !inside))) return CB200_ERR_BAD_ARG;
+    canvas_ity::canvas::host_state *s = front(canvas)->b200();
+    if (!s->device) { g_api_error = "cv_points_in_path: tapped canvas has no device"; return CB200_ERR_NO_DEVICE; }
+    std::vector<float> edges;
+    canvas_ity::flattened_path_edges(s, edges);
+    int rc = cb200_hit_test(s->device, edges.data(), uint32_t(edges.size() / 4), xy, uint32_t(n), inside, nullptr);
+    if (rc != CB200_OK) g_api_error = cb200_last_error();
+    return rc;
+}
+
+long cv_path_edges(cv_canvas *canvas, float *edges, long capacity)
+{
+    if (!canvas) return -1;
+    std::vector<float> all;
+    canvas_ity::flattened_path_edges(front(canvas)->b200(), all);
+    long n = long(all.size() / 4);
+    if (edges && capacity > 0) memcpy(edges, all.data(), sizeof(float) * 4 * size_t(std::min(n, capacity)));
+    return n;
 }
 
 int cv_write_tga(cv_canvas *canvas, const char *path)

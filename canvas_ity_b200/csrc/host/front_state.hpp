@@ -119,6 +119,7 @@ struct canvas::host_state {
 };
 
 // Host helpers shared with the bindings.
+void flattened_path_edges(const canvas::host_state *self, std::vector<float> &edges);
 color4 srgb_to_premultiplied_linear(float r, float g, float b, float a);
 
 }  // namespace canvas_ity

@@ -248,6 +248,17 @@ int cb200_read_rgba8_device(cb200_canvas *canvas, void **device_ptr);
  * with cb200_sync() before handing the buffer to another stream. */
 int cb200_read_rgba8_into(cb200_canvas *canvas, void *device_dst, int width, int height, int x, int y);
 
+/* Bulk is_point_in_path (hpp:3101-3132): the reference answers one point per call by walking every
+ * edge of the flattened path; this tests n_queries points against the same edges in one launch.
+ * `edges`: n_edges x (from.x, from.y, to.x, to.y) in device space -- the flattened current path
+ * (path_to_lines, hpp:1495-1524) with every subpath's closing edge included, which is what the
+ * front end's cv_path_edges() returns.  `queries`: n_queries xy pairs (device space, like the
+ * reference's arguments).  inside[i] = 1 when point i is inside under the non-zero winding rule or
+ * exactly on an edge, else 0 -- the reference's bool.  `kernel_ms` (optional) receives the CUDA-event
+ * time of the kernels alone.  Synchronous (it returns the answer), like the call it replaces. */
+int cb200_hit_test(cb200_canvas *canvas, const float *edges, uint32_t n_edges, const float *queries,
+                   uint32_t n_queries, uint8_t *inside, float *kernel_ms);
+
 /* ---- introspection / measurement ------------------------------------------- */
 
 typedef struct cb200_stats {

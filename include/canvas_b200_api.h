@@ -53,6 +53,16 @@ int   cv_put_image_data(cv_canvas *canvas, const uint8_t *image, int width, int 
 int   cv_is_point_in_path(cv_canvas *canvas, float x, float y);    /* :843 */
 float cv_measure_text(cv_canvas *canvas, const char *text);        /* :1025 */
 
+/* Bulk hit testing: is_point_in_path (:843, hpp:3101-3132) for n points at once against the canvas'
+ * current path.  xy: n device-space pairs; inside[i] = the reference's bool for point i.  On the
+ * B200 build this is one cb200_hit_test launch (a tapped canvas has no device: CB200_ERR_NO_DEVICE,
+ * there is no CPU path); on the reference build it is the reference's own loop, n calls. */
+int cv_points_in_path(cv_canvas *canvas, const float *xy, int n, uint8_t *inside);
+/* The flattened current path as edges (from.x, from.y, to.x, to.y), closing edges included --
+ * what cv_points_in_path hands to cb200_hit_test.  Copies at most `capacity` edges, returns the
+ * edge count.  B200 build only (returns -1 on the reference build). */
+long cv_path_edges(cv_canvas *canvas, float *edges, long capacity);
+
 /* The file demos/tiger/tiger.cpp:4333-4345 writes after get_image_data: an uncompressed 32-bit TGA
  * (18-byte header, top-down rows, BGRA).  Here the channel swap happens in the readback kernel
  * (cb200_read_bgra8) and the rows go from the pinned staging buffer to the file. */

@@ -935,6 +935,27 @@ long oracle_debug_edges(const cb200_frame *frame, uint32_t draw_index, float *ed
 }
 
 // Function-pointer friendly taps for cv_create_tapped (user = oracle canvas).
+// is_point_in_path, hpp:3101-3132, over the already flattened path: edges are (from, to) pairs with
+// every subpath's closing edge included (the reference closes them with `beginning`, hpp:3118).
+void oracle_points_in_path(const float *edges, uint32_t n_edges, const float *xy, uint32_t n, uint8_t *inside)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const float x = xy[2 * i], y = xy[2 * i + 1];
+        int winding = 0;
+        bool on_edge = false;
+        for (uint32_t k = 0; k < n_edges && !on_edge; ++k) {
+            P from = mk(edges[4 * k], edges[4 * k + 1]), to = mk(edges[4 * k + 2], edges[4 * k + 3]);
+            if ((from.y < y && y <= to.y) || (to.y < y && y <= from.y)) {
+                float side = dotp(rot90(sub(to, from)), sub(mk(x, y), from));
+                if (side == 0.0f) on_edge = true;
+                else winding += side > 0.0f ? 1 : -1;
+            } else if (from.y == y && y == to.y && ((from.x <= x && x <= to.x) || (to.x <= x && x <= from.x)))
+                on_edge = true;
+        }
+        inside[i] = (on_edge || winding != 0) ? 1 : 0;
+    }
+}
+
 void oracle_tap_frame(void *user, const cb200_frame *frame) { oracle_submit(user, frame); }
 void oracle_tap_read(void *user, uint8_t *dst, int w, int h, int stride, int x, int y)
 {

@@ -68,6 +68,13 @@ int cv_put_image_data(cv_canvas *c, const uint8_t *image, int w, int h, int stri
 }
 int cv_is_point_in_path(cv_canvas *c, float x, float y) { return ref(c)->is_point_in_path(x, y); }
 float cv_measure_text(cv_canvas *c, const char *text) { return ref(c)->measure_text(text); }
+// the reference has no bulk query: n calls of its own is_point_in_path (hpp:3101-3132)
+int cv_points_in_path(cv_canvas *c, const float *xy, int n, uint8_t *inside)
+{
+    for (int i = 0; i < n; ++i) inside[i] = ref(c)->is_point_in_path(xy[2 * i], xy[2 * i + 1]) ? 1 : 0;
+    return 0;
+}
+long cv_path_edges(cv_canvas *, float *, long) { return -1; }
 // what demos/tiger/tiger.cpp:4333-4345 does after rendering: get_image_data, swap R and B on the CPU, write
 int cv_write_tga(cv_canvas *c, const char *path)
 {

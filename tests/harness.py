@@ -51,6 +51,7 @@ def oracle_library():
         lib.oracle_read_rgba8.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5
         lib.oracle_write_rgba8.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5
         lib.oracle_read_mask.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.oracle_points_in_path.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.oracle_debug_edges.restype = C.c_long
         lib.oracle_debug_edges.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_long]
         _oracle = lib
@@ -191,6 +192,16 @@ def lower_script(script, width, height, instanced_text=True):
     finally:
         prod.cv_destroy(h)
     return frames
+
+
+@_native.FRAME_FN
+def _discard_frame(user, frame):
+    pass
+
+
+def host_only_canvas(width, height):
+    """A front-end canvas without a device (frames are dropped): path building and host queries only."""
+    return product_library().cv_create_tapped(width, height, C.cast(_discard_frame, C.c_void_p), None, None, None)
 
 
 # ------------------------------------------------------------------ comparison ----
