@@ -341,6 +341,30 @@ def main():
             "coverage": {"kernels": "k_rows/k_rows_long/k_tile_flags", "runs": runs, "ms": float(np.median(stage["coverage"])),
                          "gruns_per_s": runs / float(np.median(stage["coverage"])) / 1e6},
         }
+        # the rows SURVEY 8f marks "next": the PNG the reference's driver writes, encoded on the device from
+        # the same framebuffer (20 B per pixel like the readback), and bulk is_point_in_path
+        png_size = C.c_size_t(0)
+        check(lib.cb200_encode_png(cv, None, 0, C.byref(png_size)))
+        png_buf = lib.cb200_host_alloc(png_size.value)
+        png = []
+        for _ in range(5):
+            check(lib.cb200_encode_png(cv, png_buf, png_size.value, None))
+            check(lib.cb200_get_stats(cv, C.byref(stats)))
+            png.append(stats.png_ms)
+        lib.cb200_host_free(png_buf)
+        png_ms = float(np.median(png[1:]))
+        passes["png_encode"] = {"kernels": "k_png_rows + k_png_finish", "ms": png_ms, "bytes_per_pixel": 20, "file_bytes": png_size.value,
+                                "achieved_gbs": 20.0 * size * size / png_ms / 1e6, "frac_of_hbm_peak": 20.0 * size * size / png_ms / 1e6 / peak_gbs}
+        from tests.test_hit_testing import scene as hit_scene, _edges as hit_edges
+        edges = hit_edges(lib, hit_scene("long_path"))
+        pts = np.ascontiguousarray(np.random.default_rng(3).random((1 << 20, 2), dtype=np.float32) * np.float32(256.0))
+        inside = np.zeros(len(pts), np.uint8)
+        hit_ms, hit = C.c_float(0), []
+        for _ in range(4):
+            check(lib.cb200_hit_test(cv, edges.ctypes.data, len(edges), pts.ctypes.data, len(pts), inside.ctypes.data, C.byref(hit_ms)))
+            hit.append(hit_ms.value)
+        passes["hit_test"] = {"kernels": "k_hit_test + k_hit_resolve", "points": len(pts), "edges": len(edges), "ms": float(np.median(hit[1:])),
+                              "rule_evaluations_per_s": len(pts) * len(edges) / (float(np.median(hit[1:])) * 1e-3)}
         # config 3 of BASELINE.json on the same canvas: global_alpha 0.9, shadow_blur 16, shadow alpha 0.5
         shadow_script = H.tiger_script(size, size, global_alpha=0.9, shadow_blur=16.0, shadow_color=(0, 0, 0, 0.5))
         shadow_frame = H.lower_script(shadow_script, size, size)[0]

@@ -15,7 +15,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("draws", "cubics", "line_points", "edges", "raw_runs", "tile_entries",
                                            "composited_pixels", "shadow_pixels", "kernel_launches")] + \
                [(n, C.c_float) for n in ("last_frame_ms", "composite_ms", "raster_ms", "sort_ms", "geometry_ms",
-                                         "readback_ms", "coverage_ms", "shadow_raster_ms", "blur_ms")]
+                                         "readback_ms", "coverage_ms", "shadow_raster_ms", "blur_ms", "png_ms")]
 
 
 class Frame(C.Structure):          # cb200_frame
@@ -89,6 +89,7 @@ SIGNATURES = {
     "cb200_read_bgra8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb200_framebuffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cb200_read_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cb200_encode_png": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "cb200_read_rgba8_into": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4),
     "cb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cb200_debug_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
@@ -115,6 +116,7 @@ SIGNATURES = {
     "cv_flush": (C.c_int, [C.c_void_p]),
     "cv_set_text_instancing": (C.c_int, [C.c_void_p, C.c_int]),
     "cv_write_tga": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cv_write_png": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cv_batch_create": (C.c_void_p, [C.c_int] * 4),
     "cv_batch_canvas": (C.c_void_p, [C.c_void_p, C.c_int]),
     "cv_batch_flush": (C.c_int, [C.c_void_p]),

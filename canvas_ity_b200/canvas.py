@@ -172,7 +172,23 @@ class Canvas:
         self.flush()
         return bool(self._lib.cv_is_point_in_path(self._h, x, y))
 
+    def points_in_path(self, xy):
+        """is_point_in_path (hpp:3101-3132) for many device-space points at once: `xy` is (n, 2) float32,
+        the result (n,) bool -- one device launch (cb200_hit_test) instead of n host walks of the path."""
+        import numpy as np
+        self.flush()
+        q = np.ascontiguousarray(np.asarray(xy, np.float32).reshape(-1, 2))
+        inside = np.zeros(len(q), np.uint8)
+        if self._lib.cv_points_in_path(self._h, q.ctypes.data, len(q), inside.ctypes.data) != 0:
+            raise RuntimeError(self._lib.cv_last_error().decode())
+        return inside.astype(bool)
+
     # -- text --
+    def set_text_instancing(self, on):
+        """Text draws upload glyph instances expanded on the device (default) or host-lowered outlines."""
+        self.flush()
+        self._lib.cv_set_text_instancing(self._h, 1 if on else 0)
+
     def set_font(self, font, size):
         if font is None or len(font) == 0:
             self._w.floats("SET_FONT_RESIZE", size)
@@ -246,6 +262,13 @@ class Canvas:
         with the channel swap done by the readback kernel."""
         self.flush()
         if self._lib.cv_write_tga(self._h, str(path).encode()) != 0:
+            raise RuntimeError(self._lib.cv_last_error().decode())
+
+    def write_png(self, path):
+        """The PNG the reference's test driver writes (write_png, test/test.cpp:2415-2507); pixels, framing and
+        both checksums come off the device in one kernel (cb200_encode_png)."""
+        self.flush()
+        if self._lib.cv_write_png(self._h, str(path).encode()) != 0:
             raise RuntimeError(self._lib.cv_last_error().decode())
 
     def put_image_data(self, image, width, height, stride, x, y):

@@ -110,6 +110,12 @@ void launch_upload(float4 *fb, int width, int band_y0, int band_rows, const uint
                    int src_h, int x, int y, cudaStream_t s);
 void launch_texel_convert(const uint8_t *src, float4 *dst, uint64_t n_texels, cudaStream_t s);
 void launch_fill_f32(float *dst, float value, uint64_t n, cudaStream_t s);
+// PNG encode (the reference driver's write_png, test/test.cpp:2415-2507) straight from the float framebuffer
+struct png_sums { unsigned long long a, b; uint32_t crc, pad; };
+size_t png_table_words(int width, int height);
+void launch_png_tables(uint32_t *tables, int width, int height, cudaStream_t s);
+void launch_png_encode(const float4 *fb, int width, int height, uint8_t *out, const uint32_t *tables, png_sums *acc,
+                       cudaStream_t s);
 // hittest.cu
 void launch_hit_test(const float4 *edges, uint32_t n_edges, const float2 *queries, uint32_t n_queries, int2 *acc,
                      uint8_t *inside, cudaStream_t s);

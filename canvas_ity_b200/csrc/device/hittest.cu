@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(kHitBlock) k_hit_test(const float4 *edges, uin
                                                         uint32_t n_queries, int2 *acc, uint32_t edges_per_chunk)
 {
     __shared__ float4 tile[kHitBlock];
+    __shared__ float2 span[kHitBlock];                      // (min y, max y) of the staged edges
     const uint32_t q = blockIdx.x * kHitBlock + threadIdx.x;
     const bool live = q < n_queries;
     const float2 at = live ? queries[q] : make_float2(0.0f, 0.0f);
@@ -35,19 +36,31 @@ __global__ void __launch_bounds__(kHitBlock) k_hit_test(const float4 *edges, uin
     int winding = 0, on_edge = 0;
     for (uint32_t base = e0; base < e1; base += kHitBlock) {
         __syncthreads();
-        if (base + threadIdx.x < e1) tile[threadIdx.x] = edges[base + threadIdx.x];
+        if (base + threadIdx.x < e1) {
+            const float4 e = edges[base + threadIdx.x];
+            tile[threadIdx.x] = e;
+            // a NaN ordinate fails every comparison of the reference: give such an edge an empty span
+            const bool ordered = e.y == e.y && e.w == e.w;
+            span[threadIdx.x] = ordered ? make_float2(fminf(e.y, e.w), fmaxf(e.y, e.w)) : make_float2(1.0f, 0.0f);
+        }
         __syncthreads();
         const int n = int(min(uint32_t(kHitBlock), e1 - base));
-#pragma unroll 4
+        // The reference's (from.y < y && y <= to.y) || (to.y < y && y <= from.y) is lo < y && y <= hi;
+        // its horizontal-edge rule needs lo == y == hi.  Both live in lo <= y && y <= hi, which most
+        // edges fail, so the common path is one 8-byte broadcast load and two compares.
+#pragma unroll 8
         for (int k = 0; k < n; ++k) {
-            const float4 e = tile[k];
-            const vec2 from = v2(e.x, e.y), to = v2(e.z, e.w);
-            if ((from.y < p.y && p.y <= to.y) || (to.y < p.y && p.y <= from.y)) {
-                const float side = dot(perp(to - from), p - from);
-                if (side == 0.0f) on_edge = 1;
-                else winding += side > 0.0f ? 1 : -1;
-            } else if (from.y == p.y && p.y == to.y && ((from.x <= p.x && p.x <= to.x) || (to.x <= p.x && p.x <= from.x)))
-                on_edge = 1;
+            const float2 sp = span[k];
+            if (sp.x <= p.y && p.y <= sp.y) {
+                const float4 e = tile[k];
+                const vec2 from = v2(e.x, e.y), to = v2(e.z, e.w);
+                if (sp.x < p.y) {
+                    const float side = dot(perp(to - from), p - from);
+                    if (side == 0.0f) on_edge = 1;
+                    else winding += side > 0.0f ? 1 : -1;
+                } else if (sp.x == sp.y && ((from.x <= p.x && p.x <= to.x) || (to.x <= p.x && p.x <= from.x)))
+                    on_edge = 1;
+            }
         }
     }
     if (live) {

@@ -295,6 +295,30 @@ int cv_write_tga(cv_canvas *canvas, const char *path)
     return rc;
 }
 
+int cv_write_png(cv_canvas *canvas, const char *path)
+{
+    if (!canvas || !path) return CB200_ERR_BAD_ARG;
+    canvas_ity::canvas::host_state *s = front(canvas)->b200();
+    s->flush();
+    if (!s->device) { g_api_error = "cv_write_png: tapped canvas has no device"; return CB200_ERR_NO_DEVICE; }
+    size_t bytes = 0;
+    int rc = cb200_encode_png(s->device, nullptr, 0, &bytes);
+    if (rc != CB200_OK) { g_api_error = cb200_last_error(); return rc; }
+    uint8_t *file = static_cast<uint8_t *>(cb200_host_alloc(bytes));          // page-locked: one DMA, no bounce
+    if (!file) { g_api_error = "cv_write_png: out of host memory"; return CB200_ERR_OOM; }
+    rc = cb200_encode_png(s->device, file, bytes, nullptr);
+    if (rc == CB200_OK) {
+        FILE *f = fopen(path, "wb");
+        if (!f || fwrite(file, 1, bytes, f) != bytes) {
+            g_api_error = std::string("cv_write_png: cannot write ") + path;
+            rc = CB200_ERR_BAD_ARG;
+        }
+        if (f) fclose(f);
+    } else g_api_error = cb200_last_error();
+    cb200_host_free(file);
+    return rc;
+}
+
 int cv_set_text_instancing(cv_canvas *canvas, int on)
 {
     if (!canvas) return CB200_ERR_BAD_ARG;

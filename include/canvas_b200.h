@@ -239,6 +239,15 @@ int cb200_read_bgra8(cb200_canvas *canvas, uint8_t *dst, int width, int height, 
  * torch (__cuda_array_interface__).  Waits for queued work; valid until the next frame. */
 int cb200_framebuffer_device(cb200_canvas *canvas, void **device_ptr, int *rows, int *width);
 
+/* The whole PNG file the reference's driver writes after get_image_data (write_png,
+ * test/test.cpp:2415-2507: IHDR + sRGB + one IDAT of stored deflate blocks, one per row, + IEND),
+ * produced on the device straight from the float framebuffer: one kernel does the sRGB + dither
+ * conversion, lays the bytes out as the file and folds the Adler-32 and CRC-32 in, so no CPU pass
+ * over the pixels follows the readback.  Byte-identical to write_png() over get_image_data()'s
+ * output.  dst == NULL: only *bytes (the file size, 76 + height * (6 + 4 * width)) is returned.
+ * Whole canvases only (no bands / batches); 4 * width + 1 must fit a stored block (width <= 16383). */
+int cb200_encode_png(cb200_canvas *canvas, uint8_t *dst, size_t capacity, size_t *bytes);
+
 /* Readback without the host copy: runs the sRGB/dither kernel into a device
  * buffer owned by the canvas and returns its device pointer (for NCCL gathers
  * and device-resident timing). */
@@ -270,6 +279,7 @@ typedef struct cb200_stats {
     float    coverage_ms;          /* scanline walk: running sums + tile entries (after the sort) */
     float    shadow_raster_ms;     /* coverage * alpha into the shadow planes */
     float    blur_ms;              /* both blur sweeps */
+    float    png_ms;               /* cb200_encode_png: convert + lay out + checksums, device only */
 } cb200_stats;
 
 int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);

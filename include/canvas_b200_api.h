@@ -68,6 +68,12 @@ long cv_path_edges(cv_canvas *canvas, float *edges, long capacity);
  * (cb200_read_bgra8) and the rows go from the pinned staging buffer to the file. */
 int cv_write_tga(cv_canvas *canvas, const char *path);
 
+/* The file the reference's test driver writes (write_png, test/test.cpp:2415-2507).  On the B200
+ * build the whole file image -- pixels, stored-deflate framing, Adler-32, CRC-32 -- comes off the
+ * device (cb200_encode_png) and goes to disk as is; on the reference build it is get_image_data
+ * followed by the reference's own write_png. */
+int cv_write_png(cv_canvas *canvas, const char *path);
+
 /* A batch of n independent width x height canvases rendered together on one GPU
  * (cb200_batch_*): cv_batch_canvas(i) is an ordinary front-end canvas whose draws
  * are queued in the batch; cv_batch_flush() lowers and submits all of them in one

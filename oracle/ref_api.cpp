@@ -92,6 +92,17 @@ int cv_write_tga(cv_canvas *c, const char *path)
     fclose(f);
     return 0;
 }
+// the reference driver's own PNG writer (test/test.cpp:2415-2507), compiled in ref_png.cpp
+void ref_write_png(const char *path, const unsigned char *rgba, int width, int height);
+int cv_write_png(cv_canvas *c, const char *path)
+{
+    canvas_ity::canvas *r = ref(c);
+    const int w = r->size_x, h = r->size_y;
+    std::vector<unsigned char> image(size_t(w) * size_t(h) * 4);
+    r->get_image_data(image.data(), w, h, 4 * w, 0, 0);
+    ref_write_png(path, image.data(), w, h);
+    return 0;
+}
 int cv_set_text_instancing(cv_canvas *, int) { return 0; }
 int cv_flush(cv_canvas *) { return 0; }
 // batches are a back-end concept: the reference renders canvases one by one

@@ -56,3 +56,4 @@ def test_our_arm_line():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert line["config"]["workload"].startswith("tiger_1024")
     assert line["passes"]["readback"]["ms"] > 0 and line["single_canvas"]["value"] > 0
+    assert line["passes"]["png_encode"]["ms"] > 0 and line["passes"]["hit_test"]["rule_evaluations_per_s"] > 0

@@ -201,3 +201,18 @@ def test_gpu_hit_test_through_the_c_abi_with_timing(lib):
         assert np.array_equal(got, again)
     finally:
         lib.cb200_canvas_destroy(dev)
+
+
+@pytest.mark.gpu
+def test_python_mirror_bulk_query(lib):
+    import canvas_ity_b200 as cb
+    c = cb.Canvas(256, 256)
+    try:
+        c.move_to(30, 30); c.line_to(220, 40); c.line_to(128, 230); c.close_path()
+        q = queries(5000, seed=11)
+        many = c.points_in_path(q)
+        assert many.dtype == bool and 0 < many.sum() < len(q)
+        for i in range(0, len(q), 211):                       # the single-point host query says the same
+            assert c.is_point_in_path(float(q[i, 0]), float(q[i, 1])) == bool(many[i])
+    finally:
+        c.close()
