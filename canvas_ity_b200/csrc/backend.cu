@@ -134,7 +134,7 @@ struct cb200_canvas {
     uint64_t cap_planes = 0;
 
     // PNG encode (cb200_encode_png): per-size constant tables, the file image, the checksum accumulators
-    dev_buf<uint32_t> png_tables;  dev_buf<uint8_t> png_out;  dev_buf<png_sums> png_acc;  bool png_tables_ready = false;
+    dev_buf<uint32_t> png_tables, png_row_crc;  dev_buf<uint8_t> png_out;  dev_buf<png_sums> png_acc;  bool png_tables_ready = false;
     // bulk hit testing (cb200_hit_test)
     dev_buf<float4> hit_edges;  dev_buf<float2> hit_queries;  dev_buf<int2> hit_acc;  dev_buf<uint8_t> hit_inside;
     // device mirrors of the glyph atlases seen so far (append-only, keyed by atlas id)
@@ -1014,7 +1014,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
-    cv->png_tables.release(); cv->png_out.release(); cv->png_acc.release();
+    cv->png_tables.release(); cv->png_row_crc.release(); cv->png_out.release(); cv->png_acc.release();
     cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();
     for (auto &kv : cv->atlases) { kv.second.outlines.release(); kv.second.segs.release(); kv.second.points.release(); }
     for (int i = 0; i < 10; ++i)
@@ -1243,13 +1243,14 @@ int cb200_encode_png(cb200_canvas *cv, uint8_t *dst, size_t capacity, size_t *by
     if (!cv->png_tables_ready) {
         CK(cv->png_tables.reserve(png_table_words(cv->width, cv->height)));
         CK(cv->png_acc.reserve(1));
+        CK(cv->png_row_crc.reserve(size_t(cv->height)));
         CK(cv->png_out.reserve(size));
         launch_png_tables(cv->png_tables.p, cv->width, cv->height, s);
         ++cv->launches;
         cv->png_tables_ready = true;
     }
     CK(cudaEventRecord(cv->ev[7], s));
-    launch_png_encode(cv->fb, cv->width, cv->height, cv->png_out.p, cv->png_tables.p, cv->png_acc.p, s);
+    launch_png_encode(cv->fb, cv->width, cv->height, cv->png_out.p, cv->png_tables.p, cv->png_acc.p, cv->png_row_crc.p, s);
     cv->launches += 2;
     CK(cudaEventRecord(cv->ev[6], s));
     if (is_pinned_host(dst)) CK(cudaMemcpyAsync(dst, cv->png_out.p, size, cudaMemcpyDeviceToHost, s));

@@ -115,7 +115,7 @@ struct png_sums { unsigned long long a, b; uint32_t crc, pad; };
 size_t png_table_words(int width, int height);
 void launch_png_tables(uint32_t *tables, int width, int height, cudaStream_t s);
 void launch_png_encode(const float4 *fb, int width, int height, uint8_t *out, const uint32_t *tables, png_sums *acc,
-                       cudaStream_t s);
+                       uint32_t *row_crc, cudaStream_t s);
 // hittest.cu
 void launch_hit_test(const float4 *edges, uint32_t n_edges, const float2 *queries, uint32_t n_queries, int2 *acc,
                      uint8_t *inside, cudaStream_t s);

@@ -175,14 +175,14 @@ __global__ void __launch_bounds__(kPngBlock) k_png_tables(uint32_t *tables, int 
     }
 }
 
-__global__ void __launch_bounds__(kPngBlock) k_png_rows(const float4 *fb, int width, int height, uint8_t *out,
-                                                         const uint32_t *tables, png_sums *acc)
+__global__ void __launch_bounds__(kPngBlock, 3) k_png_rows(const float4 *fb, int width, int height, uint8_t *out,
+                                                         const uint32_t *tables, png_sums *acc, uint32_t *row_crc)
 {
     __shared__ uint32_t T[1024];
     __shared__ uint32_t staged[kPngBlock / 32][kPngSeg + kPngSeg / 8];     // word i at i + i / 8
     for (int i = threadIdx.x; i < 1024; i += kPngBlock) T[i] = tables[i];
     __syncthreads();
-    const uint32_t *col_shift = tables + 1024, *row_shift = col_shift + (width + 1);
+    const uint32_t *col_shift = tables + 1024;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *mine = staged[warp];
     const int segs_per_row = (width + kPngSeg - 1) / kPngSeg;
@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(kPngBlock) k_png_rows(const float4 *fb, int wi
     const uint32_t row_bytes = 1u + 4u * uint32_t(width), row_len = 5u + row_bytes;
     const uint64_t n_total = uint64_t(height) * row_bytes;               // uncompressed length
     unsigned long long sum_a = 0, sum_b = 0;
-    uint32_t crc_all = 0;
     for (long long sidx = (long long)blockIdx.x * (kPngBlock / 32) + warp; sidx < n_segs;
          sidx += (long long)gridDim.x * (kPngBlock / 32)) {
         const int y = int(sidx / segs_per_row), x0 = int(sidx % segs_per_row) * kPngSeg;
@@ -239,8 +238,9 @@ __global__ void __launch_bounds__(kPngBlock) k_png_rows(const float4 *fb, int wi
             uint16_t *h16 = reinterpret_cast<uint16_t *>(row_out);             // 56 + y * row_len is even
             h16[0] = uint16_t(b[0] | b[1] << 8); h16[1] = uint16_t(b[2] | b[3] << 8); h16[2] = uint16_t(b[4] | b[5] << 8);
         }
+        // the row's CRC (relative to the row's end) collects in row_crc[y]; k_png_finish shifts the rows
         const uint32_t seg_crc = __reduce_xor_sync(0xffffffffu, part);
-        crc_all ^= gf_mul(row_shift[y], seg_crc);
+        if (lane == 0 && seg_crc) atomicXor(&row_crc[y], seg_crc);
         // the pixels: rows start 2 bytes past a word boundary when y is even, so words are re-cut there
         uint8_t *seg_out = row_out + 6 + 4 * size_t(x0);
         if ((reinterpret_cast<uintptr_t>(seg_out) & 3u) == 0) {
@@ -269,14 +269,26 @@ __global__ void __launch_bounds__(kPngBlock) k_png_rows(const float4 *fb, int wi
     if (lane == 0) {
         atomicAdd(&acc->a, (unsigned long long)ra);
         atomicAdd(&acc->b, (unsigned long long)rb);
-        atomicXor(&acc->crc, crc_all);
     }
 }
 
-// Header, Adler-32, IDAT CRC and IEND (test.cpp:2430-2459, 2491-2506).  One thread.
-__global__ void k_png_finish(uint8_t *out, int width, int height, const png_sums *acc)
+// Header, Adler-32, IDAT CRC and IEND (test.cpp:2430-2459, 2491-2506).  One CTA: the threads shift every
+// row's CRC past the rows below it (x^(8 ((height - 1 - y) row_len + 4)), k_png_tables) and xor them
+// together, thread 0 writes the framing.
+__global__ void __launch_bounds__(1024) k_png_finish(uint8_t *out, int width, int height, const png_sums *acc,
+                                                     const uint32_t *tables, const uint32_t *row_crc)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    __shared__ uint32_t warp_xor[32];
+    const uint32_t *row_shift = tables + 1024 + (width + 1);
+    uint32_t rows_crc = 0;
+    for (int y = threadIdx.x; y < height; y += blockDim.x)
+        if (const uint32_t c = row_crc[y]) rows_crc ^= gf_mul(row_shift[y], c);
+    rows_crc = __reduce_xor_sync(0xffffffffu, rows_crc);
+    if ((threadIdx.x & 31) == 0) warp_xor[threadIdx.x >> 5] = rows_crc;
+    __syncthreads();
+    if (threadIdx.x) return;
+    rows_crc = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) rows_crc ^= warp_xor[w];
     const uint32_t row_bytes = 1u + 4u * uint32_t(width), row_len = 5u + row_bytes;
     const uint32_t idat_size = 6u + uint32_t(height) * row_len;
     const uint64_t n_total = uint64_t(height) * row_bytes;
@@ -298,7 +310,7 @@ __global__ void k_png_finish(uint8_t *out, int width, int height, const png_sums
     for (int i = 50; i < 56; ++i) head = crc_byte(head, header[i]);
     uint32_t tail = 0;
     for (int i = 0; i < 4; ++i) tail = crc_byte(tail, footer[i]);
-    const uint32_t state = gf_mul(gf_xpow(8ull * (uint64_t(height) * row_len + 4ull)), head) ^ acc->crc ^ tail;
+    const uint32_t state = gf_mul(gf_xpow(8ull * (uint64_t(height) * row_len + 4ull)), head) ^ rows_crc ^ tail;
     footer[4] = uint8_t(~state >> 24); footer[5] = uint8_t(~state >> 16); footer[6] = uint8_t(~state >> 8); footer[7] = uint8_t(~state);
     uint8_t *end = out + 56 + size_t(height) * size_t(row_len);
     for (int i = 0; i < 20; ++i) end[i] = footer[i];
@@ -348,13 +360,14 @@ void launch_png_tables(uint32_t *tables, int width, int height, cudaStream_t s)
 }
 
 void launch_png_encode(const float4 *fb, int width, int height, uint8_t *out, const uint32_t *tables, png_sums *acc,
-                       cudaStream_t s)
+                       uint32_t *row_crc, cudaStream_t s)
 {
     cudaMemsetAsync(acc, 0, sizeof(png_sums), s);
+    cudaMemsetAsync(row_crc, 0, sizeof(uint32_t) * size_t(height), s);
     const long long segs = (long long)((width + kPngSeg - 1) / kPngSeg) * height;
     const int ctas = int(std::min<long long>((segs + kPngBlock / 32 - 1) / (kPngBlock / 32), 4 * kSMs));
-    k_png_rows<<<std::max(ctas, 1), kPngBlock, 0, s>>>(fb, width, height, out, tables, acc);
-    k_png_finish<<<1, 32, 0, s>>>(out, width, height, acc);
+    k_png_rows<<<std::max(ctas, 1), kPngBlock, 0, s>>>(fb, width, height, out, tables, acc, row_crc);
+    k_png_finish<<<1, 1024, 0, s>>>(out, width, height, acc, tables, row_crc);
 }
 
 void launch_fill_f32(float *dst, float value, uint64_t n, cudaStream_t s)
