@@ -296,7 +296,14 @@ def main():
         launches += int(stats.kernel_launches)
     composited = int(stats.composited_pixels)
 
+    graph_replays = 0
+    for c in cvs:
+        check(lib.cb200_get_stats(c, C.byref(stats)))
+        graph_replays += int(stats.graph_replays)
+
     # ---- the compositor alone on the GPU: K more steps on ONE canvas (kernel quality, not throughput) ----
+    # stream launches here (graph replay off): every frame then carries its own compositor events
+    check(lib.cb200_set_graph_replay(cv, 0))
     barrier()
     check(lib.cb200_timer_begin(cv))
     for _ in range(args.steps):
@@ -469,6 +476,8 @@ def main():
                        "parallelism": ("bands%d+allgather" % world) if bands else
                                       ("frames x%d GPU, %d canvases in flight per GPU" % (world, n_canvases)),
                        "canvases_in_flight": n_canvases,
+                       "replay": "one CUDA graph launch per frame (%d graph replays in all)" % graph_replays if graph_replays
+                                 else "stream launches",
                        "l2": "268 MB float framebuffer per frame > 126 MB L2 (inputs larger than L2, no explicit flush)",
                        "composited_pixels_per_frame": composited,
                        "composited_mpix_per_s": composited * value / 1e6 / (1 if bands else world) * (1 if bands else world),

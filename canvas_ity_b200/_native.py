@@ -15,7 +15,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("draws", "cubics", "line_points", "edges", "raw_runs", "tile_entries",
                                            "composited_pixels", "shadow_pixels", "kernel_launches")] + \
                [(n, C.c_float) for n in ("last_frame_ms", "composite_ms", "raster_ms", "sort_ms", "geometry_ms",
-                                         "readback_ms", "coverage_ms", "shadow_raster_ms", "blur_ms", "png_ms")]
+                                         "readback_ms", "coverage_ms", "shadow_raster_ms", "blur_ms", "png_ms")] + \
+               [("graph_replays", C.c_uint32)]
 
 
 class Frame(C.Structure):          # cb200_frame
@@ -76,6 +77,7 @@ SIGNATURES = {
     "cb200_submit": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_upload": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_replay": (C.c_int, [C.c_void_p, C.c_int]),
+    "cb200_set_graph_replay": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_sync": (C.c_int, [C.c_void_p]),
     "cb200_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),
     "cb200_write_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),

@@ -157,9 +157,17 @@ struct cb200_canvas {
     bool clear_pending = false;        // cb200_clear / replay(clear): folded into the next frame, or applied by settle()
     bool inflight_clear = false;       // the frame in flight starts from a cleared canvas (kept for overflow re-runs)
     bool replay_verified = false;      // the resident frame has completed once with the current capacities
+    // replays of a verified resident frame run as ONE cudaGraphLaunch instead of ~45 stream calls
+    // (the host enqueue cost, not the GPU, bounds frames/s when several canvases replay concurrently);
+    // [0] without, [1] with the folded-in clear.  Dropped whenever the frame's buffers change.
+    cudaGraphExec_t replay_graph[2] = {nullptr, nullptr};
+    bool graph_replay = true;          // cb200_set_graph_replay
+    bool graph_broken = false;         // capture or instantiation failed once: keep to stream launches
+    uint32_t graph_replays = 0;
     // composite kernel times of the most recent frames (bench: roofline over the timed region)
     static const int kCompRing = 256;
     cudaEvent_t comp_ev[2 * kCompRing] = {};
+    bool comp_ev_valid[kCompRing] = {};   // false for frames that ran inside a graph (no per-frame events)
     uint64_t frames_run = 0, timer_frame0 = 0;
     cudaEvent_t timer_ev[2] = {};
     std::vector<cudaEvent_t> chunk_events;
@@ -515,8 +523,11 @@ size_t place(std::vector<std::pair<size_t, std::pair<const void *, size_t> > > &
     return off;
 }
 
+void drop_replay_graphs(cb200_canvas *cv);
+
 int upload_frame(cb200_canvas *cv)
 {
+    drop_replay_graphs(cv);                               // captured pointers and sizes are about to change
     staged_frame &sf = cv->staged;
     // clip masks written by this frame need planes before the table is built
     uint32_t max_slot = 0;
@@ -707,17 +718,29 @@ int upload_frame(cb200_canvas *cv)
     return CB200_OK;
 }
 
-// The fixed launch sequence of one frame.
-int run_frame(cb200_canvas *cv)
+int frame_launch_count(const cb200_canvas *cv)
+{
+    const staged_frame &sf = cv->staged;
+    const device_frame &f = cv->df;
+    return (sf.glyph_insts.empty() ? 0 : 1) + (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
+           ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
+           (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
+}
+
+// The fixed launch sequence of one frame, issued into the canvas stream -- or, with `in_graph`, into a
+// stream capture: events the host later waits on or times become event-record nodes, the per-frame
+// compositor event ring is skipped (a graph's nodes are the same for every replay).
+int enqueue_frame(cb200_canvas *cv, bool in_graph)
 {
     staged_frame &sf = cv->staged;
     device_frame &f = cv->df;
     cudaStream_t s = cv->stream;
+    auto mark = [&](cudaEvent_t e) { return in_graph ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
     CK(cudaMemsetAsync(cv->partials.p, 0, sizeof(uint32_t) * 8 * kGrid, s));
     // Stage events sit between kernels and so cut the programmatic-dependent-launch chain there;
     // with stage timing off only the frame and the compositor are bracketed.
-    const bool stages = cv->stage_timing;
-    CK(cudaEventRecord(cv->ev[0], s));
+    const bool stages = cv->stage_timing && !in_graph;
+    CK(mark(cv->ev[0]));
     launch_glyphs(f, s);
     launch_flatten(f, uint32_t(sf.units.size()), s);
     launch_dash(f, s);
@@ -731,22 +754,72 @@ int run_frame(cb200_canvas *cv)
     launch_rows(f, cv->target, sorted, s);
     if (stages) CK(cudaEventRecord(cv->ev[8], s));
     launch_shadow(f, cv->target, sorted, s, stages ? cv->ev[9] : nullptr);
-    CK(cudaEventRecord(cv->ev[4], s));
+    CK(mark(cv->ev[4]));
     const int ring = int(cv->frames_run % uint64_t(cb200_canvas::kCompRing));
-    CK(cudaEventRecord(cv->comp_ev[2 * ring], s));
+    if (!in_graph) CK(cudaEventRecord(cv->comp_ev[2 * ring], s));
     cv->target.clear_first = cv->inflight_clear ? 1 : 0;
     launch_composite(f, cv->target, sorted, s);
-    CK(cudaEventRecord(cv->comp_ev[2 * ring + 1], s));
-    CK(cudaEventRecord(cv->ev[5], s));
-    ++cv->frames_run;
+    if (!in_graph) CK(cudaEventRecord(cv->comp_ev[2 * ring + 1], s));
+    CK(mark(cv->ev[5]));
     CK(cudaMemcpyAsync(cv->pinned_hdr, f.hdr, sizeof(frame_header), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(cv->ev[6], s));
-    cv->launches += (sf.glyph_insts.empty() ? 0 : 1) + (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
-                    ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-                    (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
+    CK(mark(cv->ev[6]));
+    return CB200_OK;
+}
+
+int run_frame(cb200_canvas *cv)
+{
+    int rc = enqueue_frame(cv, false);
+    if (rc != CB200_OK) return rc;
+    cv->comp_ev_valid[cv->frames_run % uint64_t(cb200_canvas::kCompRing)] = true;
+    ++cv->frames_run;
+    cv->launches += uint64_t(frame_launch_count(cv));
     cv->pending = true;
     CK(cudaGetLastError());
     return CB200_OK;
+}
+
+void drop_replay_graphs(cb200_canvas *cv)
+{
+    for (int k = 0; k < 2; ++k)
+        if (cv->replay_graph[k]) { cudaGraphExecDestroy(cv->replay_graph[k]); cv->replay_graph[k] = nullptr; }
+}
+
+// One replay of the resident, verified frame as a single graph launch: header restore, every kernel
+// of the frame (programmatic dependent launches become programmatic graph edges), header readback.
+// Returns false when the graph path is not available (the caller then issues the stream sequence).
+bool replay_with_graph(cb200_canvas *cv, int *rc_out)
+{
+    *rc_out = CB200_OK;
+    if (!cv->graph_replay || cv->graph_broken || cv->stage_timing || !cv->replay_verified) return false;
+    const int key = cv->inflight_clear ? 1 : 0;
+    cudaStream_t s = cv->stream;
+    if (!cv->replay_graph[key]) {
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+            ok = cudaMemcpyAsync(cv->blob.p + cv->hdr_offset, cv->blob.p + cv->hdr_pristine_offset, sizeof(frame_header),
+                                 cudaMemcpyDeviceToDevice, s) == cudaSuccess;
+            ok = ok && enqueue_frame(cv, true) == CB200_OK;
+            ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && ok && graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&cv->replay_graph[key], graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();                          // clear the sticky-free error of the failed attempt
+            cv->replay_graph[key] = nullptr;
+            cv->graph_broken = true;
+            if (getenv("CB200_DEBUG")) fprintf(stderr, "[cb200] graph capture of the frame failed; staying on stream launches\n");
+            return false;
+        }
+    }
+    cudaError_t e = cudaGraphLaunch(cv->replay_graph[key], s);
+    if (e != cudaSuccess) { *rc_out = fail(CB200_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e)); return true; }
+    cv->comp_ev_valid[cv->frames_run % uint64_t(cb200_canvas::kCompRing)] = false;
+    ++cv->frames_run;
+    ++cv->graph_replays;
+    cv->launches += uint64_t(frame_launch_count(cv));
+    cv->pending = true;
+    return true;
 }
 
 // Wait for the launched frame, and if a device queue overflowed re-run it with
@@ -807,6 +880,7 @@ int finish_pending(cb200_canvas *cv)
             st.composited_pixels = seen.composited_pixels;
             st.shadow_pixels = seen.shadow_working_pixels;
             st.kernel_launches = cv->launches;
+            st.graph_replays = cv->graph_replays;
             cv->pending = false;
             cv->replay_verified = cv->resident;
             return CB200_OK;
@@ -1014,6 +1088,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
+    drop_replay_graphs(cv);
     cv->png_tables.release(); cv->png_row_crc.release(); cv->png_out.release(); cv->png_acc.release();
     cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();
     for (auto &kv : cv->atlases) { kv.second.outlines.release(); kv.second.segs.release(); kv.second.points.release(); }
@@ -1072,10 +1147,25 @@ int cb200_frame_replay(cb200_canvas *cv, int clear)
         if (rc != CB200_OK) return rc;
     }
     if (clear) cv->clear_pending = true;
+    {
+        const bool keep_clear = cv->clear_pending;
+        cv->inflight_clear = cv->clear_pending;          // what start_frame() would set; the graph is keyed on it
+        cv->clear_pending = false;
+        int rc = CB200_OK;
+        if (replay_with_graph(cv, &rc)) return rc;
+        cv->clear_pending = keep_clear;
+    }
     // the header is consumed by a run: restore it from its pristine twin (device to device)
     CK(cudaMemcpyAsync(cv->blob.p + cv->hdr_offset, cv->blob.p + cv->hdr_pristine_offset, sizeof(frame_header),
                        cudaMemcpyDeviceToDevice, cv->stream));
     return start_frame(cv);
+}
+
+int cb200_set_graph_replay(cb200_canvas *cv, int on)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    cv->graph_replay = on != 0;
+    return CB200_OK;
 }
 
 int cb200_timer_begin(cb200_canvas *cv)
@@ -1099,14 +1189,17 @@ int cb200_timer_end(cb200_canvas *cv, float *elapsed_ms, float *composite_ms, ui
     uint64_t first = cv->timer_frame0;
     if (cv->frames_run - first > uint64_t(cb200_canvas::kCompRing)) first = cv->frames_run - cb200_canvas::kCompRing;
     float sum = 0.0f;
+    uint32_t counted = 0;
     for (uint64_t k = first; k < cv->frames_run; ++k) {
         const int ring = int(k % uint64_t(cb200_canvas::kCompRing));
+        if (!cv->comp_ev_valid[ring]) continue;            // a graph replay: no per-frame events
         float ms = 0.0f;
         CK(cudaEventElapsedTime(&ms, cv->comp_ev[2 * ring], cv->comp_ev[2 * ring + 1]));
         sum += ms;
+        ++counted;
     }
     if (composite_ms) *composite_ms = sum;
-    if (composite_frames) *composite_frames = uint32_t(cv->frames_run - first);
+    if (composite_frames) *composite_frames = counted;
     return CB200_OK;
 }
 

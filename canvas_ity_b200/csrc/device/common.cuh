@@ -21,6 +21,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../geom.cuh"
@@ -178,6 +179,13 @@ __device__ __forceinline__ void grid_dependency_wait()
 }
 
 #ifdef __CUDACC__
+// CB200_PDL=0 turns the early placement off (plain stream order) -- an A/B switch for measurements.
+inline int pdl_allowed()
+{
+    static const int allowed = [] { const char *e = getenv("CB200_PDL"); return e ? atoi(e) != 0 : 1; }();
+    return allowed;
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
 {
@@ -185,7 +193,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_allowed();
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }

@@ -204,6 +204,13 @@ int cb200_submit(cb200_canvas *canvas, const cb200_frame *frame);
 int cb200_frame_upload(cb200_canvas *canvas, const cb200_frame *frame);
 int cb200_frame_replay(cb200_canvas *canvas, int clear);
 
+/* Replays of a resident frame that has completed once are issued as ONE CUDA graph launch (the frame's
+ * ~36 kernels with their programmatic-dependent-launch edges, header restore and readback) instead
+ * of ~45 stream calls: with several canvases replaying concurrently the host's enqueue cost, not the
+ * GPU, is what bounds frames/s.  On by default; off = plain stream launches (per-frame compositor
+ * events for cb200_timer_end, per-stage events).  Per-stage timing also disables it. */
+int cb200_set_graph_replay(cb200_canvas *canvas, int on);
+
 /* Wait for everything enqueued on the canvas' stream. */
 int cb200_sync(cb200_canvas *canvas);
 
@@ -280,6 +287,7 @@ typedef struct cb200_stats {
     float    shadow_raster_ms;     /* coverage * alpha into the shadow planes */
     float    blur_ms;              /* both blur sweeps */
     float    png_ms;               /* cb200_encode_png: convert + lay out + checksums, device only */
+    uint32_t graph_replays;        /* cb200_frame_replay calls that ran as one CUDA graph launch */
 } cb200_stats;
 
 int cb200_get_stats(cb200_canvas *canvas, cb200_stats *out);
@@ -289,7 +297,8 @@ int cb200_set_stage_timing(cb200_canvas *canvas, int on);
 /* Device-side stopwatch on the canvas stream, for timing a run of frames without a host round
  * trip per frame: _begin records an event, _end records another, waits for it and returns the
  * elapsed milliseconds plus the summed duration of the tile compositor over the frames in
- * between (the most recent 256 of them; *composite_frames says how many were summed). */
+ * between (the most recent 256 of them that were issued as stream launches -- graph replays carry no
+ * per-frame events; *composite_frames says how many were summed). */
 int cb200_timer_begin(cb200_canvas *canvas);
 int cb200_timer_end(cb200_canvas *canvas, float *elapsed_ms, float *composite_ms, uint32_t *composite_frames);
 
