@@ -11,4 +11,4 @@ try:
     d=json.load(open(sys.argv[1])); print(sys.argv[1], 'value %.1f'%d['value'], d.get('scaling'), d['config'].get('parallelism'), 'e2e', d.get('e2e',{}).get('value'))
 except Exception as e: print(sys.argv[1], 'unreadable', e)
 PY
-done; tail -3 $O/n${N}_*.err
+done; for f in $O/n${N}_*.err; do tail -n 3 $f; done
