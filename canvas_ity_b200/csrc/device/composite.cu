@@ -130,6 +130,26 @@ __device__ __forceinline__ void blend(float4 &back, rgba fore, uint32_t op, floa
                        fmaf(vis, a, keep * back.w));
 }
 
+// The same program where nothing clips the draw (visibility exactly 1): the closing lerp
+// back = 1 * blend + 0 * back is the blend itself, and source_over (mix_fore = 1, mix_back = 1 - fore.a,
+// three draws out of four) needs no selects.  Same products and sums as blend(), so the same bits
+// (for finite pixels; 0 * inf would be NaN in the lerp).
+__device__ __forceinline__ void blend_unclipped(float4 &back, rgba fore, uint32_t op)
+{
+    if (op == 14u) {
+        const float mb = 1.0f - fore.a;
+        back = make_float4(fore.r + mb * back.x, fore.g + mb * back.y, fore.b + mb * back.z,
+                           fminf(fore.a + mb * back.w, 1.0f));
+        return;
+    }
+    float mf = (op & 1u) ? back.w : 0.0f;
+    if (op & 2u) mf = 1.0f - mf;
+    float mb = (op & 4u) ? fore.a : 0.0f;
+    if (op & 8u) mb = 1.0f - mb;
+    back = make_float4(fmaf(mf, fore.r, mb * back.x), fmaf(mf, fore.g, mb * back.y), fmaf(mf, fore.b, mb * back.z),
+                       fminf(fmaf(mf, fore.a, mb * back.w), 1.0f));
+}
+
 constexpr int kWarpRows = 8;                                 // scanlines of a tile owned by one warp
 constexpr int kTileWarps = kTile / kWarpRows;               // 4 warps per tile
 constexpr int kCompBlock = 32 * kTileWarps;                 // one CTA = one tile = 128 threads
@@ -478,7 +498,7 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
                     float cov = fminf(fabsf(sum), 1.0f);
                     if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
                     ++painted;
-                    blend(px[r], scale(cov * alpha, flat), op, 1.0f);
+                    blend_unclipped(px[r], scale(cov * alpha, flat), op);
                 }
             } else if (kPaint && staged && gradient && !mask && !mask_out) {
                 // unclipped gradient fill: the brush set-up is hoisted out of the pixel loop
@@ -490,7 +510,7 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
                     if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
                     ++painted;
                     rgba paint = gradient_at(g, ws.brush, float(x) + 0.5f, float(row0 + r) + 0.5f);
-                    blend(px[r], scale(cov * alpha, paint), op, 1.0f);
+                    blend_unclipped(px[r], scale(cov * alpha, paint), op);
                 }
             } else if (kGeneral) {
 #pragma unroll
