@@ -224,7 +224,8 @@ int stage_frames(cb200_canvas *cv, const cb200_frame *const *frames, const uint3
         sf.draw_src.resize(draw_base + in->n_draws, make_uint2(0, 0));
         // glyph instances: rebase onto the shared instance region and the batch-wide atlas list
         const uint32_t glyph_pt_base = sf.n_glyph_points;
-        if (in->n_glyphs && (!in->glyphs || !in->atlases)) return fail(CB200_ERR_BAD_ARG, "frame.glyphs / atlases is null");
+        if ((in->n_glyphs && !in->glyphs) || (in->n_atlases && !in->atlases) || (in->n_glyphs && !in->n_atlases))
+            return fail(CB200_ERR_BAD_ARG, "frame.glyphs / atlases is null");
         std::vector<uint32_t> atlas_slot(in->n_atlases);
         for (uint32_t a = 0; a < in->n_atlases; ++a) {
             uint32_t slot = 0;

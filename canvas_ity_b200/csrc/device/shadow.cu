@@ -126,6 +126,27 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
         const uint32_t first = cs.first[te * kTile + lane];
         float *out = plane + ptrdiff_t(ty * kTile - jr.top) * ptrdiff_t(jr.pitch) + ptrdiff_t(x - jr.left + jr.skew);
         const int ly0 = max(0, jr.top - ty * kTile), ly1 = min(kTile, jr.top + jr.bh - ty * kTile);
+        // Most tiles of a shadow plane hold no edge at all (empty border, solid interior): every row is
+        // one value, and the tile goes out as 16-byte stores, four rows per step (tile columns start on
+        // a 128 B line: job_rec::skew).  Same arithmetic per row as below.
+        if (flat_alpha >= 0.0f && !__ballot_sync(0xffffffffu, first != kNoRun) &&
+            tx * kTile >= jr.left && tx * kTile + kTile <= jr.left + jr.bw) {
+            const float row_cov = fminf(fabsf(carried), 1.0f);
+            const float row_v = row_cov >= kThreshold ? row_cov * flat_alpha : 0.0f;     // lane = row
+            float *tile_out = out - lane;                                                   // the tile's first column
+            if (((tx * kTile - jr.left + jr.skew) & 3) == 0) {                              // 16-byte aligned (border % 4 == 0)
+#pragma unroll
+                for (int i = 0; i < kTile / 4; ++i) {
+                    const int ly = i * 4 + (lane >> 3);
+                    const float v = __shfl_sync(0xffffffffu, row_v, ly);
+                    if (ly >= ly0 && ly < ly1)
+                        reinterpret_cast<float4 *>(tile_out + ptrdiff_t(ly) * ptrdiff_t(jr.pitch))[lane & 7] = make_float4(v, v, v, v);
+                }
+            } else {
+                for (int ly = ly0; ly < ly1; ++ly) out[ptrdiff_t(ly) * ptrdiff_t(jr.pitch)] = __shfl_sync(0xffffffffu, row_v, ly);
+            }
+            continue;
+        }
         for (int ly = ly0; ly < ly1; ++ly) {
             const int y = ty * kTile + ly;
             float sum = __shfl_sync(0xffffffffu, carried, ly);
