@@ -13,6 +13,13 @@
 #define CANVAS_ITY_B200_FRONT_HPP
 
 #include <cstddef>
+#include <vector>               // the reference's interface section includes these two (hpp:139-140) ...
+
+#ifdef CANVAS_ITY_IMPLEMENTATION
+#include <algorithm>            // ... and its implementation section these (hpp:1216-1218): drivers such as
+#include <cmath>                // test/test.cpp rely on getting <cmath> through CANVAS_ITY_IMPLEMENTATION
+#include <numeric>
+#endif
 
 namespace canvas_ity
 {
