@@ -1537,7 +1537,7 @@ int64_t cb200_debug_lines(cb200_canvas *cv, float *edges, uint32_t *job_of_edge,
         if (!rows[size_t(i)]) continue;
         if (got < capacity && edges) {
             memcpy(edges + got * 4, &pieces[size_t(i)], sizeof(float4));
-            if (job_of_edge) job_of_edge[got] = jobs[size_t(i)];
+            if (job_of_edge) job_of_edge[got] = jobs[size_t(i)] & 0x7fffffffu;      // bit 31: projected piece (raster.cu)
         }
         ++got;
     }

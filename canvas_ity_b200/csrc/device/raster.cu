@@ -232,7 +232,11 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
             if (made < 3) {
                 uint32_t slot = it * 3 + made;
                 f.pieces[slot] = pc;
-                f.piece_job[slot] = j;
+                // bit 31: the piece lies left / right of the padded canvas and was projected onto its boundary.
+                // Its runs only cancel one another; the reference's Sutherland-Hodgman clip replaces such an
+                // excursion by ONE boundary segment between the two crossing points (hpp:2208-2229), so these
+                // runs must not widen the bounding box render_shadow takes from the runs (hpp:2409-2419).
+                f.piece_job[slot] = j | ((mid.x < 0.0f || mid.x > w) ? 0x80000000u : 0u);
                 f.piece_rows[slot] = rows;
                 f.piece_rlo[slot] = rlo;
                 sum += rows;
@@ -361,7 +365,9 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         carry += total;
         if (!valid) continue;
         const uint32_t slot = f.row_piece[it];
-        uint32_t j = f.piece_job[slot];
+        const uint32_t tagged = f.piece_job[slot];
+        const uint32_t j = tagged & 0x7fffffffu;
+        const bool projected = (tagged >> 31) != 0;              // an excursion outside the canvas, flattened onto its boundary
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
         uint64_t row_key = ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx;
@@ -390,9 +396,11 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         float d0 = (carry_area + strip - area) * e.sign, d1 = area * e.sign;
         keys[at] = row_key | uint64_t(uint32_t(px));         vals[at] = d0; ++at;
         keys[at] = row_key | uint64_t(uint32_t(px + 1.0f));  vals[at] = d1; ++at;
-        if (shadow) {
+        if (shadow && !projected) {
             // exact bounds of the runs the reference keeps (non-zero deltas) plus the
-            // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252)
+            // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252).  Runs of projected
+            // pieces are left out: the boundary segment the reference puts in their place spans the rows
+            // between the two crossing points, which the neighbouring inside pieces already reach.
             if (d0 != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
             if (d1 != 0.0f) { lo_x = min(lo_x, int(px) + 1); hi_x = max(hi_x, int(px) + 1); }
             job_rec &jr = f.jobs[j];

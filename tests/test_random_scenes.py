@@ -1,0 +1,108 @@
+"""Randomised parity: seeded scenes that mix what the 76 reference tests exercise one at a time -- transforms,
+all eleven composite operations, solid / linear / radial / pattern brushes, dashes, joins and caps, clip paths,
+shadows, global alpha, text -- through the CUDA back end and through the oracle on the same lowered frames
+(float framebuffer within 1e-4 relative, RGBA8 within 1 LSB).  The oracle side of the same scenes is pinned to
+the reference build on the CPU (`test_oracle_matches_reference_on_random_scenes`)."""
+import numpy as np
+import pytest
+
+from tests import harness as H
+
+SIZE = 192
+OPS = [1, 2, 3, 4, 7, 10, 11, 12, 13, 14, 15]
+
+
+def random_scene(seed):
+    rng = np.random.default_rng(1000 + seed)
+    u = lambda lo=0.0, hi=1.0: float(rng.uniform(lo, hi))
+    w = H.ScriptWriter()
+    # a background so that destination-dependent operations have something to work on
+    w.ints("SET_COLOR", 0); w.raw("4f", u(), u(), u(), u(0.3, 1.0))
+    w.floats("FILL_RECTANGLE", u(-20, 40), u(-20, 40), u(80, 220), u(80, 220))
+    image = rng.integers(0, 256, (8, 8, 4), dtype=np.uint8)
+    for _ in range(int(rng.integers(3, 7))):
+        w.bare("SAVE")
+        if rng.random() < 0.6:
+            w.floats("TRANSLATE", u(-20, 60), u(-20, 60)); w.floats("ROTATE", u(-0.8, 0.8)); w.floats("SCALE", u(0.5, 1.8), u(0.5, 1.8))
+        if rng.random() < 0.3:                                # clip to a blob
+            w.bare("BEGIN_PATH"); w.floats("ARC", u(40, 150), u(40, 150), u(30, 90), 0.0, 6.2831855, 0); w.bare("CLIP")
+        w.ints("SET_COMPOSITE", int(rng.choice(OPS)))
+        w.floats("SET_GLOBAL_ALPHA", u(0.3, 1.0))
+        if rng.random() < 0.25:
+            w.floats("SET_SHADOW_COLOR", u(), u(), u(), u(0.4, 1.0)); w.floats("SET_SHADOW_BLUR", u(0.0, 9.0))
+            w.floats("SET_SHADOW_OFFSET_X", u(-6, 6)); w.floats("SET_SHADOW_OFFSET_Y", u(-6, 6))
+        stroke = rng.random() < 0.5
+        which = 1 if stroke else 0
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            w.ints("SET_COLOR", which); w.raw("4f", u(), u(), u(), u(0.2, 1.0))
+        elif kind == 1:
+            w.ints("SET_LINEAR_GRADIENT", which); w.raw("4f", u(0, SIZE), u(0, SIZE), u(0, SIZE), u(0, SIZE))
+        elif kind == 2:
+            w.ints("SET_RADIAL_GRADIENT", which); w.raw("6f", u(40, 150), u(40, 150), u(0, 20), u(40, 150), u(40, 150), u(30, 120))
+        else:
+            w.ints("SET_PATTERN", which, 8, 8, 32, int(rng.integers(0, 4))); w.blob(image.tobytes())
+        if kind in (1, 2):
+            for o in sorted(rng.uniform(0, 1, int(rng.integers(2, 5)))):
+                w.ints("ADD_COLOR_STOP", which); w.raw("5f", float(o), u(), u(), u(), u(0.2, 1.0))
+        w.bare("BEGIN_PATH")
+        for _ in range(int(rng.integers(1, 3))):
+            w.floats("MOVE_TO", u(0, SIZE), u(0, SIZE))
+            for _ in range(int(rng.integers(2, 6))):
+                r = rng.random()
+                if r < 0.35:
+                    w.floats("LINE_TO", u(0, SIZE), u(0, SIZE))
+                elif r < 0.7:
+                    w.floats("BEZIER_CURVE_TO", *[u(-20, SIZE + 20) for _ in range(6)])
+                elif r < 0.85:
+                    w.floats("QUADRATIC_CURVE_TO", *[u(0, SIZE) for _ in range(4)])
+                else:
+                    w.floats("ARC", u(30, 160), u(30, 160), u(5, 60), u(0, 6.28), u(0, 6.28), int(rng.integers(0, 2)))
+            if rng.random() < 0.5:
+                w.bare("CLOSE_PATH")
+        if stroke:
+            w.floats("SET_LINE_WIDTH", u(0.5, 14.0)); w.ints("SET_LINE_JOIN", int(rng.integers(0, 3))); w.ints("SET_LINE_CAP", int(rng.integers(0, 3)))
+            w.floats("SET_MITER_LIMIT", u(1.0, 12.0))
+            if rng.random() < 0.4:
+                dashes = [u(2, 20) for _ in range(int(rng.integers(1, 5)))]
+                w.ints("SET_LINE_DASH", len(dashes)); w.raw("%df" % len(dashes), *dashes)
+                w.floats("SET_LINE_DASH_OFFSET", u(0, 30))
+            w.bare("STROKE")
+        else:
+            w.bare("FILL")
+        w.bare("RESTORE")
+    if rng.random() < 0.5:
+        w.floats("SET_FONT", u(14, 40)); w.raw("B", 1); w.blob(H.font_a())
+        w.ints("SET_COLOR", 0); w.raw("4f", u(), u(), u(), 1.0)
+        w.floats("FILL_TEXT", u(0, 80), u(30, 170), 1.0e30); w.blob(b"CDE nst*")
+    return w.take()
+
+
+SEEDS = list(range(24))
+
+
+@pytest.mark.parametrize("seed", SEEDS[:8])
+def test_oracle_matches_reference_on_random_scenes(seed):
+    ref = H.reference_library()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    script = random_scene(seed)
+    want = H.render_script(ref, script, SIZE, SIZE)
+    got = H.render_oracle(script, SIZE, SIZE)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "max |diff| %.3g" % worst
+    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", SEEDS)
+def test_gpu_matches_oracle_on_random_scenes(seed):
+    lib = H.product_library()
+    if lib.cb200_device_count() < 1:
+        pytest.skip("no CUDA device")
+    script = random_scene(seed)
+    got = H.render_script(lib, script, SIZE, SIZE)
+    want = H.render_oracle(script, SIZE, SIZE)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
+    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
