@@ -198,6 +198,22 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
             cut[m + 1] = v;
         }
         cut[nc++] = 1.0f;
+        if (job.kind == JOB_SHADOW) {
+            // Where the outline leaves or enters the padded canvas sideways, the reference's polygon clip
+            // starts / ends a boundary segment (hpp:2208-2229) whose runs count in render_shadow's bounding
+            // box (hpp:2409-2419).  Projected pieces do not lend their rows to that box (k_row_emit), and
+            // the inside piece that meets the crossing may be horizontal and emit nothing, so the
+            // crossing's own scanline is entered here.
+            for (int side = 0; side < 2; ++side) {
+                const float da = side ? w - a.x : a.x, db = side ? w - b.x : b.x;
+                if (da * db < 0.0f) {
+                    const float yc = fminf(fmaxf(mix(a, b, cross_at(da, db)).y, 0.0f), hgt);
+                    const int row = min(int(floorf(yc)), int(hgt) - 1);
+                    atomicMin(&f.jobs[j].run_min_y, row);
+                    atomicMax(&f.jobs[j].run_max_y, row);
+                }
+            }
+        }
         int row0 = job.kind == JOB_SHADOW ? 0 : t.band_y0;
         int row1 = job.kind == JOB_SHADOW ? t.height + job.pad : t.band_y0 + t.band_rows;
         int made = 0;
@@ -396,19 +412,20 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         float d0 = (carry_area + strip - area) * e.sign, d1 = area * e.sign;
         keys[at] = row_key | uint64_t(uint32_t(px));         vals[at] = d0; ++at;
         keys[at] = row_key | uint64_t(uint32_t(px + 1.0f));  vals[at] = d1; ++at;
-        if (shadow && !projected) {
+        if (shadow) {
             // exact bounds of the runs the reference keeps (non-zero deltas) plus the
-            // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252).  Runs of projected
-            // pieces are left out: the boundary segment the reference puts in their place spans the rows
-            // between the two crossing points, which the neighbouring inside pieces already reach.
+            // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252).  A projected
+            // piece only lends its column (the boundary column the reference's clip segment also
+            // touches): its rows may overshoot the two crossing points that segment joins, and the
+            // neighbouring inside pieces already reach those.
             if (d0 != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
             if (d1 != 0.0f) { lo_x = min(lo_x, int(px) + 1); hi_x = max(hi_x, int(px) + 1); }
             job_rec &jr = f.jobs[j];
             if (hi_x >= 0) {
                 atomicMin(&jr.run_min_x, lo_x); atomicMax(&jr.run_max_x, hi_x);
-                atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py));
+                if (!projected) { atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py)); }
             }
-            atomicMin(&jr.first_key, (uint32_t(w.py) << 16) | uint32_t(w.px));
+            if (!projected) atomicMin(&jr.first_key, (uint32_t(w.py) << 16) | uint32_t(w.px));
         }
     }
 }

@@ -78,7 +78,92 @@ def random_scene(seed):
     return w.take()
 
 
+def random_scene_wide(seed):
+    """A second generator: odd canvas sizes (tiles cut at the right / bottom edge), geometry far outside the
+    canvas, degenerate segments, rectangles, arc_to, nested clips, draw_image / put_image_data / clear_rectangle,
+    stroked and aligned text with a maximum width.  Returns (script, width, height)."""
+    rng = np.random.default_rng(5000 + seed)
+    u = lambda lo=0.0, hi=1.0: float(rng.uniform(lo, hi))
+    W, Hh = int(rng.integers(33, 300)), int(rng.integers(33, 300))
+    w = H.ScriptWriter()
+    image = rng.integers(0, 256, (6, 5, 4), dtype=np.uint8)
+    if rng.random() < 0.7:
+        w.ints("SET_COLOR", 0); w.raw("4f", u(), u(), u(), u(0.2, 1.0)); w.floats("FILL_RECTANGLE", u(-30, 30), u(-30, 30), u(40, 330), u(40, 330))
+    depth = 0
+    for _ in range(int(rng.integers(4, 10))):
+        r = rng.random()
+        if r < 0.15 and depth < 3:
+            w.bare("SAVE"); depth += 1
+            w.floats("TRANSLATE", u(-40, 80), u(-40, 80)); w.floats("ROTATE", u(-3.2, 3.2)); w.floats("SCALE", u(0.3, 2.5), u(0.3, 2.5))
+            continue
+        if r < 0.25 and depth > 0:
+            w.bare("RESTORE"); depth -= 1
+            continue
+        if r < 0.33:
+            w.bare("BEGIN_PATH"); w.floats("RECTANGLE", u(-50, W), u(-50, Hh), u(10, 250), u(10, 250))
+            if rng.random() < 0.5:
+                w.floats("ARC", u(0, W), u(0, Hh), u(10, 120), 0.0, 6.2831855, 0)
+            w.bare("CLIP")
+            continue
+        w.ints("SET_COMPOSITE", int(rng.choice(OPS)))
+        w.floats("SET_GLOBAL_ALPHA", u(0.2, 1.0))
+        if rng.random() < 0.3:
+            w.floats("SET_SHADOW_COLOR", u(), u(), u(), u(0.3, 1.0)); w.floats("SET_SHADOW_BLUR", u(0.0, 14.0))
+            w.floats("SET_SHADOW_OFFSET_X", u(-15, 15)); w.floats("SET_SHADOW_OFFSET_Y", u(-15, 15))
+        else:
+            w.floats("SET_SHADOW_COLOR", 0.0, 0.0, 0.0, 0.0)
+        which = int(rng.integers(0, 2))
+        w.ints("SET_COLOR", which); w.raw("4f", u(), u(), u(), u(0.2, 1.0))
+        if rng.random() < 0.3:
+            w.ints("SET_LINEAR_GRADIENT", which); w.raw("4f", u(-50, W + 50), u(-50, Hh + 50), u(-50, W + 50), u(-50, Hh + 50))
+            for o in sorted(rng.uniform(0, 1, int(rng.integers(1, 4)))):
+                w.ints("ADD_COLOR_STOP", which); w.raw("5f", float(o), u(), u(), u(), u(0.2, 1.0))
+        kind = rng.random()
+        w.floats("SET_LINE_WIDTH", float(rng.choice([0.3, 1.0, 2.5, 9.0, 31.0]))); w.ints("SET_LINE_JOIN", int(rng.integers(0, 3)))
+        w.ints("SET_LINE_CAP", int(rng.integers(0, 3))); w.floats("SET_MITER_LIMIT", u(1.0, 20.0))
+        if rng.random() < 0.3:
+            dashes = [u(0.5, 25) for _ in range(int(rng.integers(1, 6)))]
+            w.ints("SET_LINE_DASH", len(dashes)); w.raw("%df" % len(dashes), *dashes); w.floats("SET_LINE_DASH_OFFSET", u(-20, 40))
+        else:
+            w.ints("SET_LINE_DASH", 0)
+        if kind < 0.12:
+            w.floats("FILL_RECTANGLE" if which == 0 else "STROKE_RECTANGLE", u(-60, W), u(-60, Hh), u(-80, 260), u(-80, 260))
+        elif kind < 0.2:
+            w.floats("CLEAR_RECTANGLE", u(-20, W), u(-20, Hh), u(5, 120), u(5, 120))
+        elif kind < 0.3:
+            w.ints("DRAW_IMAGE", 5, 6, 20); w.raw("4f", u(-30, W), u(-30, Hh), u(-120, 200), u(-120, 200)); w.blob(image.tobytes())
+        elif kind < 0.36:
+            w.ints("PUT_IMAGE_DATA", 5, 6, 20, int(rng.integers(-4, W)), int(rng.integers(-4, Hh))); w.blob(image.tobytes())
+        elif kind < 0.5:
+            w.floats("SET_FONT", u(8, 60)); w.raw("B", 1); w.blob(H.font_a())
+            w.ints("SET_TEXT_ALIGN", int(rng.integers(0, 3))); w.ints("SET_TEXT_BASELINE", int(rng.integers(0, 5)))
+            w.floats("FILL_TEXT" if which == 0 else "STROKE_TEXT", u(-20, W), u(0, Hh), float(rng.choice([1.0e30, 40.0, 150.0]))); w.blob(b"CDEF GHI*nst")
+        else:
+            w.bare("BEGIN_PATH")
+            for _ in range(int(rng.integers(1, 4))):
+                big = 2000.0 if rng.random() < 0.15 else 0.0            # now and then far outside the canvas
+                px, py = u(-40 - big, W + 40 + big), u(-40 - big, Hh + 40 + big)
+                w.floats("MOVE_TO", px, py)
+                for _ in range(int(rng.integers(1, 7))):
+                    t = rng.random()
+                    if t < 0.3:
+                        w.floats("LINE_TO", u(-40 - big, W + 40 + big), u(-40 - big, Hh + 40 + big))
+                    elif t < 0.4:
+                        w.floats("LINE_TO", px, py)                      # back to the start: zero-length / doubled segments
+                    elif t < 0.65:
+                        w.floats("BEZIER_CURVE_TO", *[u(-60 - big, W + 60 + big) for _ in range(6)])
+                    elif t < 0.8:
+                        w.floats("ARC_TO", u(0, W), u(0, Hh), u(0, W), u(0, Hh), u(0, 60))
+                    else:
+                        w.floats("ARC", u(0, W), u(0, Hh), u(0, 80), u(-7, 7), u(-7, 7), int(rng.integers(0, 2)))
+                if rng.random() < 0.5:
+                    w.bare("CLOSE_PATH")
+            w.bare("FILL" if which == 0 else "STROKE")
+    return w.take(), W, Hh
+
+
 SEEDS = list(range(24))
+WIDE_SEEDS = list(range(24))
 
 
 @pytest.mark.parametrize("seed", SEEDS[:8])
@@ -103,6 +188,33 @@ def test_gpu_matches_oracle_on_random_scenes(seed):
     script = random_scene(seed)
     got = H.render_script(lib, script, SIZE, SIZE)
     want = H.render_oracle(script, SIZE, SIZE)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
+    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+
+
+@pytest.mark.parametrize("seed", WIDE_SEEDS[:8])
+def test_oracle_matches_reference_on_wide_random_scenes(seed):
+    ref = H.reference_library()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    script, w, h = random_scene_wide(seed)
+    want = H.render_script(ref, script, w, h)
+    got = H.render_oracle(script, w, h)
+    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+    assert nbad == 0, "max |diff| %.3g" % worst
+    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", WIDE_SEEDS)
+def test_gpu_matches_oracle_on_wide_random_scenes(seed):
+    lib = H.product_library()
+    if lib.cb200_device_count() < 1:
+        pytest.skip("no CUDA device")
+    script, w, h = random_scene_wide(seed)
+    got = H.render_script(lib, script, w, h)
+    want = H.render_oracle(script, w, h)
     nbad, worst = H.float_mismatch(got["f32"], want["f32"])
     assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
     assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
