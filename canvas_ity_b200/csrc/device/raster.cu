@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
                 if (jr.first_key != 0xffffffffu) {
                     int fy = int(jr.first_key >> 16), fx = int(jr.first_key & 0xffffu);
                     lx = min(lx, fx); hx = max(hx, fx); ly = min(ly, fy); hy = max(hy, fy);
-                } else { lx = full_w; hx = 0; ly = full_h; hy = 0; }
+                }
+                // nothing kept at all (columns come from runs, rows from inside runs and sideways crossings)
+                if (hx < 0 || hy < 0) { lx = full_w; hx = 0; ly = full_h; hy = 0; }
                 int left = max(lx - b, 0), right = min(hx + b, full_w) + 1;
                 int top = max(ly - b, 0), bottom = min(hy + b, full_h);
                 jr.left = left; jr.top = top;
