@@ -166,7 +166,7 @@ SEEDS = list(range(24))
 WIDE_SEEDS = list(range(24))
 
 
-@pytest.mark.parametrize("seed", SEEDS[:8])
+@pytest.mark.parametrize("seed", SEEDS)
 def test_oracle_matches_reference_on_random_scenes(seed):
     ref = H.reference_library()
     if ref is None:
@@ -193,7 +193,7 @@ def test_gpu_matches_oracle_on_random_scenes(seed):
     assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
 
 
-@pytest.mark.parametrize("seed", WIDE_SEEDS[:8])
+@pytest.mark.parametrize("seed", WIDE_SEEDS)
 def test_oracle_matches_reference_on_wide_random_scenes(seed):
     ref = H.reference_library()
     if ref is None:
