@@ -956,6 +956,124 @@ void oracle_points_in_path(const float *edges, uint32_t n_edges, const float *xy
     }
 }
 
+// Prototype bench for the shadow working rectangle ("Next"): out[0..3] = the run bounding box
+// render_shadow derives (hpp:2409-2419) from the reference's polygon clip, out[4..7] = the same box from
+// PER-EDGE clipping the way the CUDA rasteriser does it (inside pieces rasterised, excursions beside the
+// canvas represented by their exit -> entry crossing pairs).  rule: 0 = crossing pairs (clamped, dropped when
+// wholly above / below), 1 = what the CUDA path does today (projected pieces lend their column, crossings
+// their row).  Boxes are (min_x, max_x, min_y, max_y); empty = (-1, -1, -1, -1).
+int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int width, int height, int rule, int *out)
+{
+    const cb200_draw &d = frame->draws[draw_index];
+    for (int i = 0; i < 8; ++i) out[i] = -1;
+    if (d.kind == CB200_CLIP) return 0;
+    cb200_frame local = *frame;
+    std::vector<float> pts;
+    std::vector<cb200_subpath> subs;
+    if (frame->n_glyphs) {
+        expand_glyphs(frame, pts);
+        subs.assign(frame->subpaths, frame->subpaths + frame->n_subpaths);
+        for (size_t i = 0; i < subs.size(); ++i)
+            if (subs[i].instanced) { subs[i].first_point += frame->n_points; subs[i].instanced = 0; }
+        local.points = pts.data(); local.n_points = frame->n_points + frame->n_glyph_points;
+        local.subpaths = subs.data(); local.n_glyphs = 0;
+    }
+    Poly lines, work;
+    flatten(&local, d, lines);
+    if (d.kind == CB200_STROKE) {
+        if (d.n_dash) {
+            dash(lines, local.dashes + d.first_dash, d.n_dash, d.dash_offset, mat(d.inverse), work);
+            lines.pts.swap(work.pts); lines.subs.swap(work.subs);
+        }
+        StrokeStyle st;
+        st.half = d.line_width * 0.5f;
+        st.miter2 = d.miter_limit * d.miter_limit * st.half * st.half;
+        st.cap = d.cap; st.join = d.join;
+        st.fwd = mat(d.forward); st.inv = mat(d.inverse);
+        outline_stroke(lines, st, work);
+        lines.pts.swap(work.pts); lines.subs.swap(work.subs);
+    }
+    float sigma2 = 0.25f * d.shadow_blur * d.shadow_blur;
+    size_t radius = size_t(0.5f * sqrtf(4.0f * sigma2 + 1.0f) - 0.5f);
+    int border = 3 * (int(radius) + 1);
+    P off = mk(float(border) + d.shadow_offset_x, float(border) + d.shadow_offset_y);
+    const int pw = width + 2 * border, ph = height + 2 * border;
+    Coverage cov;
+    scan_convert(lines, off, pw, ph, cov);
+    if (!cov.empty()) { out[0] = cov.min_x; out[1] = cov.max_x; out[2] = cov.min_y; out[3] = cov.max_y; }
+    // ---- per-edge version ----
+    const float w = float(pw), h = float(ph);
+    int lx = 1 << 30, hx = -1, ly = 1 << 30, hy = -1;
+    long first_key = -1;
+    auto enter = [&](int x, int y) { lx = std::min(lx, x); hx = std::max(hx, x); ly = std::min(ly, y); hy = std::max(hy, y); };
+    size_t base = 0;
+    for (size_t s = 0; s < lines.subs.size(); ++s) {
+        size_t n = lines.subs[s].first;
+        struct Cross { float y; bool exits; };
+        std::vector<Cross> sideways[2];
+        for (size_t i = 0; i < n; ++i) {
+            P a = add(off, lines.pts[base + (i ? i : n) - 1]), b = add(off, lines.pts[base + i]);
+            float cut[6]; int nc = 0;
+            cut[nc++] = 0.0f;
+            auto cross_at = [](float da, float db) { return da / (da - db); };
+            if (a.x * b.x < 0.0f) cut[nc++] = cross_at(a.x, b.x);
+            if (a.y * b.y < 0.0f) cut[nc++] = cross_at(a.y, b.y);
+            if ((w - a.x) * (w - b.x) < 0.0f) cut[nc++] = cross_at(w - a.x, w - b.x);
+            if ((h - a.y) * (h - b.y) < 0.0f) cut[nc++] = cross_at(h - a.y, h - b.y);
+            std::sort(cut + 1, cut + nc);
+            cut[nc++] = 1.0f;
+            for (int side = 0; side < 2; ++side) {
+                float da = side ? w - a.x : a.x, db = side ? w - b.x : b.x;
+                if (da * db < 0.0f) { Cross c = { between(a, b, cross_at(da, db)).y, da > 0.0f }; sideways[side].push_back(c); }
+            }
+            for (int k = 0; k + 1 < nc; ++k) {
+                float t0 = cut[k], t1 = cut[k + 1];
+                if (!(t0 < t1)) continue;
+                P p0 = t0 == 0.0f ? a : between(a, b, t0), p1 = t1 == 1.0f ? b : between(a, b, t1);
+                P mid = mul(0.5f, add(p0, p1));
+                if (!(mid.y >= 0.0f && mid.y <= h)) continue;
+                bool projected = mid.x < 0.0f || mid.x > w;
+                Coverage one;
+                one.rows = ph + 2;
+                one.row.assign(size_t(one.rows), std::vector<Delta>());
+                edge_deltas(one, mk(std::min(std::max(p0.x, 0.0f), w), std::min(std::max(p0.y, 0.0f), h)),
+                            mk(std::min(std::max(p1.x, 0.0f), w), std::min(std::max(p1.y, 0.0f), h)));
+                for (int y = 0; y < one.rows; ++y)
+                    for (size_t r = 0; r < one.row[size_t(y)].size(); ++r) {
+                        const Delta &e = one.row[size_t(y)][r];
+                        if (!projected) {
+                            long key = (long(y) << 16) | long(e.x);
+                            if (first_key < 0 || key < first_key) first_key = key;
+                            if (e.d != 0.0f) enter(int(e.x), y);
+                        } else if (rule == 1 && e.d != 0.0f) { lx = std::min(lx, int(e.x)); hx = std::max(hx, int(e.x)); }
+                    }
+            }
+        }
+        for (int side = 0; side < 2; ++side) {
+            std::vector<Cross> &c = sideways[side];
+            const int col = side ? int(w) : 0;
+            auto row_of = [&](float y) { return std::min(int(floorf(std::min(std::max(y, 0.0f), h))), ph - 1); };
+            if (rule == 1) {
+                for (size_t k = 0; k < c.size(); ++k) { ly = std::min(ly, row_of(c[k].y)); hy = std::max(hy, row_of(c[k].y)); }
+            } else {
+                for (size_t k = 0; k < c.size(); ++k) {
+                    if (!c[k].exits) continue;
+                    const Cross &in = c[(k + 1) % c.size()];           // crossings alternate along a closed loop
+                    float y1 = c[k].y, y2 = in.y;
+                    if ((y1 < 0.0f && y2 < 0.0f) || (y1 > h && y2 > h)) continue;
+                    if (row_of(y1) == row_of(y2) && std::min(std::max(y1, 0.0f), h) == std::min(std::max(y2, 0.0f), h)) continue;
+                    enter(col, row_of(y1));
+                    enter(col, row_of(y2));
+                }
+            }
+        }
+        base += n;
+    }
+    if (first_key >= 0) enter(int(first_key & 0xffff), int(first_key >> 16));
+    if (hx >= 0 && hy >= 0) { out[4] = lx; out[5] = hx; out[6] = ly; out[7] = hy; }
+    return border;
+}
+
 void oracle_tap_frame(void *user, const cb200_frame *frame) { oracle_submit(user, frame); }
 void oracle_tap_read(void *user, uint8_t *dst, int w, int h, int stride, int x, int y)
 {
