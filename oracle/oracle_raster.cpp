@@ -1009,8 +1009,10 @@ int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int
     size_t base = 0;
     for (size_t s = 0; s < lines.subs.size(); ++s) {
         size_t n = lines.subs[s].first;
-        struct Cross { float y; bool exits; };
+        struct Cross { float y; bool exits; float at; };          // `at` = edge index + parameter: position along the loop
         std::vector<Cross> sideways[2];
+        struct Top { float x; bool leaves; float at; };
+        std::vector<Top> tops;                                      // crossings of y = 0 (rule 2)
         for (size_t i = 0; i < n; ++i) {
             P a = add(off, lines.pts[base + (i ? i : n) - 1]), b = add(off, lines.pts[base + i]);
             float cut[6]; int nc = 0;
@@ -1024,8 +1026,9 @@ int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int
             cut[nc++] = 1.0f;
             for (int side = 0; side < 2; ++side) {
                 float da = side ? w - a.x : a.x, db = side ? w - b.x : b.x;
-                if (da * db < 0.0f) { Cross c = { between(a, b, cross_at(da, db)).y, da > 0.0f }; sideways[side].push_back(c); }
+                if (da * db < 0.0f) { Cross c = { between(a, b, cross_at(da, db)).y, da > 0.0f, float(i) + cross_at(da, db) }; sideways[side].push_back(c); }
             }
+            if (a.y * b.y < 0.0f) { Top tc = { between(a, b, cross_at(a.y, b.y)).x, a.y > 0.0f, float(i) + cross_at(a.y, b.y) }; tops.push_back(tc); }
             for (int k = 0; k + 1 < nc; ++k) {
                 float t0 = cut[k], t1 = cut[k + 1];
                 if (!(t0 < t1)) continue;
@@ -1056,6 +1059,21 @@ int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int
             if (rule == 1) {
                 for (size_t k = 0; k < c.size(); ++k) { ly = std::min(ly, row_of(c[k].y)); hy = std::max(hy, row_of(c[k].y)); }
             } else {
+                if (rule == 2 && side == 1) {
+                    // The right edge is clipped AFTER the top one (hpp:2208-2229 goes left, top, right, bottom):
+                    // crossings above the canvas are gone by then; instead a top boundary segment that
+                    // straddles x = w is cut there.
+                    std::vector<Cross> kept;
+                    for (size_t k = 0; k < c.size(); ++k) if (c[k].y >= 0.0f) kept.push_back(c[k]);
+                    for (size_t k = 0; k < tops.size(); ++k) {
+                        if (!tops[k].leaves) continue;
+                        const Top &back = tops[(k + 1) % tops.size()];
+                        float x1 = std::max(tops[k].x, 0.0f), x2 = std::max(back.x, 0.0f);
+                        if ((w - x1) * (w - x2) < 0.0f) { Cross sc = { 0.0f, x1 < w, x1 < w ? tops[k].at : back.at }; kept.push_back(sc); }
+                    }
+                    std::sort(kept.begin(), kept.end(), [](const Cross &p, const Cross &q) { return p.at < q.at; });
+                    c.swap(kept);
+                }
                 for (size_t k = 0; k < c.size(); ++k) {
                     if (!c[k].exits) continue;
                     const Cross &in = c[(k + 1) % c.size()];           // crossings alternate along a closed loop

@@ -11,10 +11,13 @@ orc.oracle_debug_shadow_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_i
 orc.oracle_debug_shadow_boxes.restype = C.c_int
 DRAW_BYTES = 140
 import struct
-for rule in (0, 1):
+NA = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 900
+FIRST = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for rule in (2, 0, 1):          # 2 = pairs + clip order (left, top, right, bottom); 0 = pairs; 1 = today's CUDA rule (modelled)
     bad, total, bad_seeds = 0, 0, []
-    for gen, count in (("a", 400), ("b", 900)):
-        for seed in range(count):
+    for gen, count in (("a", NA), ("b", NB)):
+        for seed in range(FIRST, FIRST + count):
             if gen == "a": script, w, h = random_scene(seed), SIZE, SIZE
             else: script, w, h = random_scene_wide(seed)
             for fr in H.lower_script(script, w, h):
