@@ -218,3 +218,30 @@ def test_gpu_matches_oracle_on_wide_random_scenes(seed):
     nbad, worst = H.float_mismatch(got["f32"], want["f32"])
     assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
     assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+
+
+def test_exact_shadow_rectangle_rule_matches_the_reference_clip():
+    """The per-edge rule the CUDA rasteriser is to adopt for render_shadow's working rectangle (Next 1):
+    oracle_debug_shadow_boxes computes the box from the reference's polygon clip and from per-edge clipping with
+    paired crossings + clip order; they must agree on every shadowed draw of the committed scenes."""
+    import ctypes as C
+    import struct
+    orc = H.oracle_library()
+    orc.oracle_debug_shadow_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 8)]
+    orc.oracle_debug_shadow_boxes.restype = C.c_int
+    checked = 0
+    scenes = [(random_scene(s), SIZE, SIZE) for s in SEEDS] + [random_scene_wide(s) for s in range(120)]
+    for script, w, h in scenes:
+        for fr in H.lower_script(script, w, h):
+            draws = bytes(fr.parts["draws"])
+            for di in range(fr.n_draws):
+                rec = draws[di * 140:(di + 1) * 140]
+                kind = struct.unpack_from("<I", rec, 0)[0]
+                color_a, off_x, off_y, blur = struct.unpack_from("<4f", rec, 120)
+                if kind == 2 or color_a == 0.0 or (blur == 0.0 and off_x == 0.0 and off_y == 0.0):
+                    continue
+                out = (C.c_int * 8)()
+                orc.oracle_debug_shadow_boxes(C.addressof(fr.frame), di, w, h, 2, C.byref(out))
+                assert list(out[0:4]) == list(out[4:8]), (w, h, di)
+                checked += 1
+    assert checked > 100
