@@ -12,6 +12,7 @@
 //
 // There is no CPU fallback here: without a CUDA device cb200_canvas_create fails.
 #include "device/frame.cuh"
+#include "device/edge_clip.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -122,7 +123,8 @@ struct cb200_canvas {
     dev_buf<float4> pieces, texels;
     dev_buf<comp_rec> comp;
     dev_buf<uint2> job_box;
-    dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count;
+    dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count, loop_mark;
+    dev_buf<uint2> box_loops;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -468,6 +470,10 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->visit_close.reserve(size_t(want_pts) + 6 * size_t(want_sources) + 4));
     CK(cv->half_last.reserve(2 * size_t(want_sources) + 4));
     CK(cv->loops.reserve(sf.subpaths.size() + want_dash_sub + 2 * size_t(want_sources) + 2));
+    if (!sf.shadow_jobs.empty()) {
+        CK(cv->loop_mark.reserve(cv->loops.cap));
+        CK(cv->box_loops.reserve(cv->loops.cap));
+    }
     CK(cv->pieces.reserve(3 * size_t(want_items)));
     CK(cv->piece_job.reserve(3 * size_t(want_items)));
     CK(cv->piece_rows.reserve(3 * size_t(want_items)));
@@ -698,6 +704,7 @@ int upload_frame(cb200_canvas *cv)
     f.row_runs = cv->row_runs.p; f.row_piece = cv->row_piece.p; f.cap_rows = cv->cap_rows;
     f.keys[0] = cv->keys0.p; f.keys[1] = cv->keys1.p; f.vals[0] = cv->vals0.p; f.vals[1] = cv->vals1.p;
     f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p; f.long_rows = cv->long_rows.p;
+    f.loop_mark = cv->loop_mark.p; f.box_loops = cv->box_loops.p;
     f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
     f.cap_tiles = cv->cap_tiles;
     f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
@@ -725,7 +732,7 @@ int frame_launch_count(const cb200_canvas *cv)
     const device_frame &f = cv->df;
     return (sf.glyph_insts.empty() ? 0 : 1) + (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
            ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-           (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
+           (sf.shadow_jobs.empty() ? 0 : 2 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
 }
 
 // The fixed launch sequence of one frame, issued into the canvas stream -- or, with `in_graph`, into a
@@ -738,6 +745,7 @@ int enqueue_frame(cb200_canvas *cv, bool in_graph)
     cudaStream_t s = cv->stream;
     auto mark = [&](cudaEvent_t e) { return in_graph ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
     CK(cudaMemsetAsync(cv->partials.p, 0, sizeof(uint32_t) * 8 * kGrid, s));
+    if (f.n_shadow_jobs) CK(cudaMemsetAsync(cv->loop_mark.p, 0, sizeof(uint32_t) * f.cap_loops, s));
     // Stage events sit between kernels and so cut the programmatic-dependent-launch chain there;
     // with stage timing off only the frame and the compositor are bracketed.
     const bool stages = cv->stage_timing && !in_graph;
@@ -1088,7 +1096,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
-    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release();
+    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release();
     drop_replay_graphs(cv);
     cv->png_tables.release(); cv->png_row_crc.release(); cv->png_out.release(); cv->png_acc.release();
     cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();
@@ -1516,6 +1524,47 @@ int cb200_get_stats(cb200_canvas *cv, cb200_stats *out)
     cv->stats.kernel_launches = cv->launches;
     *out = cv->stats;
     return CB200_OK;
+}
+
+// Host build of what the device enters into a shadow job's run bounding box for ONE closed loop of `n`
+// points (device/edge_clip.cuh: clip_edge + the per-scanline add_runs of k_row_emit for the inside pieces,
+// the boundary-segment walk of k_shadow_boxes for the rest).  box5 = (min_x, max_x, min_y, max_y, first run
+// key y << 16 | x or -1); max < 0 when the loop enters nothing.  No device is touched: the CPU test feeds it
+// the fuzz scenes' outlines and compares with the reference's polygon clip.
+void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h, int *box5)
+{
+    struct bounds_sink {
+        int lo_x, hi_x;
+        void put(float px, float delta) { if (delta != 0.0f) { lo_x = std::min(lo_x, int(px)); hi_x = std::max(hi_x, int(px)); } }
+    };
+    const float w = float(padded_w), h = float(padded_h);
+    shadow_box_walk walk;
+    walk.init(w, h);
+    int lx = 0x7fffffff, ly = 0x7fffffff, hx = -1, hy = -1;
+    long first_key = -1;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t q = k ? k - 1 : n - 1;
+        clipped_edge ce;
+        clip_edge(v2(off_x + xy[2 * q], off_y + xy[2 * q + 1]), v2(off_x + xy[2 * k], off_y + xy[2 * k + 1]), w, h, ce);
+        for (int e = 0; e < ce.n_events; ++e) walk.consume(ce.ev[e].kind, ce.ev[e].v);
+        for (int i = 0; i < ce.n_pieces; ++i) {
+            const float4 pc = ce.piece[i];
+            if (ce.projected[i] || fabsf(pc.w - pc.y) < 2.0e-5f) continue;
+            const edge_walk ew = edge_setup(pc);
+            for (int r = 0; r < ew.rows; ++r) {
+                const row_walk rw = row_setup(ew, r);
+                if (int(rw.py) < 0 || int(rw.py) >= padded_h) continue;        // k_edges keeps rows [0, padded_h)
+                bounds_sink sink = { 0x7fffffff, -1 };
+                walk_row_runs(ew, rw, sink);
+                if (sink.hi_x >= 0) { lx = std::min(lx, sink.lo_x); hx = std::max(hx, sink.hi_x); ly = std::min(ly, int(rw.py)); hy = std::max(hy, int(rw.py)); }
+                const long key = (long(rw.py) << 16) | long(rw.px);
+                if (first_key < 0 || key < first_key) first_key = key;
+            }
+        }
+    }
+    walk.finish();
+    if (walk.hx >= 0) { lx = std::min(lx, walk.lx); hx = std::max(hx, walk.hx); ly = std::min(ly, walk.ly); hy = std::max(hy, walk.hy); }
+    box5[0] = lx; box5[1] = hx; box5[2] = ly; box5[3] = hy; box5[4] = int(first_key);
 }
 
 int64_t cb200_debug_lines(cb200_canvas *cv, float *edges, uint32_t *job_of_edge, int64_t capacity)

@@ -145,6 +145,7 @@ struct frame_header {
     uint32_t n_runs;
     uint32_t n_tile_entries;
     uint32_t n_long_rows;                  // scanline segments handed to k_rows_long
+    uint32_t n_box_loops;                  // loops of shadow jobs that cross a side or the top of the padded canvas
     uint64_t plane_floats;               // storage (pitched)
     uint64_t shadow_working_pixels;      // sum of bw * bh: what the reference blurs (hpp:2426)
     uint32_t overflow;                     // bit set: which capacity was exceeded

@@ -17,65 +17,11 @@
 //   k_job_tiles   one CTA: bounding boxes -> tile rectangles, tile-entry bases,
 //                 shadow working rectangles and plane storage (hpp:2409-2428)
 #include "frame.cuh"
+#include "edge_clip.cuh"
 
 namespace cb200 {
 
 namespace {
-
-struct edge_walk {
-    vec2 from, to;
-    float sign, ystep, dxdy, dydx, fx0, fy0;
-    bool vertical, down;
-    int rows;                  // scanlines the reference loop would visit
-};
-
-__device__ __forceinline__ edge_walk edge_setup(float4 pc)
-{
-    edge_walk e;
-    vec2 a = v2(pc.x, pc.y), b = v2(pc.z, pc.w);
-    e.sign = b.y > a.y ? 1.0f : -1.0f;
-    if (a.x > b.x) { vec2 t = a; a = b; b = t; }          // always walk left to right
-    e.from = a; e.to = b;
-    e.down = b.y > a.y;
-    e.ystep = e.down ? 1.0f : -1.0f;
-    e.dxdy = (b.x - a.x) / (b.y - a.y);
-    e.dydx = (b.y - a.y) / (b.x - a.x);
-    e.vertical = b.x - a.x < 2.0e-5f;
-    e.fx0 = floorf(a.x);
-    e.fy0 = floorf(a.y);
-    e.rows = e.down ? int(ceilf(b.y) - e.fy0) : int(e.fy0 - floorf(b.y)) + 1;
-    return e;
-}
-
-struct row_walk {
-    vec2 now, stop;            // entry / exit of the edge in this scanline
-    float px, py;              // first pixel touched
-    int inner;                 // pixels crossed before the last one
-};
-
-__device__ __forceinline__ float edge_x_at(const edge_walk &e, float y) { return (y - e.from.y) * e.dxdy + e.from.x; }
-__device__ __forceinline__ float edge_y_at(const edge_walk &e, float x) { return (x - e.from.x) * e.dydx + e.from.y; }
-
-__device__ __forceinline__ row_walk row_setup(const edge_walk &e, int r)
-{
-    row_walk w;
-    float fr = float(r);
-    if (e.down) {
-        w.py = e.fy0 + fr;
-        float y_in = e.fy0 + fr, y_out = e.fy0 + fr + 1.0f;
-        w.now = r == 0 ? e.from : v2(edge_x_at(e, y_in), y_in);
-        w.stop = e.to.y < y_out ? e.to : v2(edge_x_at(e, y_out), y_out);
-    } else {
-        w.py = e.fy0 - fr;
-        float y_in = e.fy0 - fr + 1.0f, y_out = e.fy0 - fr;
-        w.now = r == 0 ? e.from : v2(edge_x_at(e, y_in), y_in);
-        w.stop = e.to.y > y_out ? e.to : v2(edge_x_at(e, y_out), y_out);
-    }
-    w.px = (r == 0 || e.vertical) ? e.fx0 : fmaxf(e.fx0, ceilf(w.now.x) - 1.0f);
-    float crossed = e.vertical ? 0.0f : ceilf(w.stop.x) - 1.0f - w.px;
-    w.inner = crossed > 0.0f ? int(crossed) : 0;
-    return w;
-}
 
 // ------------------------------------------------------------- job items ----
 
@@ -125,10 +71,6 @@ __global__ void __launch_bounds__(kBlock) k_job_items(device_frame f)
 }
 
 // ------------------------------------------------------------------ edges ----
-
-// Parameter at which a->b crosses the line `side == 0`, the same ratio
-// Sutherland-Hodgman uses (hpp:2220-2222); only meaningful when sa * sb < 0.
-__device__ __forceinline__ float cross_at(float sa, float sb) { return sa / (sa - sb); }
 
 // Work mapping of the four kernels below: a CTA owns a contiguous slice of the items in whole
 // tiles of kBlock, and thread t takes item `tile + t` -- neighbouring lanes read and write
@@ -182,52 +124,29 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
         uint32_t q = p == loop.first ? loop.first + loop.count - 1 : p - 1;
         float2 pa = f.pts[q], pb = f.pts[p];
         vec2 a = v2(job.off_x + pa.x, job.off_y + pa.y), b = v2(job.off_x + pb.x, job.off_y + pb.y);
-        float w = float(t.width + job.pad), hgt = float(t.height + job.pad);
-        // crossing parameters with the four clip lines, in increasing order
-        float cut[6];
-        int nc = 0;
-        cut[nc++] = 0.0f;
-        if (a.x * b.x < 0.0f) cut[nc++] = cross_at(a.x, b.x);
-        if (a.y * b.y < 0.0f) cut[nc++] = cross_at(a.y, b.y);
-        if ((w - a.x) * (w - b.x) < 0.0f) cut[nc++] = cross_at(w - a.x, w - b.x);
-        if ((hgt - a.y) * (hgt - b.y) < 0.0f) cut[nc++] = cross_at(hgt - a.y, hgt - b.y);
-        for (int i = 2; i < nc; ++i) {
-            float v = cut[i];
-            int m = i - 1;
-            for (; m >= 1 && v < cut[m]; --m) cut[m + 1] = cut[m];
-            cut[m + 1] = v;
-        }
-        cut[nc++] = 1.0f;
-        if (job.kind == JOB_SHADOW) {
-            // Where the outline leaves or enters the padded canvas sideways, the reference's polygon clip
-            // starts / ends a boundary segment (hpp:2208-2229) whose runs count in render_shadow's bounding
-            // box (hpp:2409-2419).  Projected pieces do not lend their rows to that box (k_row_emit), and
-            // the inside piece that meets the crossing may be horizontal and emit nothing, so the
-            // crossing's own scanline is entered here.
-            for (int side = 0; side < 2; ++side) {
-                const float da = side ? w - a.x : a.x, db = side ? w - b.x : b.x;
-                if (da * db < 0.0f) {
-                    const float yc = fminf(fmaxf(mix(a, b, cross_at(da, db)).y, 0.0f), hgt);
-                    const int row = min(int(floorf(yc)), int(hgt) - 1);
-                    atomicMin(&f.jobs[j].run_min_y, row);
-                    atomicMax(&f.jobs[j].run_max_y, row);
-                }
-            }
+        const float w = float(t.width + job.pad), hgt = float(t.height + job.pad);
+        // the reference's four clip stages applied to this edge alone (edge_clip.cuh): the surviving part has
+        // the polygon clip's own end points, the parts cut away beside the canvas are projected onto its sides
+        clipped_edge ce;
+        clip_edge(a, b, w, hgt, ce);
+        if (job.kind == JOB_SHADOW && ce.n_events) {
+            // The reference's polygon clip joins every sideways exit of a loop to the next entry by a boundary
+            // segment whose runs count in render_shadow's bounding box (hpp:2208-2229, 2409-2419); projected
+            // pieces do not reproduce that (k_row_emit ignores them for the box).  A loop with any crossing of
+            // a side or of the top is listed once; k_shadow_boxes walks its crossings in order.
+            const uint32_t loop_id = f.pt_loop[p];
+            if (atomicExch(&f.loop_mark[loop_id], 1u) == 0u)
+                f.box_loops[atomicAdd(&h->n_box_loops, 1u)] = make_uint2(j, loop_id);
         }
         int row0 = job.kind == JOB_SHADOW ? 0 : t.band_y0;
         int row1 = job.kind == JOB_SHADOW ? t.height + job.pad : t.band_y0 + t.band_rows;
         int made = 0;
-        for (int i = 0; i + 1 < nc; ++i) {
-            float t0 = cut[i], t1 = cut[i + 1];
-            if (!(t0 < t1)) continue;
-            vec2 p0 = t0 == 0.0f ? a : mix(a, b, t0), p1 = t1 == 1.0f ? b : mix(a, b, t1);
-            vec2 mid = 0.5f * (p0 + p1);
-            if (!(mid.y >= 0.0f && mid.y <= hgt)) continue;          // above / below: no area
-            // left / right of the canvas: project onto the boundary (clamp); inside: keep
-            float4 pc = make_float4(fminf(fmaxf(p0.x, 0.0f), w), fminf(fmaxf(p0.y, 0.0f), hgt),
-                                    fminf(fmaxf(p1.x, 0.0f), w), fminf(fmaxf(p1.y, 0.0f), hgt));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (i >= ce.n_pieces) continue;
+            const float4 pc = ce.piece[i];
             uint32_t rows = 0, rlo = 0;
-            if (!(fabsf(pc.w - pc.y) < 2.0e-5f) && made < 3) {
+            if (!(fabsf(pc.w - pc.y) < 2.0e-5f)) {
                 edge_walk e = edge_setup(pc);
                 // scanlines inside [row0, row1)
                 int r_first, r_last;                       // inclusive range of r
@@ -245,19 +164,17 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
                     by0 = min(by0, y_lo); by1 = max(by1, y_hi);
                 }
             }
-            if (made < 3) {
-                uint32_t slot = it * 3 + made;
-                f.pieces[slot] = pc;
-                // bit 31: the piece lies left / right of the padded canvas and was projected onto its boundary.
-                // Its runs only cancel one another; the reference's Sutherland-Hodgman clip replaces such an
-                // excursion by ONE boundary segment between the two crossing points (hpp:2208-2229), so these
-                // runs must not widen the bounding box render_shadow takes from the runs (hpp:2409-2419).
-                f.piece_job[slot] = j | ((mid.x < 0.0f || mid.x > w) ? 0x80000000u : 0u);
-                f.piece_rows[slot] = rows;
-                f.piece_rlo[slot] = rlo;
-                sum += rows;
-                ++made;
-            }
+            uint32_t slot = it * 3 + made;
+            f.pieces[slot] = pc;
+            // bit 31: the piece lies left / right of the padded canvas and was projected onto its boundary.
+            // Its runs only cancel one another; the reference's clip replaces such an excursion by ONE
+            // boundary segment between the two crossing points (hpp:2208-2229), so these runs must not widen
+            // the bounding box render_shadow takes from the runs (hpp:2409-2419).
+            f.piece_job[slot] = j | (ce.projected[i] ? 0x80000000u : 0u);
+            f.piece_rows[slot] = rows;
+            f.piece_rlo[slot] = rlo;
+            sum += rows;
+            ++made;
         }
         for (; made < 3; ++made) f.piece_rows[it * 3 + made] = 0;
         }
@@ -358,6 +275,18 @@ __global__ void __launch_bounds__(kBlock) k_row_count(device_frame f)
     finish_partials(f.partials + 5 * kGrid, &h->tickets[5], &h->n_runs, sm);
 }
 
+// walk_row_runs sink: (key, delta) pairs of one scanline, and the columns of its non-zero deltas
+struct run_sink {
+    uint64_t *keys; float *vals; uint64_t row_key;
+    int lo_x, hi_x;
+    __device__ __forceinline__ void put(float px, float delta)
+    {
+        *keys++ = row_key | uint64_t(uint32_t(px));
+        *vals++ = delta;
+        if (delta != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
+    }
+};
+
 __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
 {
     grid_dependency_wait();
@@ -386,46 +315,73 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         const bool projected = (tagged >> 31) != 0;              // an excursion outside the canvas, flattened onto its boundary
         edge_walk e = edge_setup(f.pieces[slot]);
         row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
-        uint64_t row_key = ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx;
-        bool shadow = f.jobs[j].kind == JOB_SHADOW;
-        int lo_x = 0x7fffffff, hi_x = -1;
-        vec2 cur = w.now;
-        float px = w.px, carry_area = 0.0f;
-        for (int c = 0; c < w.inner; ++c) {
-            float gx = px + 1.0f;
-            vec2 nx = v2(gx, edge_y_at(e, gx));
-            float strip = clamp01((nx.y - cur.y) * e.ystep);
-            float mid = (nx.x + cur.x) * 0.5f;
-            float area = (mid - px) * strip;
-            float delta = (carry_area + strip - area) * e.sign;
-            keys[at] = row_key | uint64_t(uint32_t(px));
-            vals[at] = delta;
-            ++at;
-            if (delta != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
-            carry_area = area;
-            cur = nx;
-            px = gx;
-        }
-        float strip = clamp01((w.stop.y - cur.y) * e.ystep);
-        float mid = (w.stop.x + cur.x) * 0.5f;
-        float area = (mid - px) * strip;
-        float d0 = (carry_area + strip - area) * e.sign, d1 = area * e.sign;
-        keys[at] = row_key | uint64_t(uint32_t(px));         vals[at] = d0; ++at;
-        keys[at] = row_key | uint64_t(uint32_t(px + 1.0f));  vals[at] = d1; ++at;
-        if (shadow) {
+        run_sink sink = { keys + at, vals + at, ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx, 0x7fffffff, -1 };
+        walk_row_runs(e, w, sink);
+        if (f.jobs[j].kind == JOB_SHADOW) {
             // exact bounds of the runs the reference keeps (non-zero deltas) plus the
             // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252).  A projected
-            // piece only lends its column (the boundary column the reference's clip segment also
-            // touches): its rows may overshoot the two crossing points that segment joins, and the
-            // neighbouring inside pieces already reach those.
-            if (d0 != 0.0f) { lo_x = min(lo_x, int(px)); hi_x = max(hi_x, int(px)); }
-            if (d1 != 0.0f) { lo_x = min(lo_x, int(px) + 1); hi_x = max(hi_x, int(px) + 1); }
+            // piece enters nothing: its runs only cancel one another, and the boundary segment the
+            // reference's clip puts in its place is accounted for by k_shadow_boxes.
             job_rec &jr = f.jobs[j];
-            if (hi_x >= 0) {
-                atomicMin(&jr.run_min_x, lo_x); atomicMax(&jr.run_max_x, hi_x);
-                if (!projected) { atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py)); }
+            if (sink.hi_x >= 0 && !projected) {
+                atomicMin(&jr.run_min_x, sink.lo_x); atomicMax(&jr.run_max_x, sink.hi_x);
+                atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py));
             }
             if (!projected) atomicMin(&jr.first_key, (uint32_t(w.py) << 16) | uint32_t(w.px));
+        }
+    }
+}
+
+// ---------------------------------------------------------- shadow boxes ----
+
+// One warp per listed loop (a loop of a shadow job that crosses a side or the top of its padded canvas):
+// lanes take 32 consecutive edges, the lanes that found crossings feed them in edge order to the walk of
+// shadow_box.cuh (its state is replicated in every lane), and lane 0 enters what the reference's boundary
+// segments add to the job's run bounding box.
+__global__ void __launch_bounds__(kBlock) k_shadow_boxes(device_frame f, canvas_target t)
+{
+    grid_dependency_wait();
+    frame_header *h = f.hdr;
+    if (h->overflow) return;
+    const uint32_t n = h->n_box_loops;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += n_warps) {
+        const uint2 item = f.box_loops[i];
+        const job_rec &job = f.jobs[item.x];
+        const loop_span loop = f.loops[item.y];
+        const float w = float(t.width + job.pad), hgt = float(t.height + job.pad);
+        shadow_box_walk walk;
+        walk.init(w, hgt);
+        for (uint32_t base = 0; base < loop.count; base += 32) {
+            const uint32_t k = base + uint32_t(lane);
+            clipped_edge ce;
+            ce.n_events = 0;
+            ce.ev[0].v = ce.ev[1].v = ce.ev[2].v = 0.0f; ce.ev[0].kind = ce.ev[1].kind = ce.ev[2].kind = 0;
+            if (k < loop.count) {
+                const uint32_t p = loop.first + k, q = k ? p - 1 : loop.first + loop.count - 1;
+                const float2 pa = f.pts[q], pb = f.pts[p];
+                clip_edge(v2(job.off_x + pa.x, job.off_y + pa.y), v2(job.off_x + pb.x, job.off_y + pb.y), w, hgt, ce);
+            }
+            const int nev = ce.n_events;
+            uint32_t mask = __ballot_sync(0xffffffffu, nev > 0);
+            while (mask) {
+                const int src = __ffs(int(mask)) - 1;
+                mask &= mask - 1;
+                const int n_src = __shfl_sync(0xffffffffu, nev, src);
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const float v = __shfl_sync(0xffffffffu, ce.ev[e].v, src);
+                    const int kind = __shfl_sync(0xffffffffu, ce.ev[e].kind, src);
+                    if (e < n_src) walk.consume(kind, v);
+                }
+            }
+        }
+        walk.finish();
+        if (lane == 0 && walk.hx >= 0) {
+            job_rec &jr = f.jobs[item.x];
+            atomicMin(&jr.run_min_x, walk.lx); atomicMax(&jr.run_max_x, walk.hx);
+            atomicMin(&jr.run_min_y, walk.ly); atomicMax(&jr.run_max_y, walk.hy);
         }
     }
 }
@@ -570,6 +526,7 @@ void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s
     launch_pdl(k_scan_rows, kGrid, kBlock, 0, s, f);
     launch_pdl(k_row_count, kGrid, kBlock, 0, s, f);
     launch_pdl(k_row_emit, kGrid, kBlock, 0, s, f);
+    if (f.n_shadow_jobs) launch_pdl(k_shadow_boxes, kGrid, kBlock, 0, s, f, t);
     launch_pdl(k_job_tiles, 1, kBlock, 0, s, f, t);
     launch_pdl(k_clear_tiles, kGrid, kBlock, 0, s, f);
 }

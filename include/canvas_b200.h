@@ -308,6 +308,13 @@ int64_t cb200_debug_lines(cb200_canvas *canvas, float *xy_pairs, uint32_t *job_o
                           int64_t capacity);       /* edges: 4 floats each */
 int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative,
                          int64_t capacity);        /* sorted (job,y,x) runs */
+/* Host build of what the device enters into a shadow's run bounding box (render_shadow hpp:2409-2419 over the
+ * polygon clip of hpp:2208-2229) for the closed loop xy[0 .. n), offset by (off_x, off_y) into a padded
+ * canvas of padded_w x padded_h: csrc/device/edge_clip.cuh compiled for the host.  box5 = (min_x, max_x,
+ * min_y, max_y, key of the loop's first run y << 16 | x or -1); max < 0 when nothing.  Touches no device:
+ * the CPU test checks the rule against the reference's clip. */
+void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
+                            int *box5);
 
 const char *cb200_last_error(void);
 int cb200_abi_version(void);

@@ -956,13 +956,16 @@ void oracle_points_in_path(const float *edges, uint32_t n_edges, const float *xy
     }
 }
 
-// Prototype bench for the shadow working rectangle ("Next"): out[0..3] = the run bounding box
-// render_shadow derives (hpp:2409-2419) from the reference's polygon clip, out[4..7] = the same box from
-// PER-EDGE clipping the way the CUDA rasteriser does it (inside pieces rasterised, excursions beside the
-// canvas represented by their exit -> entry crossing pairs).  rule: 0 = crossing pairs (clamped, dropped when
-// wholly above / below), 1 = what the CUDA path does today (projected pieces lend their column, crossings
-// their row).  Boxes are (min_x, max_x, min_y, max_y); empty = (-1, -1, -1, -1).
-int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int width, int height, int rule, int *out)
+// The check of the CUDA path's working-rectangle rule (canvas_ity_b200/csrc/device/edge_clip.cuh) that runs
+// without a GPU: out[0..3] = the run bounding box render_shadow derives (hpp:2409-2419) from the reference's
+// polygon clip (scan_convert above); out[4..7] = the join of what `per_loop` -- the product's own host build
+// of its per-edge clip, scanline walk and boundary-segment walk, cb200_debug_shadow_box -- reports for each
+// loop of the draw's outline.  per_loop(xy, n, off_x, off_y, padded_w, padded_h, box5): box5 = (min_x, max_x,
+// min_y, max_y, first run key y << 16 | x or -1).  Boxes are (min_x, max_x, min_y, max_y); empty = all -1.
+typedef void (*loop_box_fn)(const float *xy, uint32_t n, float off_x, float off_y, int pw, int ph, int *box5);
+
+int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int width, int height,
+                              loop_box_fn per_loop, int *out)
 {
     const cb200_draw &d = frame->draws[draw_index];
     for (int i = 0; i < 8; ++i) out[i] = -1;
@@ -1001,89 +1004,17 @@ int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int
     Coverage cov;
     scan_convert(lines, off, pw, ph, cov);
     if (!cov.empty()) { out[0] = cov.min_x; out[1] = cov.max_x; out[2] = cov.min_y; out[3] = cov.max_y; }
-    // ---- per-edge version ----
-    const float w = float(pw), h = float(ph);
     int lx = 1 << 30, hx = -1, ly = 1 << 30, hy = -1;
     long first_key = -1;
     auto enter = [&](int x, int y) { lx = std::min(lx, x); hx = std::max(hx, x); ly = std::min(ly, y); hy = std::max(hy, y); };
     size_t base = 0;
     for (size_t s = 0; s < lines.subs.size(); ++s) {
         size_t n = lines.subs[s].first;
-        struct Cross { float y; bool exits; float at; };          // `at` = edge index + parameter: position along the loop
-        std::vector<Cross> sideways[2];
-        struct Top { float x; bool leaves; float at; };
-        std::vector<Top> tops;                                      // crossings of y = 0 (rule 2)
-        for (size_t i = 0; i < n; ++i) {
-            P a = add(off, lines.pts[base + (i ? i : n) - 1]), b = add(off, lines.pts[base + i]);
-            float cut[6]; int nc = 0;
-            cut[nc++] = 0.0f;
-            auto cross_at = [](float da, float db) { return da / (da - db); };
-            if (a.x * b.x < 0.0f) cut[nc++] = cross_at(a.x, b.x);
-            if (a.y * b.y < 0.0f) cut[nc++] = cross_at(a.y, b.y);
-            if ((w - a.x) * (w - b.x) < 0.0f) cut[nc++] = cross_at(w - a.x, w - b.x);
-            if ((h - a.y) * (h - b.y) < 0.0f) cut[nc++] = cross_at(h - a.y, h - b.y);
-            std::sort(cut + 1, cut + nc);
-            cut[nc++] = 1.0f;
-            for (int side = 0; side < 2; ++side) {
-                float da = side ? w - a.x : a.x, db = side ? w - b.x : b.x;
-                if (da * db < 0.0f) { Cross c = { between(a, b, cross_at(da, db)).y, da > 0.0f, float(i) + cross_at(da, db) }; sideways[side].push_back(c); }
-            }
-            if (a.y * b.y < 0.0f) { Top tc = { between(a, b, cross_at(a.y, b.y)).x, a.y > 0.0f, float(i) + cross_at(a.y, b.y) }; tops.push_back(tc); }
-            for (int k = 0; k + 1 < nc; ++k) {
-                float t0 = cut[k], t1 = cut[k + 1];
-                if (!(t0 < t1)) continue;
-                P p0 = t0 == 0.0f ? a : between(a, b, t0), p1 = t1 == 1.0f ? b : between(a, b, t1);
-                P mid = mul(0.5f, add(p0, p1));
-                if (!(mid.y >= 0.0f && mid.y <= h)) continue;
-                bool projected = mid.x < 0.0f || mid.x > w;
-                Coverage one;
-                one.rows = ph + 2;
-                one.row.assign(size_t(one.rows), std::vector<Delta>());
-                edge_deltas(one, mk(std::min(std::max(p0.x, 0.0f), w), std::min(std::max(p0.y, 0.0f), h)),
-                            mk(std::min(std::max(p1.x, 0.0f), w), std::min(std::max(p1.y, 0.0f), h)));
-                for (int y = 0; y < one.rows; ++y)
-                    for (size_t r = 0; r < one.row[size_t(y)].size(); ++r) {
-                        const Delta &e = one.row[size_t(y)][r];
-                        if (!projected) {
-                            long key = (long(y) << 16) | long(e.x);
-                            if (first_key < 0 || key < first_key) first_key = key;
-                            if (e.d != 0.0f) enter(int(e.x), y);
-                        } else if (rule == 1 && e.d != 0.0f) { lx = std::min(lx, int(e.x)); hx = std::max(hx, int(e.x)); }
-                    }
-            }
-        }
-        for (int side = 0; side < 2; ++side) {
-            std::vector<Cross> &c = sideways[side];
-            const int col = side ? int(w) : 0;
-            auto row_of = [&](float y) { return std::min(int(floorf(std::min(std::max(y, 0.0f), h))), ph - 1); };
-            if (rule == 1) {
-                for (size_t k = 0; k < c.size(); ++k) { ly = std::min(ly, row_of(c[k].y)); hy = std::max(hy, row_of(c[k].y)); }
-            } else {
-                if (rule == 2 && side == 1) {
-                    // The right edge is clipped AFTER the top one (hpp:2208-2229 goes left, top, right, bottom):
-                    // crossings above the canvas are gone by then; instead a top boundary segment that
-                    // straddles x = w is cut there.
-                    std::vector<Cross> kept;
-                    for (size_t k = 0; k < c.size(); ++k) if (c[k].y >= 0.0f) kept.push_back(c[k]);
-                    for (size_t k = 0; k < tops.size(); ++k) {
-                        if (!tops[k].leaves) continue;
-                        const Top &back = tops[(k + 1) % tops.size()];
-                        float x1 = std::max(tops[k].x, 0.0f), x2 = std::max(back.x, 0.0f);
-                        if ((w - x1) * (w - x2) < 0.0f) { Cross sc = { 0.0f, x1 < w, x1 < w ? tops[k].at : back.at }; kept.push_back(sc); }
-                    }
-                    std::sort(kept.begin(), kept.end(), [](const Cross &p, const Cross &q) { return p.at < q.at; });
-                    c.swap(kept);
-                }
-                for (size_t k = 0; k < c.size(); ++k) {
-                    if (!c[k].exits) continue;
-                    const Cross &in = c[(k + 1) % c.size()];           // crossings alternate along a closed loop
-                    float y1 = c[k].y, y2 = in.y;
-                    if ((y1 < 0.0f && y2 < 0.0f) || (y1 > h && y2 > h)) continue;
-                    if (row_of(y1) == row_of(y2) && std::min(std::max(y1, 0.0f), h) == std::min(std::max(y2, 0.0f), h)) continue;
-                    enter(col, row_of(y1));
-                    enter(col, row_of(y2));
-                }
-            }
+        if (per_loop && n) {
+            int box[5] = { 0, -1, 0, -1, -1 };
+            per_loop(&lines.pts[base].x, uint32_t(n), off.x, off.y, pw, ph, box);
+            if (box[1] >= 0 && box[3] >= 0) { enter(box[0], box[2]); enter(box[1], box[3]); }
+            if (box[4] >= 0 && (first_key < 0 || box[4] < first_key)) first_key = box[4];
         }
         base += n;
     }

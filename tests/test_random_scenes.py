@@ -162,75 +162,121 @@ def random_scene_wide(seed):
     return w.take(), W, Hh
 
 
-SEEDS = list(range(24))
-WIDE_SEEDS = list(range(24))
+# Seeds 51, 672, 679 and 695 of the wide generator were open defects of the CUDA path in round 1 (shadow working
+# rectangle; per-edge clip arithmetic): they sit inside the committed range on purpose.
+SEEDS = list(range(300))
+WIDE_SEEDS = list(range(900))
+INTEGER_SEEDS = list(range(300))
+CHUNK = 50
 
 
-@pytest.mark.parametrize("seed", SEEDS)
-def test_oracle_matches_reference_on_random_scenes(seed):
+def _scene(generator, seed):
+    if generator == "plain":
+        return random_scene(seed), SIZE, SIZE
+    if generator == "wide":
+        return random_scene_wide(seed)
+    return integer_scene(seed)
+
+
+def _chunks(generator, seeds):
+    return [(generator, seeds[i:i + CHUNK]) for i in range(0, len(seeds), CHUNK)]
+
+
+ALL_CHUNKS = _chunks("plain", SEEDS) + _chunks("wide", WIDE_SEEDS) + _chunks("integer", INTEGER_SEEDS)
+CHUNK_IDS = ["%s-%d" % (g, c[0]) for g, c in ALL_CHUNKS]
+
+
+@pytest.mark.parametrize("generator,seeds", ALL_CHUNKS, ids=CHUNK_IDS)
+def test_oracle_matches_reference_on_random_scenes(generator, seeds):
     ref = H.reference_library()
     if ref is None:
         pytest.skip("oracle/_ref not built")
-    script = random_scene(seed)
-    want = H.render_script(ref, script, SIZE, SIZE)
-    got = H.render_oracle(script, SIZE, SIZE)
-    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
-    assert nbad == 0, "max |diff| %.3g" % worst
-    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+    failed = []
+    for seed in seeds:
+        script, w, h = _scene(generator, seed)
+        want = H.render_script(ref, script, w, h)
+        got = H.render_oracle(script, w, h)
+        nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+        n8 = H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2]
+        if nbad or n8:
+            failed.append((seed, nbad, worst, n8))
+    assert not failed, failed
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", SEEDS)
-def test_gpu_matches_oracle_on_random_scenes(seed):
+@pytest.mark.parametrize("generator,seeds", ALL_CHUNKS, ids=CHUNK_IDS)
+def test_gpu_matches_oracle_on_random_scenes(generator, seeds):
     lib = H.product_library()
     if lib.cb200_device_count() < 1:
         pytest.skip("no CUDA device")
-    script = random_scene(seed)
-    got = H.render_script(lib, script, SIZE, SIZE)
-    want = H.render_oracle(script, SIZE, SIZE)
-    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
-    assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
-    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+    failed = []
+    for seed in seeds:
+        script, w, h = _scene(generator, seed)
+        got = H.render_script(lib, script, w, h)
+        want = H.render_oracle(script, w, h)
+        nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+        n8 = H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2]
+        if nbad or n8:
+            failed.append((seed, nbad, worst, n8))
+    assert not failed, "(seed, floats off, max |diff|, pixels beyond 1 LSB): %s" % failed
 
 
-@pytest.mark.parametrize("seed", WIDE_SEEDS)
-def test_oracle_matches_reference_on_wide_random_scenes(seed):
-    ref = H.reference_library()
+@pytest.mark.gpu
+@pytest.mark.parametrize("generator,seeds", _chunks("wide", [51, 672, 679, 695]) + _chunks("integer", list(range(300, 340))), ids=["round1-open-seeds", "integer-300"])
+def test_gpu_matches_reference_on_formerly_open_seeds(generator, seeds):
+    """The four seeds DESIGN.md listed as open after round 1, and a further block of integer scenes, against the
+    REFERENCE build itself (not the oracle): float framebuffer within 1e-4 relative, RGBA8 within 1 LSB."""
+    lib, ref = H.product_library(), H.reference_library()
+    if lib.cb200_device_count() < 1:
+        pytest.skip("no CUDA device")
     if ref is None:
         pytest.skip("oracle/_ref not built")
-    script, w, h = random_scene_wide(seed)
-    want = H.render_script(ref, script, w, h)
-    got = H.render_oracle(script, w, h)
-    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
-    assert nbad == 0, "max |diff| %.3g" % worst
-    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+    failed = []
+    for seed in seeds:
+        script, w, h = _scene(generator, seed)
+        got = H.render_script(lib, script, w, h)
+        want = H.render_script(ref, script, w, h)
+        nbad, worst = H.float_mismatch(got["f32"], want["f32"])
+        n8 = H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2]
+        if nbad or n8:
+            failed.append((seed, nbad, worst, n8))
+    assert not failed, "(seed, floats off, max |diff|, pixels beyond 1 LSB): %s" % failed
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("seed", WIDE_SEEDS)
-def test_gpu_matches_oracle_on_wide_random_scenes(seed):
-    lib = H.product_library()
-    if lib.cb200_device_count() < 1:
-        pytest.skip("no CUDA device")
-    script, w, h = random_scene_wide(seed)
-    got = H.render_script(lib, script, w, h)
-    want = H.render_oracle(script, w, h)
-    nbad, worst = H.float_mismatch(got["f32"], want["f32"])
-    assert nbad == 0, "%d floats off, max |diff| %.3g" % (nbad, worst)
-    assert H.rgba8_mismatch(got["rgba8"], want["rgba8"])[2] == 0
+def integer_scene(seed):
+    """Shadowed polygons and rectangles on INTEGER coordinates with integer shadow offsets, partly outside the
+    canvas: crossings and vertices land exactly on pixel and canvas boundaries, where a working rectangle that is
+    one row or column off shows.  Returns (script, width, height)."""
+    rng = np.random.default_rng(9000 + seed)
+    W, Hh = int(rng.integers(40, 200)), int(rng.integers(40, 200))
+    w = H.ScriptWriter()
+    for _ in range(int(rng.integers(2, 6))):
+        w.ints("SET_COMPOSITE", int(rng.choice([1, 2, 3, 4, 7, 14])))
+        w.floats("SET_SHADOW_COLOR", 0.0, 0.0, 0.0, 1.0); w.floats("SET_SHADOW_BLUR", float(rng.choice([0.0, 2.0, 4.0, 7.0])))
+        w.floats("SET_SHADOW_OFFSET_X", float(rng.integers(-12, 13))); w.floats("SET_SHADOW_OFFSET_Y", float(rng.integers(-12, 13)))
+        w.ints("SET_COLOR", 0); w.raw("4f", 0.5, 0.2, 0.8, 1.0)
+        if rng.random() < 0.5:
+            w.floats("FILL_RECTANGLE", float(rng.integers(-60, W)), float(rng.integers(-60, Hh)), float(rng.integers(5, 2 * W)), float(rng.integers(5, 2 * Hh)))
+        else:
+            w.bare("BEGIN_PATH")
+            w.floats("MOVE_TO", float(rng.integers(-50, W + 50)), float(rng.integers(-50, Hh + 50)))
+            for _ in range(int(rng.integers(2, 7))):
+                w.floats("LINE_TO", float(rng.integers(-50, W + 50)), float(rng.integers(-50, Hh + 50)))
+            w.bare("CLOSE_PATH"); w.bare("FILL")
+    return w.take(), W, Hh
 
 
-def test_exact_shadow_rectangle_rule_matches_the_reference_clip():
-    """The per-edge rule the CUDA rasteriser is to adopt for render_shadow's working rectangle (Next 1):
-    oracle_debug_shadow_boxes computes the box from the reference's polygon clip and from per-edge clipping with
-    paired crossings + clip order; they must agree on every shadowed draw of the committed scenes."""
+def shadow_box_mismatches(scenes):
+    """(mismatching draws, shadowed draws): the run bounding box render_shadow derives from the reference's polygon
+    clip (oracle) against what the product's own clip / scanline / boundary-segment code enters for the same
+    outlines (csrc/device/edge_clip.cuh built for the host: cb200_debug_shadow_box).  CPU only."""
     import ctypes as C
     import struct
-    orc = H.oracle_library()
-    orc.oracle_debug_shadow_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 8)]
+    orc, prod = H.oracle_library(), H.product_library()
+    orc.oracle_debug_shadow_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int * 8)]
     orc.oracle_debug_shadow_boxes.restype = C.c_int
-    checked = 0
-    scenes = [(random_scene(s), SIZE, SIZE) for s in SEEDS] + [random_scene_wide(s) for s in range(120)]
+    per_loop = C.cast(prod.cb200_debug_shadow_box, C.c_void_p)
+    bad, checked = [], 0
     for script, w, h in scenes:
         for fr in H.lower_script(script, w, h):
             draws = bytes(fr.parts["draws"])
@@ -241,7 +287,20 @@ def test_exact_shadow_rectangle_rule_matches_the_reference_clip():
                 if kind == 2 or color_a == 0.0 or (blur == 0.0 and off_x == 0.0 and off_y == 0.0):
                     continue
                 out = (C.c_int * 8)()
-                orc.oracle_debug_shadow_boxes(C.addressof(fr.frame), di, w, h, 2, C.byref(out))
-                assert list(out[0:4]) == list(out[4:8]), (w, h, di)
+                orc.oracle_debug_shadow_boxes(C.addressof(fr.frame), di, w, h, per_loop, C.byref(out))
                 checked += 1
-    assert checked > 100
+                if list(out[0:4]) != list(out[4:8]):
+                    bad.append((w, h, di, list(out[0:4]), list(out[4:8])))
+    return bad, checked
+
+
+def test_shadow_working_rectangle_equals_the_reference_clip():
+    """render_shadow's working rectangle (hpp:2409-2423) comes from the runs of the Sutherland-Hodgman-clipped
+    outline (hpp:2208-2229); the CUDA rasteriser clips edge by edge and rebuilds the clip's boundary segments from
+    the loop's crossings.  The host build of that device code must enter exactly the reference's box on every
+    shadowed draw of the fuzz scenes and of the integer-coordinate scenes."""
+    scenes = [(random_scene(s), SIZE, SIZE) for s in range(120)] + [random_scene_wide(s) for s in range(300)] + \
+             [integer_scene(s) for s in range(300)]
+    bad, checked = shadow_box_mismatches(scenes)
+    assert checked > 1000
+    assert not bad, bad[:5]
