@@ -35,9 +35,15 @@ def _image_bytes(image, width, height, stride):
     if image is None:
         return None
     data = image.tobytes() if hasattr(image, "tobytes") else bytes(image)
-    if width <= 0 or height <= 0 or stride < 0:
-        return data[:1] or b"\0"
-    return data[:(height - 1) * stride + width * 4]
+    if width <= 0 or height <= 0:
+        return data[:1] or b"\0"             # a no-op in the reference (hpp:2847, 3323, 3392): nothing is read
+    if stride < 0:
+        raise ValueError("canvas_ity_b200: a negative stride cannot be expressed for a Python buffer")
+    need = (height - 1) * stride + width * 4
+    if len(data) < need:
+        raise ValueError("canvas_ity_b200: image buffer holds %d bytes, %d x %d pixels with stride %d need %d"
+                         % (len(data), width, height, stride, need))
+    return data[:need]
 
 
 class Canvas:

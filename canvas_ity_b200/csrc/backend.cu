@@ -331,7 +331,7 @@ int stage_frames(cb200_canvas *cv, const cb200_frame *const *frames, const uint3
             // (hpp:2583-2591 with cov = vis = 1): solid colour, unclipped, and either source_copy or
             // source_over with global_alpha == colour alpha == 1
             if (j.kind == JOB_MAIN && d.mask_src == 0 && in->brushes[d.brush].type == CB200_BRUSH_COLOR &&
-                in->brushes[d.brush].n_colors == 1) {
+                in->brushes[d.brush].n_colors == 1 && in->brushes[d.brush].first_color < in->n_colors) {
                 float a = in->colors[4 * size_t(in->brushes[d.brush].first_color) + 3];
                 if (d.op == 2u || (d.op == 14u && d.global_alpha == 1.0f && a == 1.0f)) j.opaque = 1;
             }
@@ -928,6 +928,18 @@ int settle(cb200_canvas *cv)
     return CB200_OK;
 }
 
+// Clip-mask planes were freed: a resident frame's device mask table and replay graphs hold their addresses.
+// cb200_frame_replay then reports "no frame uploaded" instead of touching freed memory.
+void invalidate_resident(cb200_canvas *cv)
+{
+    bool uses_masks = false;
+    for (const draw_rec &d : cv->staged.draws) uses_masks = uses_masks || d.mask_src || d.mask_dst;
+    if (!cv->resident || !uses_masks) return;
+    cv->resident = false;
+    cv->replay_verified = false;
+    drop_replay_graphs(cv);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------- C ABI ----
@@ -1056,6 +1068,56 @@ int cb200_batch_read_rgba8(cb200_canvas *cv, uint32_t canvas, uint8_t *dst, int 
     CK(cudaStreamSynchronize(cv->stream));
     for (int row = 0; row < height; ++row)
         memcpy(dst + ptrdiff_t(row) * stride, tmp.data() + size_t(row) * size_t(width) * 4, size_t(width) * 4);
+    return CB200_OK;
+}
+
+int cb200_batch_write_rgba8(cb200_canvas *cv, uint32_t canvas, const uint8_t *src, int width, int height, int stride,
+                            int x, int y)
+{
+    if (!cv || !src) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (canvas >= uint32_t(cv->n_canvases)) return fail(CB200_ERR_BAD_ARG, "canvas index out of range");
+    if (width <= 0 || height <= 0) return CB200_OK;
+    CK(cudaSetDevice(cv->device));
+    int rc = settle(cv);
+    if (rc != CB200_OK) return rc;
+    const size_t bytes = 4 * size_t(width) * size_t(height);
+    std::vector<uint8_t> packed(bytes);
+    for (int row = 0; row < height; ++row)
+        memcpy(packed.data() + size_t(row) * size_t(width) * 4, src + ptrdiff_t(row) * stride, size_t(width) * 4);
+    CK(cv->rgba8.reserve(std::max<size_t>(bytes, 16)));
+    CK(cudaMemcpyAsync(cv->rgba8.p, packed.data(), bytes, cudaMemcpyHostToDevice, cv->stream));
+    float4 *slot = cv->fb + size_t(canvas) * size_t(cv->n_canvases > 1 ? cv->slot_rows : 0) * size_t(cv->width);
+    launch_upload(slot, cv->width, 0, cv->height, cv->rgba8.p, width, height, x, y, cv->stream);
+    ++cv->launches;
+    CK(cudaStreamSynchronize(cv->stream));       // `packed` is pageable: the copy above has completed, the kernel too
+    return CB200_OK;
+}
+
+int cb200_batch_masks_keep(cb200_canvas *cv, const uint32_t *canvas, const uint32_t *local_slot, uint32_t n)
+{
+    if (!cv || (n && (!canvas || !local_slot))) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);
+    if (rc != CB200_OK) return rc;
+    CK(cudaStreamSynchronize(cv->stream));
+    // batch-wide slots that stay: the ones the listed (canvas, local slot) pairs map to
+    std::vector<uint32_t> keep;
+    for (auto ci = cv->batch_masks.begin(); ci != cv->batch_masks.end();) {
+        for (auto si = ci->second.begin(); si != ci->second.end();) {
+            bool alive = false;
+            for (uint32_t i = 0; i < n; ++i) alive = alive || (canvas[i] == ci->first && local_slot[i] == si->first);
+            if (alive) { keep.push_back(si->second); ++si; }
+            else si = ci->second.erase(si);
+        }
+        if (ci->second.empty()) ci = cv->batch_masks.erase(ci); else ++ci;
+    }
+    for (auto it = cv->masks.begin(); it != cv->masks.end();) {
+        if (std::find(keep.begin(), keep.end(), it->first) != keep.end()) ++it;
+        else { cudaFree(it->second); it = cv->masks.erase(it); }
+    }
+    cv->resident = false;                                   // a resident frame's mask table may name freed planes
+    cv->replay_verified = false;
+    drop_replay_graphs(cv);
     return CB200_OK;
 }
 
@@ -1494,12 +1556,14 @@ int cb200_masks_keep(cb200_canvas *cv, const uint32_t *slots, uint32_t n)
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
     CK(cudaStreamSynchronize(cv->stream));
+    bool freed = false;
     for (auto it = cv->masks.begin(); it != cv->masks.end();) {
         bool keep = false;
         for (uint32_t i = 0; i < n; ++i) keep = keep || slots[i] == it->first;
         if (keep) ++it;
-        else { cudaFree(it->second); it = cv->masks.erase(it); }
+        else { cudaFree(it->second); it = cv->masks.erase(it); freed = true; }
     }
+    if (freed) invalidate_resident(cv);
     return CB200_OK;
 }
 
@@ -1510,8 +1574,15 @@ int cb200_clear(cb200_canvas *cv)
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
     cv->clear_pending = true;                    // absorbed by the next frame, or applied by the next pixel access
-    for (auto &kv : cv->masks) cudaFree(kv.second);
-    cv->masks.clear();
+    if (!cv->masks.empty()) {
+        // The planes go (the caller resets its clip state with the canvas).  A resident frame holds raw plane
+        // pointers in its uploaded mask table and in its captured graphs: it must be uploaded again.
+        CK(cudaStreamSynchronize(cv->stream));
+        for (auto &kv : cv->masks) cudaFree(kv.second);
+        cv->masks.clear();
+        cv->batch_masks.clear();
+        invalidate_resident(cv);
+    }
     return CB200_OK;
 }
 
@@ -1565,6 +1636,28 @@ void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_
     walk.finish();
     if (walk.hx >= 0) { lx = std::min(lx, walk.lx); hx = std::max(hx, walk.hx); ly = std::min(ly, walk.ly); hy = std::max(hy, walk.hy); }
     box5[0] = lx; box5[1] = hx; box5[2] = ly; box5[3] = hy; box5[4] = int(first_key);
+}
+
+// join_acosf / join_tanf (geom.cuh) over an array, on the host or on the device: the rounded join's two libm
+// calls, which must carry the host libm's bits (tests/test_geometry_math.py compares with libm itself).
+int cb200_debug_join_math(const float *x, uint32_t n, float *acos_out, float *tan_out, int on_device)
+{
+    if (!x || !acos_out || !tan_out) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (!on_device) {
+        for (uint32_t i = 0; i < n; ++i) { acos_out[i] = join_acosf(x[i]); tan_out[i] = join_tanf(x[i]); }
+        return CB200_OK;
+    }
+    float *dx = nullptr, *da = nullptr, *dt = nullptr;
+    CK(cudaMalloc(&dx, sizeof(float) * size_t(n) + 4));
+    CK(cudaMalloc(&da, sizeof(float) * size_t(n) + 4));
+    CK(cudaMalloc(&dt, sizeof(float) * size_t(n) + 4));
+    CK(cudaMemcpy(dx, x, sizeof(float) * size_t(n), cudaMemcpyHostToDevice));
+    launch_join_math(dx, n, da, dt, nullptr);
+    CK(cudaMemcpy(acos_out, da, sizeof(float) * size_t(n), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tan_out, dt, sizeof(float) * size_t(n), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(da); cudaFree(dt);
+    CK(cudaGetLastError());
+    return CB200_OK;
 }
 
 int64_t cb200_debug_lines(cb200_canvas *cv, float *edges, uint32_t *job_of_edge, int64_t capacity)

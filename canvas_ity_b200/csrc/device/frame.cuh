@@ -93,6 +93,7 @@ void launch_glyphs(const device_frame &f, cudaStream_t s);
 void launch_flatten(const device_frame &f, uint32_t n_units, cudaStream_t s);
 void launch_dash(const device_frame &f, cudaStream_t s);
 void launch_stroke(const device_frame &f, cudaStream_t s);
+void launch_join_math(const float *x, uint32_t n, float *acos_out, float *tan_out, cudaStream_t s);   // debug tap
 // raster.cu
 void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s);
 // sort.cu

@@ -452,8 +452,8 @@ __device__ __forceinline__ bool join_step(walk_state &ws, vec2 nxt, const stroke
             sink.put(apply(st.fwd, pivot + tip));
         else if (st.join == 2) {
             float cosine = dot(jin, jout);
-            float angle = acosf(fminf(fmaxf(cosine, -1.0f), 1.0f));
-            float k = 4.0f / 3.0f * tanf(0.25f * angle);
+            float angle = join_acosf(fminf(fmaxf(cosine, -1.0f), 1.0f));     // the host libm's bits (geom.cuh)
+            float k = 4.0f / 3.0f * join_tanf(0.25f * angle);
             sink.put(apply(st.fwd, a));
             flatten_cubic(apply(st.fwd, a), apply(st.fwd, a + (k * st.half) * jin),
                           apply(st.fwd, b - (k * st.half) * jout), apply(st.fwd, b), -1.0f, sink);
@@ -945,7 +945,20 @@ __global__ void __launch_bounds__(kBlock) k_stroke_finish(device_frame f)
     }
 }
 
+__global__ void k_join_math(const float *x, uint32_t n, float *acos_out, float *tan_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        acos_out[i] = join_acosf(x[i]);
+        tan_out[i] = join_tanf(x[i]);
+    }
+}
+
 }  // namespace
+
+void launch_join_math(const float *x, uint32_t n, float *acos_out, float *tan_out, cudaStream_t s)
+{
+    k_join_math<<<kGrid, kBlock, 0, s>>>(x, n, acos_out, tan_out);
+}
 
 void launch_glyphs(const device_frame &f, cudaStream_t s)
 {

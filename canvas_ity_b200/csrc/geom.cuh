@@ -39,6 +39,97 @@ CB_HD vec2 apply(const affine &m, vec2 p) {
     return v2(m.a * p.x + m.c * p.y + m.e, m.b * p.x + m.d * p.y + m.f);
 }
 
+// ---- acosf / tanf of the rounded join (hpp:1995-1997), bit for bit --------------------------------
+// The reference calls the host libm there, and the join's cubic then goes through flattening DECISIONS, so a
+// last-bit difference in the angle can change the outline.  glibc (2.39 on this image) implements both with the
+// fdlibm algorithms (flt-32/e_acosf.c, k_tanf.c): plain float polynomial arithmetic, restated here operation by
+// operation (no FMA).  Checked against glibc's acosf over ALL floats in [-1, 1] and tanf over all floats in
+// [0, pi/4] -- the join only ever needs tanf(angle / 4) with angle in [0, pi]: zero mismatches
+// (tests/test_geometry_math.py samples the same through cb200_debug_join_math).
+CB_HD float bits_float(unsigned u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { unsigned u; float f; } c; c.u = u; return c.f;
+#endif
+}
+CB_HD unsigned float_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { unsigned u; float f; } c; c.f = f; return c.u;
+#endif
+}
+
+CB_HD float join_acosf(float x)
+{
+    const float pi = bits_float(0x40490fdau), pio2_hi = bits_float(0x3fc90fdau), pio2_lo = bits_float(0x33a22168u);
+    const float p0 = bits_float(0x3e2aaaabu), p1 = bits_float(0xbea6b090u), p2 = bits_float(0x3e4e0aa8u),
+                p3 = bits_float(0xbd241146u), p4 = bits_float(0x3a4f7f04u), p5 = bits_float(0x3811ef08u);
+    const float q1 = bits_float(0xc019d139u), q2 = bits_float(0x4001572du), q3 = bits_float(0xbf303361u),
+                q4 = bits_float(0x3d9dc62eu);
+    const int hx = int(float_bits(x)), ix = hx & 0x7fffffff;
+    if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
+    if (ix > 0x3f800000) return (x - x) / (x - x);
+    if (ix < 0x3f000000) {                                   // |x| < 0.5
+        if (ix <= 0x32800000) return pio2_hi + pio2_lo;
+        const float z = x * x;
+        const float p = z * (p0 + z * (p1 + z * (p2 + z * (p3 + z * (p4 + z * p5)))));
+        const float q = 1.0f + z * (q1 + z * (q2 + z * (q3 + z * q4)));
+        const float r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (hx < 0) {                                            // x < -0.5
+        const float z = (1.0f + x) * 0.5f;
+        const float p = z * (p0 + z * (p1 + z * (p2 + z * (p3 + z * (p4 + z * p5)))));
+        const float q = 1.0f + z * (q1 + z * (q2 + z * (q3 + z * q4)));
+        const float s = sqrtf(z);
+        const float r = p / q;
+        const float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    const float z = (1.0f - x) * 0.5f;                       // x > 0.5
+    const float s = sqrtf(z);
+    const float df = bits_float(float_bits(s) & 0xfffff000u);
+    const float c = (z - df * df) / (s + df);
+    const float p = z * (p0 + z * (p1 + z * (p2 + z * (p3 + z * (p4 + z * p5)))));
+    const float q = 1.0f + z * (q1 + z * (q2 + z * (q3 + z * q4)));
+    const float r = p / q;
+    const float w = r * s + c;
+    return 2.0f * (df + w);
+}
+
+// tanf(x) for 0 <= x <= pi/4 (glibc: __kernel_tanf(x, 0, 1), no argument reduction in that range)
+CB_HD float join_tanf(float x)
+{
+    const float pio4 = bits_float(0x3f490fdau), pio4lo = bits_float(0x33222168u);
+    const float t0 = bits_float(0x3eaaaaabu), t1 = bits_float(0x3e088889u), t2 = bits_float(0x3d5d0dd1u),
+                t3 = bits_float(0x3cb327a4u), t4 = bits_float(0x3c11371fu), t5 = bits_float(0x3b6b6916u),
+                t6 = bits_float(0x3abede48u), t7 = bits_float(0x3a1a26c8u), t8 = bits_float(0x398137b9u),
+                t9 = bits_float(0x38a3f445u), t10 = bits_float(0x3895c07au), t11 = bits_float(0xb79bae5fu),
+                t12 = bits_float(0x37d95384u);
+    const int hx = int(float_bits(x)), ix = hx & 0x7fffffff;
+    if (ix < 0x39000000 && int(x) == 0) return x;            // |x| < 2^-13
+    const bool big = ix >= 0x3f2ca140;                       // |x| >= 0.6744
+    if (big) {
+        const float z = pio4 - x;
+        x = z + pio4lo;
+        if (fabsf(x) < 1.220703125e-4f) return 1.0f - 2.0f * x;    // 2^-13
+    }
+    const float z = x * x;
+    float w = z * z;
+    float r = t1 + w * (t3 + w * (t5 + w * (t7 + w * (t9 + w * t11))));
+    const float v = z * (t2 + w * (t4 + w * (t6 + w * (t8 + w * (t10 + w * t12)))));
+    const float s = z * x;
+    r = 0.0f + z * (s * (r + v) + 0.0f);
+    r += t0 * s;
+    w = x + r;
+    if (big) return 1.0f - 2.0f * (x - (w * w / (w + 1.0f) - r));
+    return w;
+}
+
 // Cosine of the largest turn a stroked curve piece may keep (hpp:1498-1500);
 // fills use -1 which also switches the emission rule (end points only).
 CB_HD float stroke_angular(float line_width) {

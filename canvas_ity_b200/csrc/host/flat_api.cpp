@@ -78,6 +78,18 @@ void batch_on_read(void *user, uint8_t *dst, int w, int h, int stride, int x, in
     cv_batch::slot *s = static_cast<cv_batch::slot *>(user);
     cv_batch_get_image_data(s->batch, s->index, dst, w, h, stride, x, y);
 }
+// put_image_data on a member (hpp:3383-3408): ordered after everything drawn so far on any member
+void batch_on_write(void *user, const uint8_t *src, int w, int h, int stride, int x, int y)
+{
+    cv_batch::slot *s = static_cast<cv_batch::slot *>(user);
+    int rc = cv_batch_flush(s->batch);
+    if (rc == CB200_OK) rc = cb200_batch_write_rgba8(s->batch->device, uint32_t(s->index), src, w, h, stride, x, y);
+    if (rc != CB200_OK) {
+        // the canvas API has no error channel: a device failure is fatal rather than silently wrong pixels
+        fprintf(stderr, "canvas_b200: put_image_data on batch canvas %d failed (%d): %s\n", s->index, rc, cb200_last_error());
+        abort();
+    }
+}
 }
 
 extern "C" {
@@ -100,6 +112,7 @@ cv_batch *cv_batch_create(int n_canvases, int width, int height, int device)
         c->b200()->tap.user = &b->slots[size_t(i)];
         c->b200()->tap.frame = batch_on_frame;
         c->b200()->tap.read_rgba8 = batch_on_read;
+        c->b200()->tap.write_rgba8 = batch_on_write;
         b->members.push_back(c);
     }
     return b;
@@ -128,9 +141,25 @@ int cv_batch_flush(cv_batch *b)
         if (rc != CB200_OK) { g_api_error = cb200_last_error(); return rc; }
     }
     int rc = cb200_sync(b->device);                        // the frames are about to be freed
+    bool submitted = false;
     for (int i = 0; i < b->n; ++i) {
+        submitted = submitted || !b->pending[size_t(i)].empty();
         for (owned_frame *f : b->pending[size_t(i)]) delete f;
         b->pending[size_t(i)].clear();
+    }
+    // clip() allocates a device plane per call: free the ones no member can reach any more (current mask +
+    // save stack of every member), or a batch that clips every frame grows without bound
+    if (rc == CB200_OK && submitted) {
+        std::vector<uint32_t> canvas, slot;
+        bool any_clip = false;
+        for (int i = 0; i < b->n; ++i) {
+            canvas_ity::canvas::host_state *st = b->members[size_t(i)]->b200();
+            any_clip = any_clip || st->next_mask > 1;
+            if (st->mask) { canvas.push_back(uint32_t(i)); slot.push_back(st->mask); }
+            for (size_t k = 0; k < st->saves.size(); ++k)
+                if (st->saves[k].mask) { canvas.push_back(uint32_t(i)); slot.push_back(st->saves[k].mask); }
+        }
+        if (any_clip) rc = cb200_batch_masks_keep(b->device, canvas.data(), slot.data(), uint32_t(canvas.size()));
     }
     return rc;
 }

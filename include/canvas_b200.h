@@ -194,6 +194,12 @@ int cb200_batch_submit(cb200_canvas *batch, const cb200_frame *const *frames,
 int cb200_batch_read_rgba8(cb200_canvas *batch, uint32_t canvas, uint8_t *dst, int width,
                            int height, int stride, int x, int y);
 int cb200_batch_read_f32(cb200_canvas *batch, uint32_t canvas, float *dst);
+/* put_image_data into canvas `canvas` of a batch (hpp:3383-3408), ordered after the frames submitted so far. */
+int cb200_batch_write_rgba8(cb200_canvas *batch, uint32_t canvas, const uint8_t *src, int width, int height,
+                            int stride, int x, int y);
+/* Batch form of cb200_masks_keep: the clip-mask planes still reachable are those of the listed (canvas, that
+ * canvas' own slot) pairs; every other plane of the batch is freed. */
+int cb200_batch_masks_keep(cb200_canvas *batch, const uint32_t *canvas, const uint32_t *local_slot, uint32_t n);
 
 /* Run `frame` (draws in order) on the canvas' stream.  Asynchronous: returns
  * once the frame is copied to pinned staging and the kernels are enqueued. */
@@ -315,6 +321,11 @@ int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative
  * the CPU test checks the rule against the reference's clip. */
 void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
                             int *box5);
+
+/* The rounded join's acosf / tanf (hpp:1995-1997) as the kernels compute them (csrc/geom.cuh: glibc's fdlibm
+ * algorithms restated), over x[0 .. n): acos_out[i] = acosf(x[i]) for |x| <= 1, tan_out[i] = tanf(x[i]) for
+ * 0 <= x <= pi/4.  on_device = 0 runs the host build of the same code, 1 a kernel. */
+int cb200_debug_join_math(const float *x, uint32_t n, float *acos_out, float *tan_out, int on_device);
 
 const char *cb200_last_error(void);
 int cb200_abi_version(void);

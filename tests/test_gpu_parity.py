@@ -425,3 +425,77 @@ def test_clear_is_deferred_but_never_lost(lib):
         assert fourth[3, 71, 3] == 255 and fourth[10, 10, 3] == 255
     finally:
         lib.cv_destroy(h)
+
+
+def test_batch_members_take_put_image_data_and_release_clip_planes(lib):
+    """Round-1 advisor findings: put_image_data on a batch member used to be dropped silently, and every clip()
+    on a member leaked a plane for the batch's lifetime.  Members now behave like solo canvases across several
+    flushes that clip, put pixels and draw (the reference semantics: hpp:3383-3408 ordered after earlier draws)."""
+    n, w, h = 3, 70, 50
+    import canvas_ity_b200 as cb
+    patch = (np.arange(6 * 5 * 4, dtype=np.uint32) * 37 % 256).astype(np.uint8).reshape(6, 5, 4)
+    patch[..., 3] |= 0x80
+
+    def round_script(i, k):
+        s = cb.script.ScriptWriter()
+        s.bare("SAVE")
+        s.bare("BEGIN_PATH"); s.floats("ARC", 30 + 3 * i, 25, 14 + 3 * k, 0, 6.28318531); s.raw("i", 0); s.bare("CLIP")
+        s.ints("SET_COLOR", 0); s.raw("4f", 0.2 * i, 0.3 * k, 0.8, 0.75)
+        s.floats("FILL_RECTANGLE", 5, 5, 60, 40)
+        s.bare("RESTORE")
+        s.ints("PUT_IMAGE_DATA", 5, 6, 20, 3 + 7 * k, 2 + i); s.blob(patch.tobytes())
+        s.ints("SET_COLOR", 0); s.raw("4f", 0.9, 0.1 * i, 0.1, 0.5)
+        s.floats("FILL_RECTANGLE", 40, 30 - 4 * k, 25, 12)
+        return s.take()
+
+    batch = lib.cv_batch_create(n, w, h, 0)
+    assert batch, lib.cv_last_error()
+    try:
+        for k in range(4):                                   # four flushes, each with a fresh clip per member
+            for i in range(n):
+                H._run(lib, lib.cv_batch_canvas(batch, i), round_script(i, k))
+            assert lib.cv_batch_flush(batch) == 0, lib.cv_last_error()
+        for i in range(n):
+            got = np.zeros((h, w, 4), np.float32)
+            assert lib.cv_batch_read_f32(batch, i, got.ctypes.data) == 0
+            want = H.render_oracle(b"".join(round_script(i, k) for k in range(4)), w, h)
+            nbad, worst = H.float_mismatch(got, want["f32"])
+            assert nbad == 0, "canvas %d: %d floats off (max %.3g)" % (i, nbad, worst)
+            assert np.abs(got).sum() > 0
+    finally:
+        lib.cv_batch_destroy(batch)
+
+
+def test_clear_invalidates_a_resident_frame_that_uses_clip_planes(lib):
+    """cb200_clear frees the clip-mask planes; a resident frame (cb200_frame_upload) holds their addresses in its
+    device mask table and its replay graphs, so replaying it afterwards must be refused, not executed
+    (round-1 advisor finding).  A resident frame without clips survives the clear."""
+    size = 128
+    clipped = H.lower_script(H.golden_script("clip"), 256, 256)[0]
+    plain = H.lower_script(H.tiger_script(size, size), size, size)[0]
+    cv = C.c_void_p()
+    assert lib.cb200_canvas_create(256, 256, 0, C.byref(cv)) == 0
+    try:
+        assert lib.cb200_set_stage_timing(cv, 0) == 0
+        assert lib.cb200_frame_upload(cv, C.byref(clipped.frame)) == 0
+        assert lib.cb200_frame_replay(cv, 1) == 0 and lib.cb200_frame_replay(cv, 1) == 0
+        first = np.zeros((256, 256, 4), np.float32)
+        assert lib.cb200_read_f32(cv, first.ctypes.data) == 0
+        assert lib.cb200_clear(cv) == 0
+        assert lib.cb200_frame_replay(cv, 1) != 0                      # refused: its planes are gone
+        assert b"no frame uploaded" in lib.cb200_last_error()
+        assert lib.cb200_frame_upload(cv, C.byref(clipped.frame)) == 0   # uploading again makes new planes
+        assert lib.cb200_frame_replay(cv, 1) == 0
+        again = np.zeros((256, 256, 4), np.float32)
+        assert lib.cb200_read_f32(cv, again.ctypes.data) == 0
+        assert np.array_equal(first, again)
+    finally:
+        lib.cb200_canvas_destroy(cv)
+    assert lib.cb200_canvas_create(size, size, 0, C.byref(cv)) == 0
+    try:
+        assert lib.cb200_frame_upload(cv, C.byref(plain.frame)) == 0
+        assert lib.cb200_frame_replay(cv, 1) == 0
+        assert lib.cb200_clear(cv) == 0
+        assert lib.cb200_frame_replay(cv, 0) == 0, lib.cb200_last_error()    # no planes involved: still resident
+    finally:
+        lib.cb200_canvas_destroy(cv)
