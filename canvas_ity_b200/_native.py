@@ -99,6 +99,7 @@ SIGNATURES = {
     "cb200_debug_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_debug_runs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_debug_shadow_box": (None, [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "cb200_debug_loop_runs": (C.c_int64, [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
     "cb200_debug_join_math": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -125,6 +125,7 @@ struct cb200_canvas {
     dev_buf<uint2> job_box;
     dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count, loop_mark;
     dev_buf<uint2> box_loops;
+    dev_buf<leak_rec> leaks;  uint32_t cap_leaks = 0;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -420,10 +421,11 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     uint32_t want_sources = uint32_t(sf.sources.size()) + std::max<uint32_t>(4096u, uint32_t(sf.dash_items.size()) * 64u);
     uint32_t want_dash_sub = sf.dash_items.empty() ? 0u : std::max<uint32_t>(4096u, uint32_t(sf.dash_items.size()) * 64u);
     uint32_t want_items = want_pts * 2, want_rows = 1u << 22, want_runs = 1u << 23, want_tiles = 1u << 17;
+    uint32_t want_leaks = 4096;
     uint64_t want_planes = sf.shadow_jobs.empty() ? 0 : uint64_t(cv->width + 64) * uint64_t(cv->height + 64) * 2;
     if (getenv("CB200_TEST_SMALL_CAPS")) {
         // test hook: start with tiny queues so that every frame exercises the overflow -> regrow -> re-run path
-        want_pts = 64; want_items = 64; want_rows = 64; want_runs = 64; want_tiles = 16;
+        want_pts = 64; want_items = 64; want_rows = 64; want_runs = 64; want_tiles = 16; want_leaks = 1;
         want_planes = sf.shadow_jobs.empty() ? 0 : 64;
         want_dash_sub = sf.dash_items.empty() ? 0u : 4u;
         want_sources = uint32_t(sf.sources.size()) + 4;
@@ -439,6 +441,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
         want_tiles = std::max(want_tiles, seen->n_tile_entries + seen->n_tile_entries / 4 + 1024);
         want_planes = std::max<uint64_t>(want_planes, seen->plane_floats + seen->plane_floats / 4 + 1024);
         if (seen->overflow & (OVF_POINTS | OVF_DASH)) want_pts = std::max(want_pts, cv->cap_pts * 2);
+        want_leaks = std::max(want_leaks, seen->n_leaks + seen->n_leaks / 4 + 16);
         if (seen->overflow & OVF_DASH) {
             want_sources = std::max(want_sources, cv->cap_sources * 2);
             want_dash_sub = std::max(want_dash_sub, cv->cap_dash_subpaths * 2);
@@ -452,6 +455,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     want_runs = std::max(want_runs, cv->cap_runs);
     want_tiles = std::max(want_tiles, cv->cap_tiles);
     want_planes = std::max(want_planes, cv->cap_planes);
+    want_leaks = std::max(want_leaks, cv->cap_leaks);
 
     CK(cv->unit_count.reserve(n_units + 1));
     CK(cv->unit_offset.reserve(n_units + 2));
@@ -487,6 +491,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->vals1.reserve(want_runs));
     CK(cv->cumulative.reserve(want_runs));
     CK(cv->long_rows.reserve(want_runs / 32 + 64));
+    CK(cv->leaks.reserve(want_leaks));
     CK(cv->te_flags.reserve(want_tiles));
     CK(cv->te_job.reserve(want_tiles));
     CK(cv->te_backdrop.reserve(size_t(want_tiles) * kTile));
@@ -514,7 +519,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->texels.reserve(std::max<uint64_t>(sf.n_texels, 1)));
     cv->cap_pts = want_pts; cv->cap_sources = want_sources; cv->cap_dash_subpaths = want_dash_sub;
     cv->cap_items = want_items; cv->cap_rows = want_rows; cv->cap_runs = want_runs;
-    cv->cap_tiles = want_tiles; cv->cap_planes = want_planes;
+    cv->cap_tiles = want_tiles; cv->cap_planes = want_planes; cv->cap_leaks = want_leaks;
     return CB200_OK;
 }
 
@@ -705,6 +710,7 @@ int upload_frame(cb200_canvas *cv)
     f.keys[0] = cv->keys0.p; f.keys[1] = cv->keys1.p; f.vals[0] = cv->vals0.p; f.vals[1] = cv->vals1.p;
     f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p; f.long_rows = cv->long_rows.p;
     f.loop_mark = cv->loop_mark.p; f.box_loops = cv->box_loops.p;
+    f.leaks = cv->leaks.p; f.cap_leaks = cv->cap_leaks;
     f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
     f.cap_tiles = cv->cap_tiles;
     f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
@@ -1158,7 +1164,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
-    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release();
+    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release(); cv->leaks.release();
     drop_replay_graphs(cv);
     cv->png_tables.release(); cv->png_row_crc.release(); cv->png_out.release(); cv->png_acc.release();
     cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();
@@ -1636,6 +1642,41 @@ void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_
     walk.finish();
     if (walk.hx >= 0) { lx = std::min(lx, walk.lx); hx = std::max(hx, walk.hx); ly = std::min(ly, walk.ly); hy = std::max(hy, walk.hy); }
     box5[0] = lx; box5[1] = hx; box5[2] = ly; box5[3] = hy; box5[4] = int(first_key);
+}
+
+// Host build of the device's scan conversion of ONE closed loop (clip_edge + per-scanline add_runs, projected
+// pieces included): every run as (x, y, delta), in edge / piece / scanline / pixel order.  Returns the run count
+// and copies at most `capacity`.  The CPU test compares this multiset with the reference's own add_runs over the
+// Sutherland-Hodgman-clipped loop, bit for bit (tests/test_scan_conversion.py).
+int64_t cb200_debug_loop_runs(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
+                              int32_t *run_xy, float *run_delta, int64_t capacity)
+{
+    struct collect_sink {
+        int32_t *xy; float *delta; int64_t cap, count; int y;
+        void put(float px, float d)
+        {
+            if (count < cap) { if (xy) { xy[2 * count] = int32_t(px); xy[2 * count + 1] = y; } if (delta) delta[count] = d; }
+            ++count;
+        }
+    };
+    collect_sink sink = { run_xy, run_delta, capacity, 0, 0 };
+    const float w = float(padded_w), h = float(padded_h);
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t q = k ? k - 1 : n - 1;
+        clipped_edge ce;
+        clip_edge(v2(off_x + xy[2 * q], off_y + xy[2 * q + 1]), v2(off_x + xy[2 * k], off_y + xy[2 * k + 1]), w, h, ce);
+        for (int i = 0; i < ce.n_pieces; ++i) {
+            const float4 pc = ce.piece[i];
+            if (fabsf(pc.w - pc.y) < 2.0e-5f) continue;
+            const edge_walk ew = edge_setup(pc);
+            for (int r = 0; r < ew.rows; ++r) {
+                const row_walk rw = row_setup(ew, r);
+                sink.y = int(rw.py);
+                walk_row_runs(ew, rw, sink);
+            }
+        }
+    }
+    return sink.count;
 }
 
 // join_acosf / join_tanf (geom.cuh) over an array, on the host or on the device: the rounded join's two libm

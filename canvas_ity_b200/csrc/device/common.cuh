@@ -128,7 +128,15 @@ enum { COMP_EVERYWHERE = 1, COMP_OPAQUE = 2 };   // comp_rec.flags
 enum { TE_NONEMPTY = 1, TE_COVERED = 2 };        // te_flags
 // job_box[j]: tile rectangle the job composites into, 11 bits per coordinate, + kind and flags:
 //   x = tx0 | ty0 << 11 | (tx1 & 0x3ff) << 22      y = tx1 >> 10 | ty1 << 1 | kind << 12 | flags
-enum { JOBBOX_EVERYWHERE = 1u << 14, JOBBOX_OPAQUE = 1u << 15 };
+enum { JOBBOX_EVERYWHERE = 1u << 14, JOBBOX_OPAQUE = 1u << 15, JOBBOX_LEAKY = 1u << 16 };
+
+// A scanline of a draw whose signed areas do not add up to zero: the coverage left over after the row's last
+// run.  render_main (hpp:2551-2605) walks the runs merged with the clip mask's, whose last run of every row
+// sits at the right canvas edge, so a residue of at least 1/8160 is painted all the way to that edge -- beyond
+// the draw's own bounding box (float rounding at coordinates in the thousands makes such residues real: tiger at
+// 4096^2, one row of draw 102).  k_rows lists them; the compositor consults the list for tiles to the right of a
+// leaky job's tile rectangle.
+struct leak_rec { uint32_t job; int32_t y; float sum; uint32_t pad; };
 
 struct frame_header {
     // inputs
@@ -145,6 +153,7 @@ struct frame_header {
     uint32_t n_runs;
     uint32_t n_tile_entries;
     uint32_t n_long_rows;                  // scanline segments handed to k_rows_long
+    uint32_t n_leaks;                      // scanlines of source_over-like draws whose coverage does not return to 0 (leak_rec)
     uint32_t n_box_loops;                  // loops of shadow jobs that cross a side or the top of the padded canvas
     uint64_t plane_floats;               // storage (pitched)
     uint64_t shadow_working_pixels;      // sum of bw * bh: what the reference blurs (hpp:2426)
@@ -155,7 +164,7 @@ struct frame_header {
 };
 
 enum { OVF_POINTS = 1, OVF_LOOPS = 2, OVF_ITEMS = 4, OVF_ROWS = 8, OVF_RUNS = 16, OVF_TILES = 32,
-       OVF_PLANES = 64, OVF_DASH = 128 };
+       OVF_PLANES = 64, OVF_DASH = 128, OVF_LEAKS = 256 };
 
 // ---- block-level primitives (kBlock threads) ----------------------------------
 

@@ -439,13 +439,23 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
             // stage the job record and this tile entry's rows: three independent coalesced loads
             uint32_t word = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
             const bool has_rows = __shfl_sync(0xffffffffu, word, 0) != JOB_SHADOW;      // word 0 = kind
-            float bk = has_rows ? f.te_backdrop[tte * kTile + lane] : 0.0f;
-            uint32_t fr = has_rows ? f.te_first[tte * kTile + lane] : kNoRun;
+            const bool leak_tile = tte == kNoRun;                                        // beyond a leaky job's rectangle
+            float bk = (has_rows && !leak_tile) ? f.te_backdrop[tte * kTile + lane] : 0.0f;
+            uint32_t fr = (has_rows && !leak_tile) ? f.te_first[tte * kTile + lane] : kNoRun;
             __syncwarp();
             reinterpret_cast<uint32_t *>(&ws.rec)[lane] = word;
             ws.back[lane] = bk;
             ws.first[lane] = fr;
             __syncwarp();
+            if (leak_tile) {
+                // rare: the rows of this job that leak are few, the list is short -- every lane scans a share
+                const int tile_row0 = ty_local * kTile;
+                for (uint32_t k = uint32_t(lane); k < h->n_leaks; k += 32) {
+                    const leak_rec l = f.leaks[k];
+                    if (l.job == jj && l.y >= tile_row0 && l.y < tile_row0 + kTile) ws.back[l.y - tile_row0] = l.sum;
+                }
+                __syncwarp();
+            }
             const comp_rec &c = ws.rec;
             const float *mask = (kGeneral && c.mask_src) ? t.mask_planes[c.mask_src] : nullptr;
             const uint32_t op = c.op;
@@ -564,6 +574,11 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
                     hit = (box.y & JOBBOX_EVERYWHERE) || (flags & TE_NONEMPTY);
                     cover = (box.y & JOBBOX_OPAQUE) && (flags & TE_COVERED);
                 }
+            } else if ((box.y & JOBBOX_LEAKY) && tx > bx1 && bx1 >= bx0 && ty_local >= by0 && ty_local <= by1) {
+                // to the right of a job with scanlines whose coverage never returns to zero (leak_rec): no tile
+                // entry there, the rows come from the frame's leak list
+                hit = true;
+                te = kNoRun;
             }
         }
         uint32_t votes = __ballot_sync(0xffffffffu, hit);

@@ -21,6 +21,30 @@ namespace {
 
 constexpr uint32_t kShortRow = 16;      // longer scanline segments go to the warp-cooperative kernel (48 -> 16: the CTA no longer waits at its barrier behind one long walk; coverage 0.141 -> 0.124 ms on the tiger)
 
+// What is left over after the last run of a scanline.  render_main and clip (hpp:2551-2605, 3057-3099) walk the
+// runs merged with the clip mask's, whose last run of a row sits at the right canvas edge: the residue carries on
+// to that edge -- to the end of the job's tile rectangle here, and beyond it through a leak record when the
+// rectangle (the outline's bounding box) stops short of the canvas.  render_shadow walks the runs alone
+// (hpp:2430-2452): after a row's last run only that run's own pixel is painted, nothing carries on.
+__device__ __forceinline__ void finish_row(const device_frame &f, frame_header *h, const job_rec &jr, uint32_t j, int y, int ly,
+                                           bool binned, bool everywhere, uint32_t te_row, int c_prev, int c_end, float sum)
+{
+    if (!binned || sum == 0.0f || jr.kind == JOB_SHADOW || !(everywhere || fabsf(sum) >= kThreshold)) return;
+    for (int cc = c_prev + 1; cc <= c_end; ++cc) {
+        uint32_t te = te_row + uint32_t(cc - jr.tx0);
+        f.te_backdrop[te * kTile + ly] = sum;
+        { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
+    }
+    if (!everywhere && (c_end + 1) * kTile < h->width) {             // an everywhere job's rectangle is the whole canvas
+        const uint32_t at = atomicAdd(&h->n_leaks, 1u);
+        if (at < f.cap_leaks) {
+            leak_rec l = { j, y, sum, 0u };
+            f.leaks[at] = l;
+            atomicOr(&f.job_box[j].y, JOBBOX_LEAKY);
+        } else atomicOr(&h->overflow, OVF_LEAKS);
+    }
+}
+
 // One short scanline segment, walked by one thread from its first run `i`.
 __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h, const uint64_t *keys, const float *delta,
                                          uint32_t n, uint32_t i, uint32_t bx, uint32_t by)
@@ -88,13 +112,7 @@ __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h,
         }
         key = kk[kBatch];
     }
-    // whatever is left over after the last run spills to the right edge
-    if (binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
-        for (int cc = c_prev + 1; cc <= c_end; ++cc) {
-            uint32_t te = te_row + uint32_t(cc - jr.tx0);
-            f.te_backdrop[te * kTile + ly] = sum;
-            { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
-        }
+    finish_row(f, h, jr, j, y, ly, binned, everywhere, te_row, c_prev, c_end, sum);
 }
 
 // A CTA takes 1024 consecutive runs per step, finds the segment heads among them (coalesced key
@@ -203,13 +221,7 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
             c_carry = max(c_carry, min(__shfl_sync(0xffffffffu, c, last_lane), c_end));
             if (vm != 0xffffffffu) break;
         }
-        float sum = float(carry);
-        if (lane == 0 && binned && sum != 0.0f && (everywhere || fabsf(sum) >= kThreshold))
-            for (int cc = c_carry + 1; cc <= c_end; ++cc) {
-                uint32_t te = te_row + uint32_t(cc - jr.tx0);
-                f.te_backdrop[te * kTile + ly] = sum;
-                { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
-            }
+        if (lane == 0) finish_row(f, h, jr, j, y, ly, binned, everywhere, te_row, c_carry, c_end, float(carry));
     }
 }
 

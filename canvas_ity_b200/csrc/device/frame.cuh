@@ -64,6 +64,7 @@ struct device_frame {
     // shadow working rectangles: loops of shadow jobs that leave the padded canvas (k_edges marks each once
     // and lists it, k_shadow_boxes walks their crossings -- shadow_box.cuh)
     uint32_t *loop_mark;   uint2 *box_loops;           // per loop id; (job, loop id)
+    leak_rec *leaks;       uint32_t cap_leaks;         // rows whose coverage residue reaches the right canvas edge
     // tiles
     uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
     float *planes, *planes_tmp;  uint64_t cap_planes;

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
         for (int ly = ly0; ly < ly1; ++ly) {
             const int y = ty * kTile + ly;
             float sum = __shfl_sync(0xffffffffu, carried, ly);
-            if (__shfl_sync(0xffffffffu, first, ly) != kNoRun) sum = tile_row_sum(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
+            if (__shfl_sync(0xffffffffu, first, ly) != kNoRun) sum = tile_row_sum<true>(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
             float cov = fminf(fabsf(sum), 1.0f);
             float v = 0.0f;
             if (cov >= kThreshold) {

@@ -37,6 +37,7 @@ __device__ __forceinline__ cov_source make_cov_source(const device_frame &f, int
 
 // `row_buf`: 32 floats of shared memory private to the calling warp.
 // (job, y) identify the scanline, x0 is the tile's left pixel in raster space.
+template <bool kStopAfterLastRun>
 __device__ __forceinline__ float tile_row_sum(const cov_source &c, uint32_t te, int ly, uint32_t job,
                                               int y, int x0, float *row_buf)
 {
@@ -49,17 +50,20 @@ __device__ __forceinline__ float tile_row_sum(const cov_source &c, uint32_t te, 
     const float quiet_nan = __int_as_float(0x7fc00000);
     row_buf[lane] = quiet_nan;
     __syncwarp();
+    bool row_goes_on = false;                               // runs of this row to the right of the tile
     for (uint32_t k = first;; k += 32) {
         uint32_t idx = k + uint32_t(lane);
         bool ok = idx < c.n_runs;
         uint64_t key = ok ? c.keys[idx] : ~0ull;
         int col = int(key & xmask) - x0;
-        ok = ok && (key >> c.bx) == row_key && col < kTile;
+        const bool same_row = ok && (key >> c.bx) == row_key;
+        ok = same_row && col < kTile;
         if (ok) {
             float v = c.cumulative[idx];
             if (v == v) row_buf[col] = v;                   // NaN = superseded by a later run
         }
-        if (!__all_sync(0xffffffffu, ok)) break;
+        const uint32_t stop = ~__ballot_sync(0xffffffffu, ok);
+        if (stop) { row_goes_on = __shfl_sync(0xffffffffu, same_row, __ffs(int(stop)) - 1); break; }
     }
     __syncwarp();
     float mine = row_buf[lane];
@@ -68,6 +72,9 @@ __device__ __forceinline__ float tile_row_sum(const cov_source &c, uint32_t te, 
     int src = upto ? 31 - __clz(upto) : 0;
     float got = __shfl_sync(0xffffffffu, mine, src);
     __syncwarp();
+    // render_shadow walks the runs alone (hpp:2430-2452): after the row's LAST run only that run's own pixel takes
+    // the sum (to = x + 1), nothing carries on to the right
+    if (kStopAfterLastRun && !row_goes_on && have && lane > 31 - __clz(have)) return 0.0f;
     return upto ? got : backdrop;
 }
 

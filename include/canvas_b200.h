@@ -322,6 +322,12 @@ int64_t cb200_debug_runs(cb200_canvas *canvas, uint64_t *keys, float *cumulative
 void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
                             int *box5);
 
+/* Host build of the device's scan conversion (csrc/device/edge_clip.cuh) of the closed loop xy[0 .. n): every
+ * signed-area run as run_xy[2 i] = x, run_xy[2 i + 1] = y, run_delta[i], unsorted.  Returns the count and copies at
+ * most `capacity`.  Touches no device. */
+int64_t cb200_debug_loop_runs(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
+                              int32_t *run_xy, float *run_delta, int64_t capacity);
+
 /* The rounded join's acosf / tanf (hpp:1995-1997) as the kernels compute them (csrc/geom.cuh: glibc's fdlibm
  * algorithms restated), over x[0 .. n): acos_out[i] = acosf(x[i]) for |x| <= 1, tan_out[i] = tanf(x[i]) for
  * 0 <= x <= pi/4.  on_device = 0 runs the host build of the same code, 1 a kernel. */

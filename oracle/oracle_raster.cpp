@@ -403,10 +403,9 @@ static void edge_deltas(Coverage &cov, P a, P b)
     } while (cur.y != b.y);
 }
 
-// hpp:2193-2253: Sutherland-Hodgman clip of every closed loop against the padded
-// canvas, clamp, per-edge deltas, then order each row by (x, |delta|) and merge
-// equal x.  Rows hold merged deltas afterwards.
-static void scan_convert(const Poly &poly, P offset, int width_px, int height_px, Coverage &cov)
+// hpp:2193-2240: Sutherland-Hodgman clip of every closed loop against the padded
+// canvas, clamp, per-edge deltas (rows hold the raw runs in emission order).
+static void scan_convert_raw(const Poly &poly, P offset, int width_px, int height_px, Coverage &cov)
 {
     float w = float(width_px), h = float(height_px);
     cov = Coverage();
@@ -438,6 +437,12 @@ static void scan_convert(const Poly &poly, P offset, int width_px, int height_px
                         mk(std::min(std::max(b.x, 0.0f), w), std::min(std::max(b.y, 0.0f), h)));
         }
     }
+}
+
+// hpp:2193-2253: scan_convert_raw, then the sort and the merge of equal pixels.
+static void scan_convert(const Poly &poly, P offset, int width_px, int height_px, Coverage &cov)
+{
+    scan_convert_raw(poly, offset, width_px, height_px, cov);
     // Merge in global (y, x, |delta|) order exactly like hpp:2244-2252: a run opens
     // a new entry only if its own delta is non-zero (the very first run always
     // does); later runs on the same pixel add to it.  The bounding box that
@@ -694,15 +699,28 @@ static void shadow_pass(Canvas &cv, const Poly &poly, const Brush &br, const cb2
     size_t bw = size_t(std::max(right - left, 0)), bh = size_t(std::max(bottom - top, 0));
     std::vector<float> plane(bw * bh + std::max(bw, bh) + radius + 4, 0.0f);
     M inv = mat(d.inverse);
-    std::vector<float> line;
+    // hpp:2430-2452: between two runs of a row the pixels get the running coverage; after the LAST run of a row only
+    // that run's own pixel does (to = x + 1 when the next run starts another row) -- unlike render_main, no mask run
+    // at the right canvas edge carries a residual sum onward -- and the last run of all is never painted (the loop
+    // paints on arrival of the next run).
+    int last_row = -1;
+    for (int y = top; y < bottom; ++y)
+        if (size_t(y) < cov.row.size() && !cov.row[size_t(y)].empty()) last_row = y;
     for (int y = top; y < bottom; ++y) {
         if (size_t(y) >= cov.row.size() || cov.row[size_t(y)].empty()) continue;
-        row_coverage(cov.row[size_t(y)], right, line);
-        for (int x = left; x < right && x < int(line.size()); ++x) {
-            float c = line[size_t(x)];
+        const std::vector<Delta> &r = cov.row[size_t(y)];
+        float sum = 0.0f;
+        for (size_t i = 0; i < r.size(); ++i) {
+            sum += r[i].d;
+            const bool last_of_row = i + 1 == r.size();
+            if (last_of_row && y == last_row) break;
+            int x0 = int(r[i].x), x1 = last_of_row ? x0 + 1 : int(r[i + 1].x);
+            float c = std::min(fabsf(sum), 1.0f);
             if (c < kThreshold) continue;
-            P centre = sub(mk(float(x) + 0.5f, float(y) + 0.5f), off);
-            plane[size_t(y - top) * bw + size_t(x - left)] = c * paint(br, inv, centre).a;
+            for (int x = std::max(x0, left); x < std::min(x1, right); ++x) {
+                P centre = sub(mk(float(x) + 0.5f, float(y) + 0.5f), off);
+                plane[size_t(y - top) * bw + size_t(x - left)] = c * paint(br, inv, centre).a;
+            }
         }
     }
     float alpha = float(2 * radius + 1) * (float(radius * (radius + 1)) - sigma2) /
@@ -1021,6 +1039,65 @@ int oracle_debug_shadow_boxes(const cb200_frame *frame, uint32_t draw_index, int
     if (first_key >= 0) enter(int(first_key & 0xffff), int(first_key >> 16));
     if (hx >= 0 && hy >= 0) { out[4] = lx; out[5] = hx; out[6] = ly; out[7] = hy; }
     return border;
+}
+
+// Stage tap for tests/test_scan_conversion.py: the outline of one draw (flattened, dashed, stroked) as closed loops
+// -- counts[l] points each, xy packed -- so a test can hand single loops to both scan converters.  Returns the number
+// of loops; *n_points the total point count (copies at most the capacities).
+long oracle_debug_loops(const cb200_frame *frame, uint32_t draw_index, float *xy, long cap_points, uint32_t *counts,
+                        long cap_loops, long *n_points)
+{
+    const cb200_draw &d = frame->draws[draw_index];
+    cb200_frame local = *frame;
+    std::vector<float> pts;
+    std::vector<cb200_subpath> subs;
+    if (frame->n_glyphs) {
+        expand_glyphs(frame, pts);
+        subs.assign(frame->subpaths, frame->subpaths + frame->n_subpaths);
+        for (size_t i = 0; i < subs.size(); ++i)
+            if (subs[i].instanced) { subs[i].first_point += frame->n_points; subs[i].instanced = 0; }
+        local.points = pts.data(); local.n_points = frame->n_points + frame->n_glyph_points;
+        local.subpaths = subs.data(); local.n_glyphs = 0;
+    }
+    Poly lines, work;
+    flatten(&local, d, lines);
+    if (d.kind == CB200_STROKE) {
+        if (d.n_dash) {
+            dash(lines, local.dashes + d.first_dash, d.n_dash, d.dash_offset, mat(d.inverse), work);
+            lines.pts.swap(work.pts); lines.subs.swap(work.subs);
+        }
+        StrokeStyle st;
+        st.half = d.line_width * 0.5f;
+        st.miter2 = d.miter_limit * d.miter_limit * st.half * st.half;
+        st.cap = d.cap; st.join = d.join;
+        st.fwd = mat(d.forward); st.inv = mat(d.inverse);
+        outline_stroke(lines, st, work);
+        lines.pts.swap(work.pts); lines.subs.swap(work.subs);
+    }
+    for (size_t i = 0; i < lines.pts.size() && long(i) < cap_points; ++i) { xy[2 * i] = lines.pts[i].x; xy[2 * i + 1] = lines.pts[i].y; }
+    for (size_t s = 0; s < lines.subs.size() && long(s) < cap_loops; ++s) counts[s] = uint32_t(lines.subs[s].first);
+    if (n_points) *n_points = long(lines.pts.size());
+    return long(lines.subs.size());
+}
+
+// The reference's scan conversion (polygon clip + add_runs, hpp:2193-2240, before the sort) of ONE closed loop:
+// every run as (x, y, delta).  Returns the count, copies at most `capacity`.
+long oracle_debug_loop_runs(const float *xy, uint32_t n, float off_x, float off_y, int padded_w, int padded_h,
+                            int32_t *run_xy, float *run_delta, long capacity)
+{
+    Poly one;
+    for (uint32_t i = 0; i < n; ++i) one.pts.push_back(mk(xy[2 * i], xy[2 * i + 1]));
+    one.subs.push_back(std::make_pair(size_t(n), true));
+    Coverage cov;
+    scan_convert_raw(one, mk(off_x, off_y), padded_w, padded_h, cov);
+    long count = 0;
+    for (int y = 0; y < cov.rows; ++y)
+        for (size_t r = 0; r < cov.row[size_t(y)].size(); ++r, ++count)
+            if (count < capacity) {
+                if (run_xy) { run_xy[2 * count] = int32_t(cov.row[size_t(y)][r].x); run_xy[2 * count + 1] = y; }
+                if (run_delta) run_delta[count] = cov.row[size_t(y)][r].d;
+            }
+    return count;
 }
 
 void oracle_tap_frame(void *user, const cb200_frame *frame) { oracle_submit(user, frame); }
