@@ -1626,7 +1626,7 @@ void cb200_debug_shadow_box(const float *xy, uint32_t n, float off_x, float off_
         for (int e = 0; e < ce.n_events; ++e) walk.consume(ce.ev[e].kind, ce.ev[e].v);
         for (int i = 0; i < ce.n_pieces; ++i) {
             const float4 pc = ce.piece[i];
-            if (ce.projected[i] || fabsf(pc.w - pc.y) < 2.0e-5f) continue;
+            if (ce.projected[i] || !piece_has_runs(pc, false)) continue;
             const edge_walk ew = edge_setup(pc);
             for (int r = 0; r < ew.rows; ++r) {
                 const row_walk rw = row_setup(ew, r);
@@ -1667,7 +1667,7 @@ int64_t cb200_debug_loop_runs(const float *xy, uint32_t n, float off_x, float of
         clip_edge(v2(off_x + xy[2 * q], off_y + xy[2 * q + 1]), v2(off_x + xy[2 * k], off_y + xy[2 * k + 1]), w, h, ce);
         for (int i = 0; i < ce.n_pieces; ++i) {
             const float4 pc = ce.piece[i];
-            if (fabsf(pc.w - pc.y) < 2.0e-5f) continue;
+            if (!piece_has_runs(pc, ce.projected[i] != 0)) continue;
             const edge_walk ew = edge_setup(pc);
             for (int r = 0; r < ew.rows; ++r) {
                 const row_walk rw = row_setup(ew, r);

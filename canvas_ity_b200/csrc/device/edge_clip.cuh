@@ -136,6 +136,16 @@ CB_HD void clip_edge(vec2 a, vec2 b, float w, float h, clipped_edge &out)
 
 // ------------------------------------------------------------ add_runs, per scanline ----
 
+// add_runs drops an edge flatter than 2e-5 (hpp:2113-2114).  A projected piece is exempt: the projections of an
+// excursion form a closed chain with the inside pieces only if every link is kept -- the reference has ONE boundary
+// segment there (or, for a loop wholly beside the canvas, nothing at all), so a dropped link would leave a coverage
+// residue of up to 2e-5 per loop that the reference does not have (round-1 fuzz seed 672: ten glyph outlines left
+// of the canvas, each with one 1.5e-5 link, add up to more than the 1/8160 paint threshold along a whole row).
+CB_HD bool piece_has_runs(float4 pc, bool projected)
+{
+    return projected ? pc.w != pc.y : !(fabsf(pc.w - pc.y) < 2.0e-5f);
+}
+
 struct edge_walk {
     vec2 from, to;
     float sign, ystep, dxdy, dydx, fx0, fy0;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) k_edges(device_frame f, canvas_target 
             if (i >= ce.n_pieces) continue;
             const float4 pc = ce.piece[i];
             uint32_t rows = 0, rlo = 0;
-            if (!(fabsf(pc.w - pc.y) < 2.0e-5f)) {
+            if (piece_has_runs(pc, ce.projected[i] != 0)) {
                 edge_walk e = edge_setup(pc);
                 // scanlines inside [row0, row1)
                 int r_first, r_last;                       // inclusive range of r

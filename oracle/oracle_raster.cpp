@@ -921,6 +921,18 @@ int oracle_read_mask(void *canvas, uint32_t slot, float *dst)
 long oracle_debug_edges(const cb200_frame *frame, uint32_t draw_index, float *edges, long capacity)
 {
     const cb200_draw &d = frame->draws[draw_index];
+    cb200_frame local = *frame;
+    std::vector<float> pts;
+    std::vector<cb200_subpath> subs;
+    if (frame->n_glyphs) {                       // text drawn as glyph instances: expand them first
+        expand_glyphs(frame, pts);
+        subs.assign(frame->subpaths, frame->subpaths + frame->n_subpaths);
+        for (size_t i = 0; i < subs.size(); ++i)
+            if (subs[i].instanced) { subs[i].first_point += frame->n_points; subs[i].instanced = 0; }
+        local.points = pts.data(); local.n_points = frame->n_points + frame->n_glyph_points;
+        local.subpaths = subs.data(); local.n_glyphs = 0;
+    }
+    frame = &local;
     Poly lines, work;
     flatten(frame, d, lines);
     if (d.kind == CB200_STROKE) {

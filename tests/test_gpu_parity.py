@@ -134,8 +134,11 @@ def test_full_size_properties_4096(lib):
     a = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
     b = H.render_script(lib, script, size, size, want_f32=False)["rgba8"]
     assert np.array_equal(a, b)
-    # the tiger's first draw paints its 733:757 page opaque; the side margins stay transparent
-    assert a[:, 100:3990, 3].min() == 255 and a[:, :60].max() == 0 and a[:, 4040:].max() == 0
+    # the tiger's first draw paints its 733:757 page opaque; the left margin stays transparent, the right one too but
+    # for single scanlines whose coverage residue the reference carries on to the canvas edge (hpp:2573; row 955 of
+    # draw 102, alpha ~ 4e-4 -- test_reference_fullsize.py compares that with the reference itself)
+    assert a[:, 100:3990, 3].min() == 255 and a[:, :60].max() == 0 and a[:, 4040:, 3].max() <= 1
+    assert (a[:, 4040:].reshape(size, -1).max(axis=1) > 0).sum() <= 8
     y0, rows = 1500, 300
     h = lib.cv_create_band(size, size, 0, y0, rows)
     try:
