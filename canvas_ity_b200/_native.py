@@ -105,6 +105,9 @@ SIGNATURES = {
     "cb200_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_timer_begin": (C.c_int, [C.c_void_p]),
     "cb200_timer_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "cb200_stream": (C.c_void_p, [C.c_void_p]),
+    "cb200_timer_stop": (C.c_int, [C.c_void_p]),
+    "cb200_timer_between": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "cb200_abi_version": (C.c_int, []),
     "cb200_device_count": (C.c_int, []),
     "cb200_struct_size": (C.c_int, [C.c_int]),

@@ -173,6 +173,7 @@ struct cb200_canvas {
     bool comp_ev_valid[kCompRing] = {};   // false for frames that ran inside a graph (no per-frame events)
     uint64_t frames_run = 0, timer_frame0 = 0;
     cudaEvent_t timer_ev[2] = {};
+    bool timer_stopped = false;       // cb200_timer_stop already recorded the end event
     std::vector<cudaEvent_t> chunk_events;
     cb200_stats stats;
     uint64_t launches = 0;
@@ -1254,11 +1255,21 @@ int cb200_timer_begin(cb200_canvas *cv)
     return CB200_OK;
 }
 
+int cb200_timer_stop(cb200_canvas *cv)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    CK(cudaEventRecord(cv->timer_ev[1], cv->stream));
+    cv->timer_stopped = true;
+    return CB200_OK;
+}
+
 int cb200_timer_end(cb200_canvas *cv, float *elapsed_ms, float *composite_ms, uint32_t *composite_frames)
 {
     if (!cv || !elapsed_ms) return fail(CB200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(cv->device));
-    CK(cudaEventRecord(cv->timer_ev[1], cv->stream));
+    if (!cv->timer_stopped) CK(cudaEventRecord(cv->timer_ev[1], cv->stream));
+    cv->timer_stopped = false;
     int rc = finish_pending(cv);
     if (rc != CB200_OK) return rc;
     CK(cudaEventSynchronize(cv->timer_ev[1]));
@@ -1277,6 +1288,18 @@ int cb200_timer_end(cb200_canvas *cv, float *elapsed_ms, float *composite_ms, ui
     }
     if (composite_ms) *composite_ms = sum;
     if (composite_frames) *composite_frames = counted;
+    return CB200_OK;
+}
+
+void *cb200_stream(cb200_canvas *cv) { return cv ? static_cast<void *>(cv->stream) : nullptr; }
+
+int cb200_timer_between(cb200_canvas *from, cb200_canvas *to, float *elapsed_ms)
+{
+    if (!from || !to || !elapsed_ms) return fail(CB200_ERR_BAD_ARG, "null argument");
+    if (from->device != to->device) return fail(CB200_ERR_BAD_ARG, "cb200_timer_between: canvases on different devices");
+    CK(cudaSetDevice(from->device));
+    CK(cudaEventSynchronize(to->timer_ev[1]));
+    CK(cudaEventElapsedTime(elapsed_ms, from->timer_ev[0], to->timer_ev[1]));
     return CB200_OK;
 }
 

@@ -307,6 +307,17 @@ int cb200_set_stage_timing(cb200_canvas *canvas, int on);
  * per-frame events; *composite_frames says how many were summed). */
 int cb200_timer_begin(cb200_canvas *canvas);
 int cb200_timer_end(cb200_canvas *canvas, float *elapsed_ms, float *composite_ms, uint32_t *composite_frames);
+/* The canvas' CUDA stream (a cudaStream_t): everything a canvas does is ordered on it, so a caller that chains its
+ * own device work -- an NCCL gather of finished bands, say -- enqueues it there (or makes its stream wait on an
+ * event recorded there) instead of synchronising with the host. */
+void *cb200_stream(cb200_canvas *canvas);
+/* Record the end event now without waiting (cb200_timer_end then only waits and reads): with several canvases,
+ * stop all of them first so that no end event is recorded late because the host was waiting on another canvas. */
+int cb200_timer_stop(cb200_canvas *canvas);
+/* Milliseconds from `from`'s _begin event to `to`'s _end event (both recorded, same device): with several canvases
+ * replaying concurrently the timed region is the earliest begin to the latest end, the maximum of this over all
+ * pairs. */
+int cb200_timer_between(cb200_canvas *from, cb200_canvas *to, float *elapsed_ms);
 
 /* Debug taps used by the parity tests: intermediate buffers of the last frame.
  * Each returns the element count (>= 0) and copies at most `capacity`. */

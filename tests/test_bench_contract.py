@@ -24,8 +24,12 @@ def run_bench(*flags, env=None):
 
 
 def test_reference_arm_line():
-    line = run_bench("--impl", "reference", "--size", "200", "--steps", "1", "--warmup", "1")
+    line = run_bench("--impl", "reference", "--size", "200", "--steps", "3", "--warmup", "2")
     assert COMMON <= set(line) and line["impl"] == "reference"
+    assert line["steps"] == 3 and line["warmup"] == 2                       # the arm honours --steps / --warmup
+    sys.path.insert(0, H.ROOT)
+    import bench
+    assert line["config"]["workload"] == bench.workload_name(200)           # the same string our arm prints
     assert line["value"] > 0 and line["unit"] == "frames/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
@@ -44,10 +48,14 @@ def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch):
 
 @pytest.mark.gpu
 def test_our_arm_line():
-    line = run_bench("--size", "1024", "--steps", "6", "--warmup", "3", "--lanes", "2", "--no-cpu-baseline")
+    line = run_bench("--size", "1024", "--steps", "6", "--warmup", "3", "--lanes", "2", "--no-cpu-baseline", "--skip-configs")
     assert COMMON <= set(line) and "impl" not in line
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 6 and line["scaling"] == "weak"
-    assert line["gpu_launches"] >= 6 * 30
+    assert line["config"]["frames_per_step"] == 2 and line["gpu_launches"] >= 6 * 2 * 30
+    assert line["timed"]["regions"] >= 3 and (line["timed"]["seconds_timed"] >= 0.5 or line["timed"]["regions"] == 64)
+    assert line["span_ms"]["min"] <= line["span_ms"]["median"] <= line["span_ms"]["max"]
+    assert abs(line["value"] - 6 * 2 / (line["span_ms"]["median"] * 1e-3)) < 1e-6 * line["value"]
+    assert abs(line["ms_per_step"] - line["span_ms"]["median"] / 6) < 1e-9
     roof = line["roofline"]
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["achieved"] > 0
