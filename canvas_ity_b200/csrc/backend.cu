@@ -116,7 +116,7 @@ struct cb200_canvas {
     // device work buffers
     dev_buf<uint32_t> unit_count, unit_offset, pt_loop, dash_pts_count, dash_sub_count, dash_tail,
         half_count, half_offset, half_unit_off, half_dirty, stroke_unit_pts, half_last, visit_prev, long_rows, piece_job, piece_rows, piece_rlo, piece_row_off, row_runs, row_piece, te_flags, te_job,
-        te_first, partials, sort_hist;
+        te_first, te_mask, partials, sort_hist;
     dev_buf<float2> pts;
     dev_buf<loop_span> loops;
     dev_buf<stroke_src> sources;
@@ -126,6 +126,7 @@ struct cb200_canvas {
     dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count, loop_mark;
     dev_buf<uint2> box_loops;
     dev_buf<leak_rec> leaks;  uint32_t cap_leaks = 0;
+    dev_buf<uint32_t> tile_cover;
     dev_buf<uint64_t> keys0, keys1;
     dev_buf<float> vals0, vals1, cumulative, te_backdrop, planes, planes_tmp;
     dev_buf<uint8_t> rgba8, visit_close;
@@ -493,10 +494,17 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->cumulative.reserve(want_runs));
     CK(cv->long_rows.reserve(want_runs / 32 + 64));
     CK(cv->leaks.reserve(want_leaks));
+    {   // one word per tile of the target (band or stacked batch)
+        const size_t tiles_x = size_t((cv->width + kTile - 1) / kTile);
+        const size_t rows = cv->n_canvases > 1 ? size_t(cv->n_canvases) * size_t(cv->slot_rows / kTile)
+                                                : size_t((cv->band_y0 + cv->band_rows - 1) / kTile - cv->band_y0 / kTile + 1);
+        CK(cv->tile_cover.reserve(tiles_x * rows));
+    }
     CK(cv->te_flags.reserve(want_tiles));
     CK(cv->te_job.reserve(want_tiles));
     CK(cv->te_backdrop.reserve(size_t(want_tiles) * kTile));
     CK(cv->te_first.reserve(size_t(want_tiles) * kTile));
+    CK(cv->te_mask.reserve(size_t(want_tiles) * kTile));
     CK(cv->planes.reserve(want_planes));
     CK(cv->planes_tmp.reserve(want_planes));
     CK(cv->partials.reserve(8 * kGrid));
@@ -712,7 +720,8 @@ int upload_frame(cb200_canvas *cv)
     f.cap_runs = cv->cap_runs; f.cumulative = cv->cumulative.p; f.long_rows = cv->long_rows.p;
     f.loop_mark = cv->loop_mark.p; f.box_loops = cv->box_loops.p;
     f.leaks = cv->leaks.p; f.cap_leaks = cv->cap_leaks;
-    f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p;
+    f.tile_cover = cv->tile_cover.p; f.n_target_tiles = uint32_t(cv->tile_cover.cap);
+    f.te_flags = cv->te_flags.p; f.te_job = cv->te_job.p; f.te_backdrop = cv->te_backdrop.p; f.te_first = cv->te_first.p; f.te_mask = cv->te_mask.p;
     f.cap_tiles = cv->cap_tiles;
     f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
     f.partials = cv->partials.p; f.sort_hist = cv->sort_hist.p;
@@ -753,6 +762,7 @@ int enqueue_frame(cb200_canvas *cv, bool in_graph)
     auto mark = [&](cudaEvent_t e) { return in_graph ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
     CK(cudaMemsetAsync(cv->partials.p, 0, sizeof(uint32_t) * 8 * kGrid, s));
     if (f.n_shadow_jobs) CK(cudaMemsetAsync(cv->loop_mark.p, 0, sizeof(uint32_t) * f.cap_loops, s));
+    CK(cudaMemsetAsync(cv->tile_cover.p, 0, sizeof(uint32_t) * f.n_target_tiles, s));
     // Stage events sit between kernels and so cut the programmatic-dependent-launch chain there;
     // with stage timing off only the frame and the compositor are bracketed.
     const bool stages = cv->stage_timing && !in_graph;
@@ -1161,11 +1171,11 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->dash_pts_count.release(); cv->dash_sub_count.release(); cv->dash_tail.release();
     cv->half_count.release(); cv->half_offset.release(); cv->half_unit_off.release(); cv->half_dirty.release(); cv->stroke_unit_pts.release(); cv->half_last.release(); cv->visit_prev.release(); cv->visit_close.release(); cv->piece_job.release();
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
-    cv->row_runs.release(); cv->row_piece.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->partials.release();
+    cv->row_runs.release(); cv->row_piece.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->te_mask.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
     cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
-    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release(); cv->leaks.release();
+    cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release(); cv->leaks.release(); cv->tile_cover.release();
     drop_replay_graphs(cv);
     cv->png_tables.release(); cv->png_row_crc.release(); cv->png_out.release(); cv->png_acc.release();
     cv->hit_edges.release(); cv->hit_queries.release(); cv->hit_acc.release(); cv->hit_inside.release();

@@ -112,16 +112,19 @@ struct job_rec {
     uint32_t canvas;                       // batch slot this job draws into
 };
 
-// Everything the tile compositor needs to know about one job, packed into one
-// 128-byte line so a warp fetches it with a single coalesced load.
+// Everything the tile compositor needs to know about one job, one 128-byte line.  The first 48 bytes are what every
+// job needs (three 16-byte loads with a warp-uniform address); the rest only shadows, masks and non-solid brushes.
 struct comp_rec {
-    uint32_t kind, op, flags, mask_src, mask_dst, brush, draw, te_base;
-    int32_t tx0, ty0, tw, th, cx0, cy0, cx1, cy1;
-    float alpha;                       // global_alpha
-    float color[4];                    // solid colour, or the shadow tint
-    int32_t border, left, top, bw;     // shadow plane placement: storage origin (left - skew, top), row pitch
-    uint32_t plane_lo, plane_hi;       // plane offset (floats), 64 bit
-    uint32_t brush_type, pad[4];
+    uint32_t kind, op, flags, brush_type;              // brush_type 0xff: an empty brush paints nothing
+    float color[4];                                    // solid colour, or the shadow tint
+    float alpha;                                       // global_alpha
+    uint32_t mask_src, mask_dst, brush;
+    int32_t cx0, cy0, cx1, cy1;                        // canvas pixels a shadow job composites into
+    int32_t border, left, top, bw;                     // shadow plane placement: storage origin (left - skew, top), row pitch
+    uint32_t plane_lo, plane_hi;                       // plane offset (floats), 64 bit
+    uint32_t draw, te_base;
+    int32_t tx0, ty0, tw, th;
+    uint32_t pad[4];
 };
 static_assert(sizeof(comp_rec) == 128, "comp_rec must be one 128 B line");
 enum { COMP_EVERYWHERE = 1, COMP_OPAQUE = 2 };   // comp_rec.flags

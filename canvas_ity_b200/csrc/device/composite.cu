@@ -153,60 +153,6 @@ __device__ __forceinline__ void blend_unclipped(float4 &back, rgba fore, uint32_
 constexpr int kWarpRows = 8;                                 // scanlines of a tile owned by one warp
 constexpr int kTileWarps = kTile / kWarpRows;               // 4 warps per tile
 constexpr int kCompBlock = 32 * kTileWarps;                 // one CTA = one tile = 128 threads
-constexpr int kList = 64;                                   // job list capacity per warp
-
-// Coverage of one tile row from staged row info (see tile_cov.cuh for the global
-// memory variant used by the shadow rasteriser).  row_prefetch() requests the first 32 runs of a
-// row -- key and running sum TOGETHER, the sum is not held back until the key has been checked:
-// one dependent global-memory hop less per row (tiger 4096^2: k_composite 0.193 -> 0.174 ms).
-// Also requesting row r + 1 while row r is resolved, or the next job's record while this one is
-// painted, costs more in spills than it hides at 64 registers (measured: 0.179 / 0.181 ms).
-__device__ __forceinline__ void row_prefetch(const cov_source &c, uint32_t first, uint64_t &key, float &v)
-{
-    const uint32_t idx = first + uint32_t(threadIdx.x & 31);
-    const bool in = first != kNoRun && idx < c.n_runs;
-    key = in ? c.keys[idx] : ~0ull;
-    v = in ? c.cumulative[idx] : __int_as_float(0x7fc00000);
-}
-
-__device__ __forceinline__ float staged_row_sum(const cov_source &c, float backdrop, uint32_t first, uint32_t job,
-                                                int y, int x0, float *row_buf, uint64_t key, float v)
-{
-    if (first == kNoRun) return backdrop;
-    const int lane = threadIdx.x & 31;
-    const uint64_t row_key = (uint64_t(job) << c.by) | uint64_t(uint32_t(y));
-    const uint64_t xmask = (1ull << c.bx) - 1;
-    row_buf[lane] = __int_as_float(0x7fc00000);
-    __syncwarp();
-    for (uint32_t k = first;;) {
-        const int col = int(key & xmask) - x0;
-        const bool ok = (key >> c.bx) == row_key && col < kTile;       // key = ~0 past the last run: never ok
-        if (ok && v == v) row_buf[col] = v;                            // NaN = superseded by a later run
-        if (!__all_sync(0xffffffffu, ok)) break;
-        k += 32;
-        const uint32_t idx = k + uint32_t(lane);
-        const bool in = idx < c.n_runs;
-        key = in ? c.keys[idx] : ~0ull;
-        v = in ? c.cumulative[idx] : __int_as_float(0x7fc00000);
-    }
-    __syncwarp();
-    float mine = row_buf[lane];
-    uint32_t have = __ballot_sync(0xffffffffu, mine == mine);
-    uint32_t upto = have & (0xffffffffu >> (31 - lane));
-    int src = upto ? 31 - __clz(upto) : 0;
-    float got = __shfl_sync(0xffffffffu, mine, src);
-    __syncwarp();
-    return upto ? got : backdrop;
-}
-
-__device__ __forceinline__ float staged_row_sum(const cov_source &c, float backdrop, uint32_t first, uint32_t job,
-                                                int y, int x0, float *row_buf)
-{
-    uint64_t key;
-    float v;
-    row_prefetch(c, first, key, v);
-    return staged_row_sum(c, backdrop, first, job, y, x0, row_buf, key, v);
-}
 
 // A non-solid brush staged in shared memory once per (job, warp): record, brush-space matrix and
 // up to kStagedStops gradient stops, so the per-pixel code touches no global tables.
@@ -354,22 +300,22 @@ __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t
     return paint_at(f, f.brushes[brush], f.draws[draw].inverse, v2(x, y));
 }
 
-// Per-warp scratch in shared memory.
-struct warp_scratch {
-    comp_rec rec;                       // staged job record (128 B)
-    float back[kTile];                  // staged tile-entry rows: sum carried in from the left ...
-    uint32_t first[kTile];              // ... and first run inside the tile
-    float row_buf[kTile];
-    uint32_t job[kList], te[kList];
-    staged_brush brush;
-};
-
-// One WARP owns 8 scanlines x 32 pixels of a tile (8 pixels per lane, in registers) and works
-// completely on its own: no block-wide barrier anywhere, so an SM keeps ~20 independent
-// tile-quarters in flight and their dependent loads (job table -> tile entry -> runs) overlap.
-// Three builds of the same code, picked by the host per frame (device_frame::general_compositor):
+// One WARP owns 8 scanlines x 32 pixels of a tile (8 pixels per lane, in registers) and works completely on its
+// own: no block-wide barrier anywhere, so an SM keeps ~20 independent tile-quarters in flight and their dependent
+// loads (job table -> tile entry -> sums) overlap.  Per warp:
+//   * occlusion culling comes first and costs one load: k_tile_flags left, per tile, the last job that covers the
+//     whole tile with an opaque colour (cov = vis = 1, source_over / copy: the draw REPLACES the pixel exactly).
+//     Everything before it -- including the old pixels -- is irrelevant; the replay starts at that job;
+//   * the old pixels are requested right away otherwise, so that their latency overlaps the job search;
+//   * the job search tests 32 candidates per step against the compact table (8 B tile box + flags, 4 B first tile
+//     entry) and replays the hits of the step immediately, in order: no hit list, one replay site;
+//   * a hit needs three 16-byte loads of its record (warp-uniform address) and ONE coalesced load of this warp's
+//     eight rows of the tile entry (lanes 0-7 the sums carried in, 8-15 the first compacted entries, 16-23 the pixel
+//     masks), handed to the rows by shuffles -- no shared memory, no warp synchronisation in the solid-colour builds;
+//   * per row and pixel: coverage = one popc + one load (tile_cov.cuh), paint, the 4-bit Porter-Duff program.
+// Builds of the same code, picked by the host per frame (device_frame::general_compositor):
 //   kMode 0  lean: frames that only hold unclipped solid-colour fills and strokes without shadows
-//            (the tiger, most UI and plots) -- no gradient/pattern/mask/shadow code, no spills
+//            (the tiger, most UI and plots) -- no gradient/pattern/mask/shadow code
 //   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
 //   kMode 2  lean + unclipped gradient brushes with at most kStagedStops stops (full-canvas gradient fills)
 //   kMode 3  everything: masks, shadows, gradients, patterns
@@ -379,20 +325,18 @@ struct warp_scratch {
 #define CB200_COMP_CTAS0 8
 #endif
 template <int kMode, bool kLists>
-__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5) k_composite(device_frame f, canvas_target t, int sb,
-                                                          int tiles_x, int tile_y0, int eager_load)
+__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5)
+k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager_load)
 {
     constexpr bool kGeneral = kMode == 1 || kMode == 3, kPaint = kMode >= 2, kPattern = kMode == 3;
     grid_dependency_wait();
-    __shared__ __align__(16) warp_scratch scratch[kTileWarps];
+    __shared__ __align__(16) staged_brush staged_brushes[kPaint ? kTileWarps : 1];
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    warp_scratch &ws = scratch[warp];
     const int tx = blockIdx.x % tiles_x, ty = tile_y0 + blockIdx.x / tiles_x;
     const int x = tx * kTile + lane;
     const int band_y1 = t.band_y0 + t.band_rows;
-    const int tile_x0 = tx * kTile;
     // batches stack their canvases vertically: which canvas is this tile in, and where does it start?
     int canvas = 0, ty_local = ty;
     if (t.n_canvases > 1) {
@@ -403,108 +347,151 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
     const int yoff = canvas * t.slot_rows;                   // fb row of the canvas' row 0 (0 unless batched)
     const int row0 = ty_local * kTile + warp * kWarpRows;    // first scanline of this warp, canvas coordinates
     const uint2 job_range = t.canvas_jobs[canvas];
-    const uint32_t job_begin = job_range.x, job_end = job_range.x + job_range.y;
+    const uint32_t job_end = job_range.x + job_range.y;
     if (row0 >= band_y1 || row0 + kWarpRows <= t.band_y0) return;
+    const uint32_t *row_list = kLists ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
+    const uint32_t search_end = kLists ? f.row_job_count[ty - tile_y0] : job_end;
+    if (search_end == (kLists ? 0u : job_range.x) && !t.clear_first) return;      // no job reaches this tile row
 
-    // The old pixels are requested right away so that their latency overlaps the job search
-    // (they are dropped again if a covering job turns up).
+    // occlusion culling: the last opaque job that covers this tile voids everything before it
+    const uint32_t cover = f.tile_cover[blockIdx.x];
+    const uint32_t first_job = cover ? cover - 1u : job_range.x;
+
     float4 px[kWarpRows];
     uint32_t live_mask = 0;                                  // bit r: scanline row0 + r is ours and x is on the canvas
     const size_t local_index = size_t(row0 - t.band_y0) * size_t(t.width) + size_t(x);   // into canvas-sized planes
     float4 *const fb_at = t.fb + (size_t(yoff) * size_t(t.width) + local_index);         // this lane's first pixel
+    const bool fetch_now = eager_load && !t.clear_first && !cover;
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
         const int y = row0 + r;
         const bool live = x < t.width && y >= t.band_y0 && y < band_y1;
         live_mask |= uint32_t(live) << r;
-        px[r] = (live && eager_load && !t.clear_first) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        px[r] = (live && fetch_now) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    bool loaded = eager_load != 0 || t.clear_first != 0;
-    const cov_source cs = make_cov_source(f, sb);
-    const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
+    bool loaded = fetch_now || t.clear_first != 0 || cover != 0;
+    bool touched = cover != 0;
     uint32_t painted = 0;
-    bool touched = false;
-    uint32_t n_list = 0;
+    const paint_tables tables = { f.colors, f.stops, f.texels, f.brushes, f.draws };
+    staged_brush &sbrush = staged_brushes[kPaint ? warp : 0];
 
-    // Replays the jobs collected in ws.job[0 .. n_list) in order.
-    auto flush = [&]() {
-        if (n_list && !loaded) {                          // lazy variant: fetch the old pixels on first use
+    for (uint32_t base = kLists ? 0u : first_job; base < search_end; base += 32) {
+        const uint32_t at = base + uint32_t(lane);
+        const uint32_t j = kLists ? (at < search_end ? row_list[at] : job_end) : at;
+        uint32_t te = 0;
+        bool hit = false;
+        if (j < job_end && j >= first_job) {
+            const uint2 box = f.job_box[j];
+            const int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
+            const int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
+            if (ty_local >= by0 && ty_local <= by1 && tx >= bx0) {
+                if (tx <= bx1) {
+                    if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
+                    else {
+                        te = f.job_te[j] + uint32_t(ty_local - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
+                        hit = (box.y & JOBBOX_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY);
+                    }
+                } else if ((box.y & JOBBOX_LEAKY) && bx1 >= bx0) {
+                    // to the right of a job with scanlines whose coverage never returns to zero (leak_rec): no tile
+                    // entry there, the rows come from the frame's leak list
+                    hit = true;
+                    te = kNoRun;
+                }
+            }
+        }
+        uint32_t votes = __ballot_sync(0xffffffffu, hit);
+        if (votes && !loaded) {                               // lazy variant: fetch the old pixels on first use
 #pragma unroll
             for (int r = 0; r < kWarpRows; ++r)
                 if (live_mask >> r & 1u) px[r] = __ldcs(fb_at + size_t(r) * size_t(t.width));
             loaded = true;
         }
-        for (uint32_t q = 0; q < n_list; ++q) {
-            const uint32_t jj = ws.job[q], tte = ws.te[q];
-            // stage the job record and this tile entry's rows: three independent coalesced loads
-            uint32_t word = reinterpret_cast<const uint32_t *>(&f.comp[jj])[lane];
-            const bool has_rows = __shfl_sync(0xffffffffu, word, 0) != JOB_SHADOW;      // word 0 = kind
-            const bool leak_tile = tte == kNoRun;                                        // beyond a leaky job's rectangle
-            float bk = (has_rows && !leak_tile) ? f.te_backdrop[tte * kTile + lane] : 0.0f;
-            uint32_t fr = (has_rows && !leak_tile) ? f.te_first[tte * kTile + lane] : kNoRun;
-            __syncwarp();
-            reinterpret_cast<uint32_t *>(&ws.rec)[lane] = word;
-            ws.back[lane] = bk;
-            ws.first[lane] = fr;
-            __syncwarp();
-            if (leak_tile) {
-                // rare: the rows of this job that leak are few, the list is short -- every lane scans a share
-                const int tile_row0 = ty_local * kTile;
-                for (uint32_t k = uint32_t(lane); k < h->n_leaks; k += 32) {
-                    const leak_rec l = f.leaks[k];
-                    if (l.job == jj && l.y >= tile_row0 && l.y < tile_row0 + kTile) ws.back[l.y - tile_row0] = l.sum;
-                }
-                __syncwarp();
+        touched = touched || votes != 0;
+        while (votes) {
+            const int src = __ffs(int(votes)) - 1;
+            votes &= votes - 1u;
+            const uint32_t jj = __shfl_sync(0xffffffffu, j, src), tte = __shfl_sync(0xffffffffu, te, src);
+            // the job's record: three 16-byte loads, the same address in every lane
+            const comp_rec *rec = f.comp + jj;
+            const uint4 head = __ldg(reinterpret_cast<const uint4 *>(rec));            // kind, op, flags, brush_type
+            const float4 colour = __ldg(reinterpret_cast<const float4 *>(rec) + 1);
+            const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);        // alpha, mask_src, mask_dst, brush
+            const uint32_t kind = head.x, op = head.y, brush_type = head.w;
+            const float alpha = __uint_as_float(tail.x);
+            // this warp's eight rows of the tile entry in one load: lanes 0-7 carried-in sums, 8-15 first compacted
+            // entries, 16-23 pixel masks
+            const bool leak_tile = tte == kNoRun;
+            uint32_t info = (lane >= 8 && lane < 16) ? kNoRun : 0u;
+            if (kind != JOB_SHADOW && !leak_tile && lane < 24) {
+                const uint32_t slot = tte * kTile + uint32_t(warp * kWarpRows + (lane & 7));
+                info = lane < 8 ? __float_as_uint(f.te_backdrop[slot]) : lane < 16 ? f.te_first[slot] : f.te_mask[slot];
             }
-            const comp_rec &c = ws.rec;
-            const float *mask = (kGeneral && c.mask_src) ? t.mask_planes[c.mask_src] : nullptr;
-            const uint32_t op = c.op;
-            if (kGeneral && c.kind == JOB_SHADOW) {
-                const float *plane = f.planes + (uint64_t(c.plane_hi) << 32 | c.plane_lo);
-                const rgba tint = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
+            if (leak_tile) {
+                // rare: the rows of this job that leak are few, the list is short -- every lane scans a share and
+                // hands what it finds to the lane that holds that row's carried-in sum
+                for (uint32_t k0 = 0; k0 < h->n_leaks; k0 += 32) {
+                    const uint32_t k = k0 + uint32_t(lane);
+                    leak_rec l = { 0xffffffffu, 0, 0.0f, 0u };
+                    if (k < h->n_leaks) l = f.leaks[k];
+                    const bool mine = l.job == jj && l.y >= row0 && l.y < row0 + kWarpRows;
+                    uint32_t found = __ballot_sync(0xffffffffu, mine);
+                    while (found) {
+                        const int from = __ffs(int(found)) - 1;
+                        found &= found - 1u;
+                        const int r = __shfl_sync(0xffffffffu, l.y, from) - row0;
+                        const float sum = __shfl_sync(0xffffffffu, l.sum, from);
+                        if (lane == r) info = __float_as_uint(sum);
+                    }
+                }
+            }
+            const float *mask = (kGeneral && tail.y) ? t.mask_planes[tail.y] : nullptr;
+            if (kGeneral && kind == JOB_SHADOW) {
+                const int4 box = __ldg(reinterpret_cast<const int4 *>(rec) + 3);       // cx0, cy0, cx1, cy1
+                const int4 place = __ldg(reinterpret_cast<const int4 *>(rec) + 4);     // border, left, top, pitch
+                const uint2 off = __ldg(reinterpret_cast<const uint2 *>(rec) + 10);    // plane offset
+                const float *plane = f.planes + (uint64_t(off.y) << 32 | off.x);
+                const rgba tint = mk(colour.x, colour.y, colour.z, colour.w);
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
-                    if (!(live_mask >> r & 1u) || x < c.cx0 || x >= c.cx1 || y < c.cy0 || y >= c.cy1) continue;
+                    if (!(live_mask >> r & 1u) || x < box.x || x >= box.z || y < box.y || y >= box.w) continue;
                     float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
                     if (vis < kThreshold) continue;
-                    float s = plane[size_t(y + c.border - c.top) * size_t(c.bw) + size_t(x + c.border - c.left)];
-                    blend(px[r], scale(c.alpha * s, tint), op, vis);
+                    float s = plane[size_t(y + place.x - place.z) * size_t(place.w) + size_t(x + place.x - place.y)];
+                    blend(px[r], scale(alpha * s, tint), op, vis);
                     ++painted;
                 }
                 continue;
             }
             const bool everywhere = (~op & 8u) != 0;
-            const uint32_t brush_type = c.brush_type;
-            const rgba flat = mk(c.color[0], c.color[1], c.color[2], c.color[3]);
-            const float alpha = c.alpha;
-            float *mask_out = (kGeneral && c.kind == JOB_CLIP) ? t.mask_planes[c.mask_dst] : nullptr;
+            const rgba flat = mk(colour.x, colour.y, colour.z, colour.w);
+            float *mask_out = (kGeneral && kind == JOB_CLIP) ? t.mask_planes[tail.z] : nullptr;
             const bool gradient = brush_type == CB200_BRUSH_LINEAR || brush_type == CB200_BRUSH_RADIAL;
             bool staged = false;
-            if (kPaint && (gradient || (kPattern && brush_type == CB200_BRUSH_PATTERN)) && c.kind == JOB_MAIN) {
+            if (kPaint && (gradient || (kPattern && brush_type == CB200_BRUSH_PATTERN)) && kind == JOB_MAIN) {
                 // stage the brush: record (14 words), brush-space matrix (6 words), gradient stops
-                const brush_rec *gb = &f.brushes[c.brush];
+                const brush_rec *gb = &f.brushes[tail.w];
                 const uint32_t n_stops = gradient ? gb->n_colors : 0;
                 staged = n_stops <= kStagedStops;
+                __syncwarp();
                 if (staged) {
                     if (lane < int(sizeof(brush_rec) / 4))
-                        reinterpret_cast<uint32_t *>(&ws.brush.b)[lane] = reinterpret_cast<const uint32_t *>(gb)[lane];
+                        reinterpret_cast<uint32_t *>(&sbrush.b)[lane] = reinterpret_cast<const uint32_t *>(gb)[lane];
                     if (lane < 6)
-                        reinterpret_cast<float *>(&ws.brush.inv)[lane] = reinterpret_cast<const float *>(&f.draws[c.draw].inverse)[lane];
+                        reinterpret_cast<float *>(&sbrush.inv)[lane] = reinterpret_cast<const float *>(&f.draws[rec->draw].inverse)[lane];
                     if (uint32_t(lane) < n_stops) {
-                        ws.brush.stops[lane] = f.stops[gb->first_color + lane];
-                        ws.brush.colors[lane] = f.colors[gb->first_color + lane];
+                        sbrush.stops[lane] = f.stops[gb->first_color + lane];
+                        sbrush.colors[lane] = f.colors[gb->first_color + lane];
                     }
                 }
                 __syncwarp();
             }
-            const float *back_row = ws.back + warp * kWarpRows;
-            const uint32_t *first_row = ws.first + warp * kWarpRows;
             if ((!kGeneral && !kPaint) || (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR)) {
                 // the common case -- unclipped solid colour -- carries no per-row address arithmetic
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
-                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, row0 + r, tile_x0, ws.row_buf);
+                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
+                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
                     float cov = fminf(fabsf(sum), 1.0f);
                     if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
                     ++painted;
@@ -512,97 +499,42 @@ __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kM
                 }
             } else if (kPaint && staged && gradient && !mask && !mask_out) {
                 // unclipped gradient fill: the brush set-up is hoisted out of the pixel loop
-                const gradient_ctx g = make_gradient_ctx(ws.brush);
+                const gradient_ctx g = make_gradient_ctx(sbrush);
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
-                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, row0 + r, tile_x0, ws.row_buf);
+                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
+                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
                     float cov = fminf(fabsf(sum), 1.0f);
                     if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
                     ++painted;
-                    rgba paint = gradient_at(g, ws.brush, float(x) + 0.5f, float(row0 + r) + 0.5f);
+                    rgba paint = gradient_at(g, sbrush, float(x) + 0.5f, float(row0 + r) + 0.5f);
                     blend_unclipped(px[r], scale(cov * alpha, paint), op);
                 }
             } else if (kGeneral) {
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
-                    // warp-uniform: every lane of the warp shares the row
-                    float sum = staged_row_sum(cs, back_row[r], first_row[r], jj, y, tile_x0, ws.row_buf);
+                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
+                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
                     float cov = fminf(fabsf(sum), 1.0f);
                     if (!(live_mask >> r & 1u)) continue;
-                    const size_t at = local_index + size_t(r) * size_t(t.width);
-                    float vis = mask ? fminf(fabsf(mask[at]), 1.0f) : 1.0f;
-                    if (mask_out) { mask_out[at] = cov * vis; continue; }
+                    const size_t at_px = local_index + size_t(r) * size_t(t.width);
+                    float vis = mask ? fminf(fabsf(mask[at_px]), 1.0f) : 1.0f;
+                    if (mask_out) { mask_out[at_px] = cov * vis; continue; }
                     if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
                     ++painted;
                     rgba paint;
                     if (brush_type == CB200_BRUSH_COLOR) paint = flat;
                     else if (brush_type == 0xffu) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
                     else if (!kPattern) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);     // unreachable: the host picked mode 3
-                    else if (staged && gradient) paint = paint_gradient(ws.brush, float(x) + 0.5f, float(y) + 0.5f);
-                    else if (staged) paint = paint_pattern(f.texels, &ws.brush, float(x) + 0.5f, float(y) + 0.5f);
-                    else paint = paint_slow(tables, c.brush, c.draw, float(x) + 0.5f, float(y) + 0.5f);
+                    else if (staged && gradient) paint = paint_gradient(sbrush, float(x) + 0.5f, float(y) + 0.5f);
+                    else if (staged) paint = paint_pattern(f.texels, &sbrush, float(x) + 0.5f, float(y) + 0.5f);
+                    else paint = paint_slow(tables, tail.w, rec->draw, float(x) + 0.5f, float(y) + 0.5f);
                     blend(px[r], scale(cov * alpha, paint), op, vis);
                 }
             }
         }
-        touched = touched || n_list != 0;
-        n_list = 0;
-    };
-
-    // Job search through the compact table (8 B tile box + flags, 4 B first tile entry per job),
-    // 32 candidates per step.  Occlusion culling: a job that paints this whole tile with an opaque
-    // solid colour (covered tile entry, source_over/copy, alpha 1, unclipped -- then cov = vis = 1
-    // replaces the pixel exactly) voids everything collected or painted before it.
-    const uint32_t *row_list = kLists ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
-    const uint32_t search_begin = kLists ? 0u : job_begin;
-    const uint32_t search_end = kLists ? f.row_job_count[ty - tile_y0] : job_end;
-    for (uint32_t base = search_begin; base < search_end; base += 32) {
-        const uint32_t at = base + uint32_t(lane);
-        const uint32_t j = kLists ? (at < search_end ? row_list[at] : job_end) : at;
-        uint32_t te = 0;
-        bool hit = false, cover = false;
-        if (j < job_end) {
-            const uint2 box = f.job_box[j];
-            const int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
-            const int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
-            if (tx >= bx0 && tx <= bx1 && ty_local >= by0 && ty_local <= by1) {
-                if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
-                else {
-                    te = f.job_te[j] + uint32_t(ty_local - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
-                    const uint32_t flags = f.te_flags[te];
-                    hit = (box.y & JOBBOX_EVERYWHERE) || (flags & TE_NONEMPTY);
-                    cover = (box.y & JOBBOX_OPAQUE) && (flags & TE_COVERED);
-                }
-            } else if ((box.y & JOBBOX_LEAKY) && tx > bx1 && bx1 >= bx0 && ty_local >= by0 && ty_local <= by1) {
-                // to the right of a job with scanlines whose coverage never returns to zero (leak_rec): no tile
-                // entry there, the rows come from the frame's leak list
-                hit = true;
-                te = kNoRun;
-            }
-        }
-        uint32_t votes = __ballot_sync(0xffffffffu, hit);
-        const uint32_t covers = __ballot_sync(0xffffffffu, cover);
-        if (covers) {
-            const int last = 31 - __clz(int(covers));
-            votes &= ~((1u << last) - 1u);                   // the covering job itself stays
-            n_list = 0;
-            loaded = true;                                 // the covering job replaces the old pixels
-#pragma unroll
-            for (int r = 0; r < kWarpRows; ++r) px[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
-        if (votes) {
-            if (votes >> lane & 1u) {
-                uint32_t slot = n_list + __popc(votes & ((1u << lane) - 1u));
-                ws.job[slot] = j;
-                ws.te[slot] = te;
-            }
-            n_list += __popc(votes);
-            __syncwarp();
-            if (n_list > kList - 32) flush();
-        }
     }
-    flush();
     if (!touched && !t.clear_first) return;                  // no job reaches these pixels: leave them alone
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r)
@@ -654,17 +586,15 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     int ty0 = t.band_y0 / kTile, ty1 = (t.band_y0 + t.band_rows - 1) / kTile;
     if (t.n_canvases > 1) { ty0 = 0; ty1 = t.n_canvases * (t.slot_rows / kTile) - 1; }
     int tiles = tiles_x * (ty1 - ty0 + 1);
-    // Eager: request the old pixels before the job search (hides their latency) -- best when no job
-    // can cover a tile.  Frames with opaque jobs load on first use instead, so tiles that a covering
-    // job overwrites are never read (measured on the tiger: 0.342 vs 0.362 ms).  CB200_EAGER_LOAD=0/1
-    // overrides.
-    int eager = f.n_opaque_jobs == 0;
+    // Eager: request the old pixels before the job search (hides their latency).  Tiles that an opaque job covers
+    // are known up front (tile_cover) and never read.  CB200_EAGER_LOAD=0 loads on first use instead.
+    int eager = 1;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
     if (f.row_jobs) {
         const int n_rows = ty1 - ty0 + 1;
         launch_pdl(k_row_lists, (n_rows * 32 + kBlock - 1) / kBlock, kBlock, 0, s, f, t, ty0, n_rows);
     }
-    auto go = [&](auto kernel) { launch_pdl(kernel, tiles, kCompBlock, 0, s, f, t, sorted_buffer, tiles_x, ty0, eager); };
+    auto go = [&](auto kernel) { launch_pdl(kernel, tiles, kCompBlock, 0, s, f, t, tiles_x, ty0, eager); };
     if (f.row_jobs) {
         if (f.general_compositor == 3) go(k_composite<3, true>);
         else if (f.general_compositor == 2) go(k_composite<2, true>);

@@ -5,12 +5,15 @@
 // walks a scanline left to right (lines_to_runs hpp:2244-2252, render_main
 // hpp:2570, 2601).  Here the thread that owns the first run of a (job, scanline)
 // segment walks that segment in the same left-to-right order and
-//   * stores the running sum after each pixel's last run (`cumulative`; earlier
-//     runs of the same pixel get NaN = "superseded"),
-//   * for every tile column the scanline enters, records the sum carried in from
-//     the left (te_backdrop) and the index of the first run inside that tile
-//     (te_first), so the tile compositor can rebuild dense coverage for its 32
-//     pixels without looking at anything outside the tile.
+//   * stores the running sum after each pixel's last run, COMPACTED per scanline: entry
+//     `head + k` of `cumulative` is the sum after the k-th distinct pixel of the segment that
+//     starts at run `head` (runs of one pixel are coalesced exactly as the reference does),
+//   * for every tile column the scanline enters, records the sum carried in from the left
+//     (te_backdrop), the compacted index of the first pixel inside that tile (te_first; bit 31:
+//     the scanline's last run lies in this tile) and a 32-bit mask of the tile's pixels that hold
+//     a run (te_mask) -- so a lane of the tile compositor finds the coverage of its pixel with
+//     one popc and one load: cumulative[first + popc(mask & pixels up to mine) - 1], or the
+//     carried-in sum when no run lies at or left of it.  Nothing outside the tile is looked at.
 // Segments are independent, so all scanlines of all jobs run in parallel; the
 // serial part is one scanline's run list, as in the reference.
 #include "frame.cuh"
@@ -45,12 +48,13 @@ __device__ __forceinline__ void finish_row(const device_frame &f, frame_header *
     }
 }
 
+constexpr uint32_t kRowEndsHere = 0x80000000u;          // te_first bit 31
+
 // One short scanline segment, walked by one thread from its first run `i`.
 __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h, const uint64_t *keys, const float *delta,
                                          uint32_t n, uint32_t i, uint32_t bx, uint32_t by)
 {
     const uint64_t xmask = (1ull << bx) - 1, ymask = (1ull << by) - 1;
-    const float quiet_nan = __int_as_float(0x7fc00000);
     uint64_t key = keys[i];
     const uint64_t row = key >> bx;
     uint32_t j = uint32_t(row >> by);
@@ -68,6 +72,8 @@ __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h,
     int c_prev = jr.tx0 - 1;                                     // last tile column handled
     const int c_end = jr.tx0 + jr.tw - 1;
     float sum = 0.0f;
+    uint32_t distinct = i;                                       // where the next distinct pixel's sum goes
+    uint32_t open_slot = kNoRun, open_mask = 0, open_first = 0;  // the tile the walk is inside: its (te, row) slot
     // runs are fetched four at a time (plus the key that follows them), so that the walk waits for
     // memory once per batch instead of once per run; reading past the segment's end is harmless
     constexpr int kBatch = 4;
@@ -85,11 +91,11 @@ __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h,
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             if (!more) break;
-            const uint32_t k = k0 + uint32_t(u);
             int x = int(kk[u] & xmask);
             int c = x / kTile;
             if (binned && c > c_prev) {
                 int last = min(c, c_end);
+                if (open_slot != kNoRun) { f.te_first[open_slot] = open_first; f.te_mask[open_slot] = open_mask; open_slot = kNoRun; }
                 // tiles entered since the previous run inherit the sum so far
                 if (sum != 0.0f)
                     for (int cc = c_prev + 1; cc <= last; ++cc) {
@@ -99,7 +105,7 @@ __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h,
                     }
                 if (c <= c_end) {
                     uint32_t te = te_row + uint32_t(c - jr.tx0);
-                    f.te_first[te * kTile + ly] = k;
+                    open_slot = te * kTile + uint32_t(ly); open_first = distinct; open_mask = 0;
                     { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
                 }
                 c_prev = max(c_prev, last);
@@ -107,11 +113,15 @@ __device__ __forceinline__ void walk_row(const device_frame &f, frame_header *h,
             sum += dd[u];
             const uint64_t nkey = kk[u + 1];
             const bool same_row = (nkey >> bx) == row;
-            f.cumulative[k] = (same_row && int(nkey & xmask) == x) ? quiet_nan : sum;
+            if (!(same_row && int(nkey & xmask) == x)) {             // the pixel's last run: its sum is final
+                f.cumulative[distinct++] = sum;
+                open_mask |= 1u << (x % kTile);
+            }
             more = same_row;
         }
         key = kk[kBatch];
     }
+    if (open_slot != kNoRun) { f.te_first[open_slot] = open_first | kRowEndsHere; f.te_mask[open_slot] = open_mask; }
     finish_row(f, h, jr, j, y, ly, binned, everywhere, te_row, c_prev, c_end, sum);
 }
 
@@ -181,6 +191,8 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
         const int c_end = jr.tx0 + jr.tw - 1;
         int c_carry = jr.tx0 - 1;                     // tile column of the last run seen so far
         double carry = 0.0;
+        uint32_t distinct = head;                     // compacted index of the next distinct pixel (see walk_row)
+        uint32_t last_slot = kNoRun;                  // (te, row) slot of the tile that holds the latest run
         for (uint32_t base = head;; base += 32) {
             uint32_t idx = base + uint32_t(lane);
             uint64_t key = idx < n ? keys[idx] : ~0ull;
@@ -197,9 +209,14 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
             int x = int(key & xmask), c = valid ? x / kTile : 0x3fffffff;
             int c_left = __shfl_up_sync(0xffffffffu, c, 1);
             if (lane == 0) c_left = c_carry;
+            // distinct pixels: a run is its pixel's last when the next run is elsewhere
+            const bool final_of_pixel = valid && !((nkey >> bx) == row && int(nkey & xmask) == x);
+            const uint32_t finals = __ballot_sync(0xffffffffu, final_of_pixel);
+            const uint32_t my_entry = distinct + uint32_t(__popc(finals & ((1u << lane) - 1u)));   // entry of my pixel
+            if (final_of_pixel) f.cumulative[my_entry] = after;
+            const bool in_rect = valid && binned && c >= jr.tx0 && c <= c_end;    // projected runs may lie left of a shadow's rectangle
+            const uint32_t slot = in_rect ? (te_row + uint32_t(c - jr.tx0)) * kTile + uint32_t(ly) : kNoRun;
             if (valid) {
-                bool same_x_next = (nkey >> bx) == row && int(nkey & xmask) == x;
-                f.cumulative[idx] = same_x_next ? quiet_nan : after;
                 if (binned && c > c_left) {
                     int last = min(c, c_end);
                     if (before != 0.0f)
@@ -210,17 +227,27 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
                         }
                     if (c <= c_end) {
                         uint32_t te = te_row + uint32_t(c - jr.tx0);
-                        f.te_first[te * kTile + ly] = idx;
+                        f.te_first[slot] = my_entry;                  // first run inside the tile: its pixel's entry
                         { f.te_flags[te] = TE_NONEMPTY; f.te_job[te] = j; }
                     }
                 }
             }
+            // pixel masks: the lanes of one tile combine their bits, one of them adds them to the slot (zeroed by
+            // k_clear_tiles; this warp is the only writer of the row)
+            const uint32_t peers = __match_any_sync(0xffffffffu, slot);
+            const uint32_t bits = __reduce_or_sync(peers, final_of_pixel ? 1u << (x % kTile) : 0u);
+            if (slot != kNoRun && lane == __ffs(int(peers)) - 1 && bits) f.te_mask[slot] |= bits;
             uint32_t vm = __ballot_sync(0xffffffffu, valid);
             int last_lane = 31 - __clz(int(vm));
             carry += __shfl_sync(0xffffffffu, incl, last_lane);
             c_carry = max(c_carry, min(__shfl_sync(0xffffffffu, c, last_lane), c_end));
+            distinct += uint32_t(__popc(finals));
+            const uint32_t tail_slot = __shfl_sync(0xffffffffu, slot, last_lane);
+            if (vm) last_slot = tail_slot;
+            __syncwarp();                                 // slot updates of this step are visible to the next step's lanes
             if (vm != 0xffffffffu) break;
         }
+        if (lane == 0 && last_slot != kNoRun) f.te_first[last_slot] |= kRowEndsHere;
         if (lane == 0) finish_row(f, h, jr, j, y, ly, binned, everywhere, te_row, c_carry, c_end, float(carry));
     }
 }
@@ -249,7 +276,14 @@ __global__ void __launch_bounds__(kBlock) k_tile_flags(device_frame f, canvas_ta
         int y = ty * kTile + lane;
         bool on_canvas = y >= t.band_y0 && y < t.band_y0 + t.band_rows;
         bool full = !on_canvas || (f.te_first[te * kTile + lane] == kNoRun && fabsf(f.te_backdrop[te * kTile + lane]) >= 1.0f);
-        if (__all_sync(0xffffffffu, full) && lane == 0) f.te_flags[te] = flags | TE_COVERED;
+        if (__all_sync(0xffffffffu, full) && lane == 0) {
+            f.te_flags[te] = flags | TE_COVERED;
+            // the compositor's occlusion culling: the LAST covering job of the target tile
+            const int tx = jr.tx0 + int(local % uint32_t(jr.tw));
+            const int tiles_x = (t.width + kTile - 1) / kTile;
+            const int row = t.n_canvases > 1 ? int(jr.canvas) * (t.slot_rows / kTile) + ty : ty - t.band_y0 / kTile;
+            atomicMax(&f.tile_cover[size_t(row) * size_t(tiles_x) + size_t(tx)], lo + 1u);
+        }
     }
 }
 

@@ -39,6 +39,9 @@ struct device_frame {
     uint32_t *row_jobs, *row_job_count;  uint32_t row_stride;
     uint32_t *blur_units;                              // [2][n_shadow_jobs + 1] prefix of blur sweep units (x, y)
     uint2 *job_box;  uint32_t *job_te;                 // compact per-job tile box + first tile entry
+    // per tile of the target: 1 + the last job that covers the whole tile with an opaque colour (0: none) -- every
+    // earlier job and the old pixels are irrelevant there (occlusion culling, k_tile_flags -> k_composite)
+    uint32_t *tile_cover;  uint32_t n_target_tiles;
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
     int general_compositor;                            // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything
     float4 *texels;
@@ -66,7 +69,7 @@ struct device_frame {
     uint32_t *loop_mark;   uint2 *box_loops;           // per loop id; (job, loop id)
     leak_rec *leaks;       uint32_t cap_leaks;         // rows whose coverage residue reaches the right canvas edge
     // tiles
-    uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first;  uint32_t cap_tiles;
+    uint32_t *te_flags, *te_job;  float *te_backdrop;  uint32_t *te_first, *te_mask;  uint32_t cap_tiles;
     float *planes, *planes_tmp;  uint64_t cap_planes;
     uint32_t *shadow_jobs; uint32_t n_shadow_jobs;     // job indices with kind JOB_SHADOW
     int max_shadow_pad, max_shadow_radius, min_shadow_radius;

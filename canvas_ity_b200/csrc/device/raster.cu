@@ -513,6 +513,7 @@ __global__ void k_clear_tiles(device_frame f)
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         f.te_backdrop[i] = 0.0f;
         f.te_first[i] = kNoRun;
+        f.te_mask[i] = 0u;
         if (i < h->n_tile_entries) f.te_flags[i] = 0;
     }
 }

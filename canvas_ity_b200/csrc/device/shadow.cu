@@ -101,7 +101,6 @@ __device__ float paint_alpha(const device_frame &f, const brush_rec &b, const af
 __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb)
 {
     grid_dependency_wait();
-    __shared__ float row_buf[kBlock / 32][kTile];
     frame_header *h = f.hdr;
     if (h->overflow) return;
     const uint32_t j = f.shadow_jobs[blockIdx.y];
@@ -110,7 +109,6 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     if (blockIdx.x * (kBlock / 32) >= tiles) return;
     const draw_rec &d = f.draws[jr.draw];
     const brush_rec &br = f.brushes[d.brush];
-    const cov_source cs = make_cov_source(f, sb);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *plane = f.planes + jr.plane_offset;
     // a solid brush has one alpha for the whole plane (negative: evaluate the brush per pixel)
@@ -121,9 +119,10 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
         uint32_t te = jr.te_base + tl;
         int x = tx * kTile + lane;
         const bool x_in = x >= jr.left && x < jr.left + jr.bw;
-        // row info of the whole tile in two coalesced loads; most rows have no run in the tile
-        const float carried = cs.backdrop[te * kTile + lane];
-        const uint32_t first = cs.first[te * kTile + lane];
+        // row info of the whole tile in three coalesced loads (lane = row); most rows have no run in the tile
+        const float carried = f.te_backdrop[te * kTile + lane];
+        const uint32_t first = f.te_first[te * kTile + lane];
+        const uint32_t pixels = f.te_mask[te * kTile + lane];
         float *out = plane + ptrdiff_t(ty * kTile - jr.top) * ptrdiff_t(jr.pitch) + ptrdiff_t(x - jr.left + jr.skew);
         const int ly0 = max(0, jr.top - ty * kTile), ly1 = min(kTile, jr.top + jr.bh - ty * kTile);
         // Most tiles of a shadow plane hold no edge at all (empty border, solid interior): every row is
@@ -149,8 +148,8 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
         }
         for (int ly = ly0; ly < ly1; ++ly) {
             const int y = ty * kTile + ly;
-            float sum = __shfl_sync(0xffffffffu, carried, ly);
-            if (__shfl_sync(0xffffffffu, first, ly) != kNoRun) sum = tile_row_sum<true>(cs, te, ly, j, y, tx * kTile, row_buf[warp]);
+            const float sum = pixel_sum<true>(f.cumulative, __shfl_sync(0xffffffffu, carried, ly), __shfl_sync(0xffffffffu, first, ly),
+                                              __shfl_sync(0xffffffffu, pixels, ly));
             float cov = fminf(fabsf(sum), 1.0f);
             float v = 0.0f;
             if (cov >= kThreshold) {

@@ -60,7 +60,8 @@ def test_our_arm_line():
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["achieved"] > 0
     e2e = line["e2e"]
-    assert e2e["value"] > 0 and e2e["d2h_bytes_per_step"] == 1024 * 1024 * 4 and e2e["h2d_bytes_per_step"] > 10000
+    assert e2e["value"] > 0 and e2e["d2h_bytes_per_frame"] == 1024 * 1024 * 4 and e2e["h2d_bytes_per_frame"] > 10000
+    assert e2e["d2h_bytes_per_step"] == e2e["frames_per_step"] * e2e["d2h_bytes_per_frame"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert line["config"]["workload"].startswith("tiger_1024")
     assert line["passes"]["readback"]["ms"] > 0 and line["single_canvas"]["value"] > 0
