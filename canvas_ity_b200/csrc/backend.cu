@@ -862,7 +862,7 @@ int finish_pending(cb200_canvas *cv)
                     "tiles=%u long=%u planes=%llu composited=%llu | caps pts=%u items=%u rows=%u runs=%u tiles=%u\n",
                     attempt, seen.overflow, seen.n_line_points, seen.n_stroke_units, seen.n_stroke_points, seen.n_items,
                     seen.n_row_items, seen.n_runs, seen.n_tile_entries, seen.n_long_rows,
-                    (unsigned long long)seen.plane_floats, seen.composited_pixels, cv->cap_pts, cv->cap_items, cv->cap_rows,
+                    (unsigned long long)seen.plane_floats, seen.composited_slots[0], cv->cap_pts, cv->cap_items, cv->cap_rows,
                     cv->cap_runs, cv->cap_tiles);
         if (getenv("CB200_DEBUG") && cv->staged.subpaths.size() < 64) {
             size_t ns = cv->staged.subpaths.size(), nu = cv->staged.units.size(), nsrc = cv->staged.sources.size();
@@ -904,6 +904,7 @@ int finish_pending(cb200_canvas *cv)
             st.raw_runs = seen.n_runs;
             st.tile_entries = seen.n_tile_entries;
             st.composited_pixels = seen.composited_pixels;
+            for (int k = 0; k < 32; ++k) st.composited_pixels += seen.composited_slots[k];
             st.shadow_pixels = seen.shadow_working_pixels;
             st.kernel_launches = cv->launches;
             st.graph_replays = cv->graph_replays;

@@ -324,6 +324,25 @@ __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t
 #ifndef CB200_COMP_CTAS0
 #define CB200_COMP_CTAS0 8
 #endif
+// The 4-bit mix program (hpp:2583-2591) as two affine maps, decoded once per job: mix_fore = f0 + f1 * back.a and
+// mix_back = b0 + b1 * fore.a with (f0, f1), (b0, b1) in {(0,0), (0,1), (1,0), (1,-1)}.  fmaf(1, a, 0) = a and
+// fmaf(-1, a, 1) = 1 - a exactly, so the per-pixel selects of blend() become two FMAs with the same bits.
+struct mix_program { float f0, f1, b0, b1; };
+__device__ __forceinline__ mix_program decode_mix(uint32_t op)
+{
+    mix_program m;
+    m.f1 = (op & 1u) ? ((op & 2u) ? -1.0f : 1.0f) : 0.0f;  m.f0 = (op & 2u) ? 1.0f : 0.0f;
+    m.b1 = (op & 4u) ? ((op & 8u) ? -1.0f : 1.0f) : 0.0f;  m.b0 = (op & 8u) ? 1.0f : 0.0f;
+    return m;
+}
+// blend_unclipped() with the program decoded (visibility exactly 1)
+__device__ __forceinline__ void blend_program(float4 &back, rgba fore, const mix_program &m)
+{
+    const float mf = fmaf(m.f1, back.w, m.f0), mb = fmaf(m.b1, fore.a, m.b0);
+    back = make_float4(fmaf(mf, fore.r, mb * back.x), fmaf(mf, fore.g, mb * back.y), fmaf(mf, fore.b, mb * back.z),
+                       fminf(fmaf(mf, fore.a, mb * back.w), 1.0f));
+}
+
 template <int kMode, bool kLists>
 __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5)
 k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager_load)
@@ -332,11 +351,13 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
     grid_dependency_wait();
     __shared__ __align__(16) staged_brush staged_brushes[kPaint ? kTileWarps : 1];
     frame_header *h = f.hdr;
-    if (h->overflow) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx = blockIdx.x % tiles_x, ty = tile_y0 + blockIdx.x / tiles_x;
-    const int x = tx * kTile + lane;
-    const int band_y1 = t.band_y0 + t.band_rows;
+    const int trow = int(blockIdx.x) / tiles_x;
+    const int tx = int(blockIdx.x) - trow * tiles_x, ty = tile_y0 + trow;
+    // requests that depend on nothing but the tile go out first: their latencies overlap
+    const uint32_t overflow = h->overflow;
+    const uint32_t cover = f.tile_cover[blockIdx.x];          // 1 + the last opaque job that covers the whole tile
+    const uint32_t search_rows = kLists ? f.row_job_count[trow] : 0u;
     // batches stack their canvases vertically: which canvas is this tile in, and where does it start?
     int canvas = 0, ty_local = ty;
     if (t.n_canvases > 1) {
@@ -344,31 +365,42 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
         canvas = ty / slot_tiles;
         ty_local = ty - canvas * slot_tiles;
     }
-    const int yoff = canvas * t.slot_rows;                   // fb row of the canvas' row 0 (0 unless batched)
-    const int row0 = ty_local * kTile + warp * kWarpRows;    // first scanline of this warp, canvas coordinates
     const uint2 job_range = t.canvas_jobs[canvas];
     const uint32_t job_end = job_range.x + job_range.y;
-    if (row0 >= band_y1 || row0 + kWarpRows <= t.band_y0) return;
-    const uint32_t *row_list = kLists ? f.row_jobs + size_t(ty - tile_y0) * f.row_stride : nullptr;
-    const uint32_t search_end = kLists ? f.row_job_count[ty - tile_y0] : job_end;
+    const int row0 = ty_local * kTile + warp * kWarpRows;    // first scanline of this warp, canvas coordinates
+    const int x = tx * kTile + lane;
+    // scanlines [r_lo, r_hi) of this warp lie in the band; a lane is live when its column is on the canvas
+    const int r_lo = max(t.band_y0 - row0, 0), r_hi = min(t.band_y0 + t.band_rows - row0, kWarpRows);
+    if (r_hi <= r_lo) return;
+    const bool whole = r_lo == 0 && r_hi == kWarpRows && tx * kTile + kTile <= t.width;   // no partial rows or columns
+    const uint32_t live_mask = x < t.width ? ((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u) : 0u;
+    const uint32_t *row_list = kLists ? f.row_jobs + size_t(trow) * f.row_stride : nullptr;
+    const uint32_t search_end = kLists ? search_rows : job_end;
+    const size_t local_index = size_t(row0 - t.band_y0) * size_t(t.width) + size_t(x);   // into canvas-sized planes
+    float4 *const fb_at = t.fb + (size_t(canvas) * size_t(t.slot_rows) * size_t(t.width) + local_index);
+    const size_t pitch = size_t(t.width);
+    if (overflow) return;
     if (search_end == (kLists ? 0u : job_range.x) && !t.clear_first) return;      // no job reaches this tile row
 
-    // occlusion culling: the last opaque job that covers this tile voids everything before it
-    const uint32_t cover = f.tile_cover[blockIdx.x];
+    // occlusion culling: the last opaque job that covers this tile voids everything before it -- old pixels included
     const uint32_t first_job = cover ? cover - 1u : job_range.x;
-
     float4 px[kWarpRows];
-    uint32_t live_mask = 0;                                  // bit r: scanline row0 + r is ours and x is on the canvas
-    const size_t local_index = size_t(row0 - t.band_y0) * size_t(t.width) + size_t(x);   // into canvas-sized planes
-    float4 *const fb_at = t.fb + (size_t(yoff) * size_t(t.width) + local_index);         // this lane's first pixel
     const bool fetch_now = eager_load && !t.clear_first && !cover;
+    auto fetch = [&]() {
+        if (whole) {
 #pragma unroll
-    for (int r = 0; r < kWarpRows; ++r) {
-        const int y = row0 + r;
-        const bool live = x < t.width && y >= t.band_y0 && y < band_y1;
-        live_mask |= uint32_t(live) << r;
-        px[r] = (live && fetch_now) ? __ldcs(fb_at + size_t(r) * size_t(t.width)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int r = 0; r < kWarpRows; ++r) px[r] = __ldcs(fb_at + size_t(r) * pitch);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r)
+                if (live_mask >> r & 1u) px[r] = __ldcs(fb_at + size_t(r) * pitch);
+        }
+    };
+    if (!(fetch_now && whole)) {
+#pragma unroll
+        for (int r = 0; r < kWarpRows; ++r) px[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    if (fetch_now) fetch();
     bool loaded = fetch_now || t.clear_first != 0 || cover != 0;
     bool touched = cover != 0;
     uint32_t painted = 0;
@@ -382,13 +414,14 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
         bool hit = false;
         if (j < job_end && j >= first_job) {
             const uint2 box = f.job_box[j];
+            const uint32_t te_base = f.job_te[j];
             const int bx0 = int(box.x & 0x7ffu), by0 = int((box.x >> 11) & 0x7ffu);
             const int bx1 = int((box.x >> 22) & 0x3ffu) | int((box.y & 1u) << 10), by1 = int((box.y >> 1) & 0x7ffu);
             if (ty_local >= by0 && ty_local <= by1 && tx >= bx0) {
                 if (tx <= bx1) {
                     if ((box.y >> 12 & 3u) == JOB_SHADOW) hit = true;
                     else {
-                        te = f.job_te[j] + uint32_t(ty_local - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
+                        te = te_base + uint32_t(ty_local - by0) * uint32_t(bx1 - bx0 + 1) + uint32_t(tx - bx0);
                         hit = (box.y & JOBBOX_EVERYWHERE) || (f.te_flags[te] & TE_NONEMPTY);
                     }
                 } else if ((box.y & JOBBOX_LEAKY) && bx1 >= bx0) {
@@ -401,9 +434,7 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
         }
         uint32_t votes = __ballot_sync(0xffffffffu, hit);
         if (votes && !loaded) {                               // lazy variant: fetch the old pixels on first use
-#pragma unroll
-            for (int r = 0; r < kWarpRows; ++r)
-                if (live_mask >> r & 1u) px[r] = __ldcs(fb_at + size_t(r) * size_t(t.width));
+            fetch();
             loaded = true;
         }
         touched = touched || votes != 0;
@@ -444,6 +475,8 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                     }
                 }
             }
+            // rows with an edge inside the tile (most tiles of a filled shape have none: the carried-in sum is all)
+            const uint32_t edge_rows = (__ballot_sync(0xffffffffu, info != kNoRun) >> 8) & 0xffu;
             const float *mask = (kGeneral && tail.y) ? t.mask_planes[tail.y] : nullptr;
             if (kGeneral && kind == JOB_SHADOW) {
                 const int4 box = __ldg(reinterpret_cast<const int4 *>(rec) + 3);       // cx0, cy0, cx1, cy1
@@ -455,7 +488,7 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
                     if (!(live_mask >> r & 1u) || x < box.x || x >= box.z || y < box.y || y >= box.w) continue;
-                    float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * size_t(t.width) + size_t(x)]), 1.0f) : 1.0f;
+                    float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * pitch + size_t(x)]), 1.0f) : 1.0f;
                     if (vis < kThreshold) continue;
                     float s = plane[size_t(y + place.x - place.z) * size_t(place.w) + size_t(x + place.x - place.y)];
                     blend(px[r], scale(alpha * s, tint), op, vis);
@@ -486,39 +519,53 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                 }
                 __syncwarp();
             }
+            // coverage sum of this lane's pixel in row r (tile_cov.cuh); `r` is a compile-time constant at every use
+            auto row_sum = [&](int r) -> float {
+                const float carried = __uint_as_float(__shfl_sync(0xffffffffu, info, r));
+                if (!(edge_rows >> r & 1u)) return carried;
+                return pixel_sum<false>(f.cumulative, carried, __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
+            };
             if ((!kGeneral && !kPaint) || (!mask && !mask_out && brush_type == CB200_BRUSH_COLOR)) {
-                // the common case -- unclipped solid colour -- carries no per-row address arithmetic
+                // the common case -- unclipped solid colour.  Dead lanes and rows are blended too (they hold zeros and
+                // are never stored): no per-row liveness test here.
+                const float scale_all = alpha;
+                if (op == 14u) {
 #pragma unroll
-                for (int r = 0; r < kWarpRows; ++r) {
-                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
-                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
-                    float cov = fminf(fabsf(sum), 1.0f);
-                    if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
-                    ++painted;
-                    blend_unclipped(px[r], scale(cov * alpha, flat), op);
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                        if (!(cov >= kThreshold)) continue;
+                        ++painted;
+                        blend_unclipped(px[r], scale(cov * scale_all, flat), 14u);
+                    }
+                } else {
+                    const mix_program m = decode_mix(op);
+#pragma unroll
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                        if (!(cov >= kThreshold || everywhere)) continue;
+                        ++painted;
+                        blend_program(px[r], scale(cov * scale_all, flat), m);
+                    }
                 }
             } else if (kPaint && staged && gradient && !mask && !mask_out) {
                 // unclipped gradient fill: the brush set-up is hoisted out of the pixel loop
                 const gradient_ctx g = make_gradient_ctx(sbrush);
+                const mix_program m = decode_mix(op);
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
-                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
-                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
-                    float cov = fminf(fabsf(sum), 1.0f);
-                    if (!(live_mask >> r & 1u) || !(cov >= kThreshold || everywhere)) continue;
+                    const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                    if (!(cov >= kThreshold || everywhere)) continue;
                     ++painted;
                     rgba paint = gradient_at(g, sbrush, float(x) + 0.5f, float(row0 + r) + 0.5f);
-                    blend_unclipped(px[r], scale(cov * alpha, paint), op);
+                    blend_program(px[r], scale(cov * alpha, paint), m);
                 }
             } else if (kGeneral) {
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
-                    const float sum = pixel_sum<false>(f.cumulative, __uint_as_float(__shfl_sync(0xffffffffu, info, r)),
-                                                       __shfl_sync(0xffffffffu, info, 8 + r), __shfl_sync(0xffffffffu, info, 16 + r));
-                    float cov = fminf(fabsf(sum), 1.0f);
+                    const float cov = fminf(fabsf(row_sum(r)), 1.0f);
                     if (!(live_mask >> r & 1u)) continue;
-                    const size_t at_px = local_index + size_t(r) * size_t(t.width);
+                    const size_t at_px = local_index + size_t(r) * pitch;
                     float vis = mask ? fminf(fabsf(mask[at_px]), 1.0f) : 1.0f;
                     if (mask_out) { mask_out[at_px] = cov * vis; continue; }
                     if (!((cov >= kThreshold || everywhere) && vis >= kThreshold)) continue;
@@ -536,12 +583,17 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
         }
     }
     if (!touched && !t.clear_first) return;                  // no job reaches these pixels: leave them alone
+    if (whole) {
 #pragma unroll
-    for (int r = 0; r < kWarpRows; ++r)
-        if (live_mask >> r & 1u) fb_at[size_t(r) * size_t(t.width)] = px[r];
-    // statistics: composited pixel count of the frame
+        for (int r = 0; r < kWarpRows; ++r) fb_at[size_t(r) * pitch] = px[r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < kWarpRows; ++r)
+            if (live_mask >> r & 1u) fb_at[size_t(r) * pitch] = px[r];
+    }
+    // statistics: composited pixel count of the frame (dead lanes of edge tiles included in the solid-colour path)
     painted = __reduce_add_sync(0xffffffffu, painted);
-    if (lane == 0 && painted) atomicAdd(&h->composited_pixels, (unsigned long long)painted);
+    if (lane == 0 && painted) atomicAdd(&h->composited_slots[blockIdx.x & 31u], (unsigned long long)painted);
 }
 
 // One warp per tile row of the target: the ordered list of jobs whose composite box reaches the row.

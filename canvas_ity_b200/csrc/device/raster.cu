@@ -427,6 +427,16 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
                 jr.cx0 = max(left - b, 0); jr.cx1 = min(right - b, t.width);
                 jr.cy0 = max(top - b, t.band_y0); jr.cy1 = min(bottom - b, t.band_y0 + t.band_rows);
                 if (plane == 0) { jr.cx1 = jr.cx0; jr.cy1 = jr.cy0; }
+                // the plane rows this band composites, the y-sweep chunks that hold them, the rows those read
+                // (hpp:2402-2405: the blur couples rows over 3 (r + 1) = border rows at most)
+                const int ya = min(max(jr.cy0 + b - top, 0), jr.bh), yb = min(max(jr.cy1 + b - top, 0), jr.bh);
+                jr.need_r0 = jr.need_r1 = 0; jr.chunk_lo = 0; jr.chunk_n = 0;
+                if (plane && yb > ya) {
+                    jr.chunk_lo = ya / kBlurChunkY;
+                    jr.chunk_n = (yb - 1) / kBlurChunkY - jr.chunk_lo + 1;
+                    jr.need_r0 = max(jr.chunk_lo * kBlurChunkY - b, 0);
+                    jr.need_r1 = min((jr.chunk_lo + jr.chunk_n) * kBlurChunkY + b, jr.bh);
+                }
             } else {
                 if (everywhere) { x0 = 0; y0 = t.band_y0; x1 = t.width; y1 = t.band_y0 + t.band_rows; }
                 else {
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_tar
         // plane storage: order of allocation does not matter, only disjointness
         if (plane) {
             unsigned long long off = atomicAdd(&plane_carry, plane);
-            atomicAdd(&working_carry, (unsigned long long)f.jobs[j].bw * (unsigned long long)f.jobs[j].bh);
+            atomicAdd(&working_carry, (unsigned long long)f.jobs[j].bw * (unsigned long long)(f.jobs[j].need_r1 - f.jobs[j].need_r0));
             f.jobs[j].plane_offset = off;
             f.comp[j].plane_lo = uint32_t(off); f.comp[j].plane_hi = uint32_t(off >> 32);
         }

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
         const uint32_t first = f.te_first[te * kTile + lane];
         const uint32_t pixels = f.te_mask[te * kTile + lane];
         float *out = plane + ptrdiff_t(ty * kTile - jr.top) * ptrdiff_t(jr.pitch) + ptrdiff_t(x - jr.left + jr.skew);
-        const int ly0 = max(0, jr.top - ty * kTile), ly1 = min(kTile, jr.top + jr.bh - ty * kTile);
+        // rows of the plane this canvas (band) needs: [need_r0, need_r1) (job_rec)
+        const int ly0 = max(0, jr.top + jr.need_r0 - ty * kTile), ly1 = min(kTile, jr.top + jr.need_r1 - ty * kTile);
+        if (ly1 <= ly0) continue;
         // Most tiles of a shadow plane hold no edge at all (empty border, solid interior): every row is
         // one value, and the tile goes out as 16-byte stores, four rows per step (tile columns start on
         // a 128 B line: job_rec::skew).  Same arithmetic per row as below.
@@ -224,12 +226,6 @@ __device__ __forceinline__ float steady_step(float *at, float *at1, stream_pass 
     return run;
 }
 
-__device__ __forceinline__ uint32_t sweep_units(int len, int cross)
-{
-    if (len <= 0 || cross <= 0) return 0;
-    return uint32_t((cross + 31) / 32) * uint32_t((len + kStreamChunk - 1) / kStreamChunk);
-}
-
 // Prefix sums of every shadow job's sweep units (32 adjacent lines x one chunk), so that the
 // sweeps can deal all units of a frame to warps as they become free -- plane sizes differ by
 // orders of magnitude.  Also resets the two unit tickets.  One CTA.
@@ -246,7 +242,12 @@ __global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
         uint32_t ux = 0, uy = 0;
         if (i < n) {
             const job_rec &jr = f.jobs[f.shadow_jobs[i]];
-            if (jr.radius <= kStreamMaxRadius) { ux = sweep_units(jr.bw, jr.bh); uy = sweep_units(jr.bh, jr.pitch); }
+            if (jr.radius <= kStreamMaxRadius && jr.need_r1 > jr.need_r0) {
+                // x sweep: the 32-row strips that hold rows [need_r0, need_r1), every chunk along the row;
+                // y sweep: every 32-column strip, the chunks [chunk_lo, chunk_lo + chunk_n)
+                ux = uint32_t((jr.need_r1 - 1) / 32 - jr.need_r0 / 32 + 1) * uint32_t((jr.bw + kStreamChunk - 1) / kStreamChunk);
+                uy = uint32_t((jr.pitch + 31) / 32) * uint32_t(jr.chunk_n);
+            }
         }
         uint32_t total_x, total_y;
         const uint32_t ex = block_exclusive_scan(ux, sm, total_x);
@@ -295,12 +296,15 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
         const float *src = src_base + jr.plane_offset;
         float *dst = dst_base + jr.plane_offset;
         float *ring2 = ring1 + kRingPass, *ring3 = ring2 + kRingPass;
-        const int n_strips = (cross + 31) / 32;
+        // the strips / chunks this canvas needs (job_rec::need_r0 ..): see k_blur_units
+        const int strip_lo = kAlongRows ? jr.need_r0 / 32 : 0;
+        const int n_strips = kAlongRows ? (jr.need_r1 - 1) / 32 - strip_lo + 1 : (cross + 31) / 32;
         const int unit = int(global_unit - prefix[lo]);
-        const int strip = unit % n_strips, chunk = unit / n_strips;
+        const int strip = strip_lo + unit % n_strips, chunk = (kAlongRows ? 0 : jr.chunk_lo) + unit / n_strips;
         const int line = strip * 32 + lane;
-        const bool active = kAlongRows ? line < cross : (line >= skew && line < skew + jr.bw);
-        const int y0 = chunk * kStreamChunk, y1 = min(len, y0 + kStreamChunk);
+        const bool active = kAlongRows ? (line >= jr.need_r0 && line < jr.need_r1) : (line >= skew && line < skew + jr.bw);
+        constexpr int kChunk = kAlongRows ? kStreamChunk : kBlurChunkY;
+        const int y0 = chunk * kChunk, y1 = min(len, y0 + kChunk);
         const int t_begin = chunk ? y0 - 3 * p : 0, t_last = y1 + 3 * p;
         const int start1 = chunk ? y0 - 2 * p : 0, start2 = chunk ? y0 - p : 0, start3 = chunk ? y0 : 0;
         // [t_steady, t_inside): every pass is past its first output and still inside the line, and
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
             // that global accesses stay coalesced; the next block is fetched while this one is swept
             float *mine = tile + lane * 33;
             const float *in = src + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane);
-            const int rows_here = min(32, cross - strip * 32);
+            const int rows_here = min(32, min(cross, jr.need_r1) - strip * 32);
             float ahead[32];
             auto fetch = [&](int tb) {
                 const int col = tb + lane;
