@@ -227,7 +227,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this back end has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     pin_to_gpu_numa_node(local, world)
     size = args.size
     peak_gbs, peak_src = measured_hbm_peak()
@@ -250,15 +251,17 @@ def main():
     script = H.tiger_script(size, size)
     frame = H.lower_script(script, size, size)[0]
 
-    def timed_regions(cvs, steps, min_seconds, max_regions=64, after_frame=None):
-        """Spans (ms) of repeated regions of exactly `steps` steps (one frame on every canvas per step)."""
-        spans, total = [], 0.0
+    def timed_regions(cvs, steps, min_seconds, max_regions=64, after_frame=None, all_ranks=True):
+        """Spans (ms) of repeated regions of exactly `steps` steps (one frame on every canvas per step).  `all_ranks`:
+        every rank is in here (barriers between regions); False for passes that only rank 0 runs."""
+        spans = []
         ms = C.c_float()
-        while len(spans) < 3 or (total < min_seconds and len(spans) < max_regions):
+        sync = barrier if all_ranks else torch.cuda.synchronize
+        n_regions = 3                                       # fixed after the first region (the same on every rank)
+        while len(spans) < n_regions:
             for c in cvs:                                   # one untimed frame: the streams are busy when the
                 check(lib.cb200_frame_replay(c, 1))         # begin events are recorded
-            barrier_light = world > 1 and not spans
-            if barrier_light:
+            if all_ranks and world > 1 and not spans:
                 dist.barrier()
             for c in cvs:
                 check(lib.cb200_timer_begin(c))
@@ -276,9 +279,13 @@ def main():
                 for b in cvs:
                     check(lib.cb200_timer_between(a, b, C.byref(ms)))
                     span = max(span, ms.value)
-            barrier()
+            sync()
             spans.append(span)
-            total += span / 1e3
+            if len(spans) == 1:
+                first = torch.tensor([span], dtype=torch.float64, device="cuda")
+                if all_ranks and world > 1:
+                    dist.all_reduce(first, op=dist.ReduceOp.MAX)
+                n_regions = int(min(max_regions, max(3, np.ceil(min_seconds * 1e3 / max(float(first[0]), 1e-3)))))
         return spans
 
     # ---- device-resident arm: `value` ----
@@ -392,7 +399,7 @@ def main():
         f_ms, b_ms, r_ms, c_ms = [float(np.median(c)) for c in zip(*rows3)]
         plane_px, comp_px = int(stats.shadow_pixels), int(stats.composited_pixels)
         check(lib.cb200_set_stage_timing(cv3, 0))
-        spans3 = timed_regions([cv3], 8, 0.3, max_regions=16)
+        spans3 = timed_regions([cv3], 8, 0.3, max_regions=16, all_ranks=False)
         lib.cb200_canvas_destroy(cv3)
         algo3 = 32.0 * comp_px + 20.0 * plane_px              # per-pass bytes of SURVEY 8d for this frame (composite + blur + raster)
         passes["config3_tiger_alpha0.9_shadow_blur16"] = {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Print the figures of a bench.py JSON line that the kernel work watches."""
 import json, sys
-b = json.load(open(sys.argv[1]))
+b = json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
 print({k: b[k] for k in ("value", "span_ms", "single_canvas", "stages_ms")})
 print("k_composite ms", b["roofline"]["kernel_ms"], "frac", b["roofline"]["frac"], "e2e", b["e2e"]["value"], b["e2e"]["serial_value"])
 p = b.get("passes", {})
