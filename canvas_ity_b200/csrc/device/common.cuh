@@ -35,7 +35,7 @@ constexpr int kSMs = 148;                  // B200
 constexpr int kGrid = kSMs * 4;            // fixed 1-D grid: 4 CTAs per B200 SM
 constexpr float kThreshold = 1.0f / 8160.0f;   // hpp:1289, 2429, 2573
 constexpr uint32_t kNoRun = 0xffffffffu;
-constexpr int kBlurChunkY = 128;           // rows per chunk of the blur's y sweep (shadow.cu; job_rec::chunk_lo)
+constexpr int kBlurChunkY = 256;           // rows per chunk of the blur's y sweep (shadow.cu; job_rec::chunk_lo)
 
 // job.kind
 enum { JOB_MAIN = 0, JOB_SHADOW = 1, JOB_CLIP = 2 };

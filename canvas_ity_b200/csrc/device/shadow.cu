@@ -8,10 +8,12 @@
 //                    working rectangle (hpp:2453-2503), as ONE streaming sweep: a thread owns one
 //                    line (a plane row for the x axis, a plane column for the y axis) and pushes
 //                    every sample through three cascaded running sums whose 2r+3-deep histories
-//                    live in shared memory.  The running sum is updated with the reference's own
-//                    four terms in the reference's order, so a line that is swept in one piece is
-//                    bit-identical to the reference.  One global read + one write per pixel and
-//                    axis (16 B per working pixel for the whole blur = the algorithmic figure).
+//                    live in shared memory.  A step is the reference's four-term update of the
+//                    window sum (hpp:2463-2479) written as two differences and two fused
+//                    multiply-adds; sweeps restart every chunk, so the result stays within ~1e-7 of
+//                    the reference's own running sum (the plane is only ever a factor of the
+//                    composite, hpp:2519-2523).  One global read + one write per pixel and axis
+//                    (16 B per working pixel for the whole blur = the algorithmic figure).
 //   k_blur_rows      fallback for radii whose history does not fit (r > kStreamMaxRadius): the
 //   k_transpose      three passes per row in shared memory, each output a windowed sum, with
 //                    32x32 tiled transposes around the column passes.
@@ -171,59 +173,28 @@ constexpr int kStreamThreads = 128;        // lines in flight per CTA; every war
 constexpr int kStreamMaxRadius = 30;       // history 3 x (2r+3) x 128 floats <= 95 KB
 constexpr int kStreamChunk = 1024;         // longer lines are swept in pieces (with a 3(r+1) run-in)
 
-struct stream_pass { float running, prev; };
-
 // Histories: ring[(slot * 3 + pass) * kStreamThreads + tid], slot in [0, 2r+3): the three passes of
-// one slot sit at constant offsets from one another, so a step needs two slot addresses in all.
+// one slot sit at constant offsets from one another, and the slot a step reads is the slot the next
+// step overwrites, so a step advances ONE address (add, compare, select).
 constexpr int kRingSlot = 3 * kStreamThreads;                      // floats per slot
 constexpr int kRingPass = kStreamThreads;                          // floats between passes
 
-// One sample `v` (index ik + r + 1 of this pass's input) enters; returns output ik of the pass.
-// `at` points at this thread's entry of the slot that holds the sample 2r+3 back (overwritten by
-// v), `at1` at the next older slot.  hpp:2463-2479: running -= w2 s[x-r-1]; running -= w1 s[x-r-2];
-// running += w2 s[x+r]; running += w1 s[x+r+1].
-__device__ __forceinline__ float stream_step(float *ring, int W, int slot, int slot1, stream_pass &ps, float v,
-                                             int ik, int start, int len, float w1, float w2, float w12)
-{
-    const float a = ring[slot * kRingSlot], b = ring[slot1 * kRingSlot];
-    ring[slot * kRingSlot] = v;
-    if (ik > start) {
-        float run = ps.running;
-        run -= w2 * b;
-        run -= w1 * a;
-        run += w2 * ps.prev;
-        run += w1 * v;
-        ps.running = run;
-    } else if (ik == start) {
-        // first output of the sweep: w1 s[r+1] + w12 (s[0] + ... + s[r]) at the head of a line
-        // (hpp:2460-2462; the history left of the line is zero), the full window mid-line
-        float run = w1 * v;
-        int at = slot1;
-        run += w1 * ring[at * kRingSlot];
-#pragma unroll 1
-        for (int j = W - 2; j >= 1; --j) {
-            at = at + 1 == W ? 0 : at + 1;
-            run += w12 * ring[at * kRingSlot];
-        }
-        ps.running = run;
-    }
-    ps.prev = v;
-    return (ik >= start && ik < len) ? ps.running : 0.0f;
-}
+// One pass of the cascade: `run` is the window sum after the newest sample, `prev` that sample,
+// `old` the sample that left the window last step (= what this step's read was last step).
+struct stream_pass { float run, prev, old; };
 
-// The same once every pass is under way and no pass has run off the end of the line.
-__device__ __forceinline__ float steady_step(float *at, float *at1, stream_pass &ps, float v, float w1, float w2)
+// hpp:2463-2479 per output: running -= w2 s[x-r-1]; running -= w1 s[x-r-2]; running += w2 s[x+r];
+// running += w1 s[x+r+1].  Here as two differences and two fused multiply-adds (the same sum, other
+// rounding: the shadow plane only enters the composite as a factor, hpp:2519-2523 -- no decision is
+// taken on it -- and a sweep restarts every chunk, so the difference stays near 1e-7).
+// v = s[x+r+1] enters, leaving = s[x-r-1] (read from the ring), ps.old = s[x-r-2].
+__device__ __forceinline__ float pass_step(stream_pass &ps, float v, float leaving, float w1, float w2)
 {
-    const float a = *at, b = *at1;
-    *at = v;
-    float run = ps.running;
-    run -= w2 * b;
-    run -= w1 * a;
-    run += w2 * ps.prev;
-    run += w1 * v;
-    ps.running = run;
+    const float d2 = ps.prev - leaving, d1 = v - ps.old;
+    ps.run = __fmaf_rn(w1, d1, __fmaf_rn(w2, d2, ps.run));
+    ps.old = leaving;
     ps.prev = v;
-    return run;
+    return ps.run;
 }
 
 // Prefix sums of every shadow job's sweep units (32 adjacent lines x one chunk), so that the
@@ -261,6 +232,66 @@ __global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
     }
 }
 
+__device__ __forceinline__ uint32_t shared_address(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+template <int kOffset>
+__device__ __forceinline__ float ring_load(uint32_t at)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(at), "n"(kOffset));
+    return v;
+}
+template <int kOffset>
+__device__ __forceinline__ void ring_store(uint32_t at, float v)
+{
+    asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(at), "n"(kOffset), "f"(v));
+}
+
+// The three cascaded passes of one line.  Pass k's output x is final once its input x + r + 1 has
+// entered, so sample t of the line yields output t - (r+1) of pass 1, t - 2(r+1) of pass 2 and
+// t - 3(r+1) of pass 3.  The reference pads every pass with zeros outside the line: the outputs
+// a pass produces left of sample 0 or right of sample len-1 enter the next pass as zero
+// (kMasked; only the first 3(r+1) and the last 2(r+1) steps of a line need it).  Started from an
+// all-zero state anywhere on a line the cascade is exact after 3(r+1) further samples: what entered
+// a window before it was complete leaves it again with the same value.
+struct cascade {
+    stream_pass p1, p2, p3;
+    float l1, l2, l3;                      // the samples leaving the windows at the next step
+    uint32_t wr, rd, first, end;           // shared-memory byte addresses: slot written next, slot after it, ring bounds
+    float w1, w2;
+    int p, len;
+
+    __device__ __forceinline__ void reset(float *ring, int W, int r, int line_len, float weight_1, float weight_2)
+    {
+        for (int k = 0; k < 3 * W; ++k) ring[k * kStreamThreads] = 0.0f;
+        p1 = p2 = p3 = stream_pass{0.0f, 0.0f, 0.0f};
+        l1 = l2 = l3 = 0.0f;
+        first = shared_address(ring);
+        end = first + uint32_t(W * kRingSlot) * 4u;
+        wr = first; rd = first + kRingSlot * 4u;
+        w1 = weight_1; w2 = weight_2; p = r + 1; len = line_len;
+    }
+
+    template <bool kMasked>
+    __device__ __forceinline__ float push(float v, int t)
+    {
+        constexpr int kPassBytes = kRingPass * 4;
+        ring_store<0>(wr, v);
+        float o1 = pass_step(p1, v, l1, w1, w2);
+        if (kMasked && unsigned(t - p) >= unsigned(len)) o1 = 0.0f;
+        ring_store<kPassBytes>(wr, o1);
+        float o2 = pass_step(p2, o1, l2, w1, w2);
+        if (kMasked && unsigned(t - 2 * p) >= unsigned(len)) o2 = 0.0f;
+        ring_store<2 * kPassBytes>(wr, o2);
+        const float o3 = pass_step(p3, o2, l3, w1, w2);
+        // the slot after next holds what leaves at the next step (2r+3 >= 3 slots: never one just written)
+        uint32_t ahead = rd + kRingSlot * 4u;
+        if (ahead == end) ahead = first;
+        l1 = ring_load<0>(ahead); l2 = ring_load<kPassBytes>(ahead); l3 = ring_load<2 * kPassBytes>(ahead);
+        wr = rd; rd = ahead;
+        return o3;
+    }
+};
+
 // Persistent grid of independent warps; each takes the next unit off a ticket counter.
 template <bool kAlongRows>
 __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, const float *src_base, float *dst_base)
@@ -275,7 +306,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // x sweep: one 32 x 32 staging tile per warp (skewed), then everybody's histories
     float *tile = blur_smem + warp * 32 * 33;
-    float *ring1 = blur_smem + (kAlongRows ? kStreamThreads * 33 : 0) + tid;
+    float *ring = blur_smem + (kAlongRows ? kStreamThreads * 33 : 0) + tid;
     for (;;) {
         uint32_t global_unit = 0;
         if (lane == 0) global_unit = atomicAdd(ticket, 1u);
@@ -292,10 +323,8 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
         // lines of the y sweep are storage columns, so that a warp always covers one aligned 128 B line
         const int len = kAlongRows ? jr.bw : jr.bh, cross = kAlongRows ? jr.bh : jr.pitch;
         const int pitch = jr.pitch, skew = jr.skew;
-        const float w1 = jr.w1, w2 = jr.w2, w12 = jr.w1 + jr.w2;
         const float *src = src_base + jr.plane_offset;
         float *dst = dst_base + jr.plane_offset;
-        float *ring2 = ring1 + kRingPass, *ring3 = ring2 + kRingPass;
         // the strips / chunks this canvas needs (job_rec::need_r0 ..): see k_blur_units
         const int strip_lo = kAlongRows ? jr.need_r0 / 32 : 0;
         const int n_strips = kAlongRows ? (jr.need_r1 - 1) / 32 - strip_lo + 1 : (cross + 31) / 32;
@@ -304,32 +333,13 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
         const int line = strip * 32 + lane;
         const bool active = kAlongRows ? (line >= jr.need_r0 && line < jr.need_r1) : (line >= skew && line < skew + jr.bw);
         constexpr int kChunk = kAlongRows ? kStreamChunk : kBlurChunkY;
+        // outputs [y0, y1) of the line; they leave the cascade at steps [t_store, t_last)
         const int y0 = chunk * kChunk, y1 = min(len, y0 + kChunk);
-        const int t_begin = chunk ? y0 - 3 * p : 0, t_last = y1 + 3 * p;
-        const int start1 = chunk ? y0 - 2 * p : 0, start2 = chunk ? y0 - p : 0, start3 = chunk ? y0 : 0;
-        // [t_steady, t_inside): every pass is past its first output and still inside the line, and
-        // every output lands in [y0, y1) -- the branch-free part of the sweep
-        const int t_steady = start3 + 3 * p + 1, t_inside = min(len, t_last);
-        for (int k = 0; k < 3 * W; ++k) ring1[k * kStreamThreads] = 0.0f;
-        stream_pass p1 = {0.0f, 0.0f}, p2 = {0.0f, 0.0f}, p3 = {0.0f, 0.0f};
-        int slot = 0;
-        auto push = [&](int t, float v) -> float {
-            const int slot1 = slot + 1 == W ? 0 : slot + 1;
-            float o1 = stream_step(ring1, W, slot, slot1, p1, v, t - p, start1, len, w1, w2, w12);
-            float o2 = stream_step(ring2, W, slot, slot1, p2, o1, t - 2 * p, start2, len, w1, w2, w12);
-            float o3 = stream_step(ring3, W, slot, slot1, p3, o2, t - 3 * p, start3, len, w1, w2, w12);
-            slot = slot1;
-            return o3;
-        };
-        auto push_steady = [&](float v) -> float {
-            const int slot1 = slot + 1 == W ? 0 : slot + 1;
-            float *at = ring1 + slot * kRingSlot, *at1 = ring1 + slot1 * kRingSlot;
-            float o1 = steady_step(at, at1, p1, v, w1, w2);
-            float o2 = steady_step(at + kRingPass, at1 + kRingPass, p2, o1, w1, w2);
-            float o3 = steady_step(at + 2 * kRingPass, at1 + 2 * kRingPass, p3, o2, w1, w2);
-            slot = slot1;
-            return o3;
-        };
+        const int t_begin = chunk ? y0 - 3 * p : 0, t_store = y0 + 3 * p, t_last = y1 + 3 * p;
+        // steps in [plain_lo, plain_hi): no pass is left of its first or right of its last output
+        const int plain_lo = 3 * p, plain_hi = len + p;
+        cascade c;
+        c.reset(ring, W, r, len, jr.w1, jr.w2);
         if (kAlongRows) {
             // lines are plane rows: stage 32 columns of the warp's 32 rows through a skewed tile so
             // that global accesses stay coalesced; the next block is fetched while this one is swept
@@ -337,13 +347,22 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
             const float *in = src + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane);
             const int rows_here = min(32, min(cross, jr.need_r1) - strip * 32);
             float ahead[32];
+            // whole strips away from the line's ends load without predicates; addresses are one
+            // 32-bit multiply-add off a pointer that moves once per block
             auto fetch = [&](int tb) {
-                const int col = tb + lane;
+                const float *from = in + tb;
+                if (rows_here == 32 && tb >= 0 && tb + 32 <= len) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    ahead[q] = (q < rows_here && col >= 0 && col < len) ? in[ptrdiff_t(q) * pitch + tb] : 0.0f;
+                    for (int q = 0; q < 32; ++q) ahead[q] = from[q * pitch];
+                } else {
+                    const int col = tb + lane;
+                    const bool col_in = col >= 0 && col < len;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) ahead[q] = (col_in && q < rows_here) ? from[q * pitch] : 0.0f;
+                }
             };
             const int t_first = t_begin - ((t_begin + skew) & 31);      // blocks start on 128 B lines
+            float *out_rows = dst + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane - 3 * p);
             fetch(t_first);
             for (int tb = t_first; tb < t_last; tb += 32) {
 #pragma unroll
@@ -351,22 +370,24 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
                 if (tb + 32 < t_last) fetch(tb + 32);
                 __syncwarp();
                 if (active) {
-                    // [u_steady, u_tail) of this block is the branch-free stretch
-                    const int u_first = max(t_begin - tb, 0), u_last = min(t_last - tb, 32);
-                    const int u_steady = min(max(t_steady - tb, u_first), u_last), u_tail = max(min(t_inside - tb, u_last), u_steady);
-#pragma unroll 1
-                    for (int u = u_first; u < u_steady; ++u) mine[u] = push(tb + u, mine[u]);
-#pragma unroll 4
-                    for (int u = u_steady; u < u_tail; ++u) mine[u] = push_steady(mine[u]);
-#pragma unroll 1
-                    for (int u = u_tail; u < u_last; ++u) mine[u] = push(tb + u, mine[u]);
+                    if (tb >= plain_lo && tb + 32 <= plain_hi) {
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) mine[u] = c.push<false>(mine[u], 0);
+                    } else {
+#pragma unroll 8
+                        for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(mine[u], tb + u);
+                    }
                 }
                 __syncwarp();
                 const int col = tb + lane - 3 * p;
                 if (col >= y0 && col < y1) {
-                    float *out = dst + size_t(strip * 32) * size_t(pitch) + size_t(skew + col);
-#pragma unroll 8
-                    for (int q = 0; q < rows_here; ++q) out[size_t(q) * size_t(pitch)] = tile[q * 33 + lane];
+                    float *out = out_rows + tb;
+                    if (rows_here == 32) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) out[q * pitch] = tile[q * 33 + lane];
+                    } else {
+                        for (int q = 0; q < rows_here; ++q) out[q * pitch] = tile[q * 33 + lane];
+                    }
                 }
                 __syncwarp();
             }
@@ -374,31 +395,40 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
             if (!active) continue;
             constexpr int kAhead = 8;
             const float *in = src + size_t(line);
+            float *out = dst + size_t(line);
             float ahead[kAhead];
             auto fetch = [&](int tb) {
+                const float *from = in + ptrdiff_t(tb) * ptrdiff_t(pitch);
+                if (tb >= 0 && tb + kAhead <= len) {
 #pragma unroll
-                for (int u = 0; u < kAhead; ++u) ahead[u] = tb + u < len ? in[size_t(tb + u) * size_t(pitch)] : 0.0f;
+                    for (int u = 0; u < kAhead; ++u) ahead[u] = from[u * pitch];
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kAhead; ++u) ahead[u] = unsigned(tb + u) < unsigned(len) ? from[u * pitch] : 0.0f;
+                }
             };
-            fetch(t_begin);
-            for (int tb = t_begin; tb < t_last; tb += kAhead) {
+            // blocks of kAhead steps, laid out so that none straddles the first stored output
+            const int t_first = t_store - ((t_store - t_begin + kAhead - 1) & ~(kAhead - 1));
+            fetch(t_first);
+            for (int tb = t_first; tb < t_last; tb += kAhead) {
                 float v[kAhead];
 #pragma unroll
                 for (int u = 0; u < kAhead; ++u) v[u] = ahead[u];
                 if (tb + kAhead < t_last) fetch(tb + kAhead);
-                if (tb >= t_steady && tb + kAhead <= t_inside) {
-                    float *out = dst + size_t(tb - 3 * p) * size_t(pitch) + size_t(line);
+                const bool plain = tb >= plain_lo && tb + kAhead <= plain_hi;
+                if (plain && tb < t_store) {
 #pragma unroll
-                    for (int u = 0; u < kAhead; ++u) out[u * pitch] = push_steady(v[u]);
+                    for (int u = 0; u < kAhead; ++u) c.push<false>(v[u], 0);
+                } else if (plain && tb + kAhead <= t_last) {
+                    float *o = out + ptrdiff_t(tb - 3 * p) * ptrdiff_t(pitch);
+#pragma unroll
+                    for (int u = 0; u < kAhead; ++u) o[u * pitch] = c.push<false>(v[u], 0);
                 } else {
-#pragma unroll 1
-                    for (int u = 0; u < kAhead; ++u) {
-                        if (tb + u >= t_last) break;
-                        float x = v[0];                              // v[u] without indexing registers
 #pragma unroll
-                        for (int k = 1; k < kAhead; ++k) x = u == k ? v[k] : x;
-                        const float o = push(tb + u, x);
+                    for (int u = 0; u < kAhead; ++u) {
+                        const float o = c.push<true>(v[u], tb + u);
                         const int i3 = tb + u - 3 * p;
-                        if (i3 >= y0 && i3 < y1) dst[size_t(i3) * size_t(pitch) + size_t(line)] = o;
+                        if (i3 >= y0 && i3 < y1) out[size_t(i3) * size_t(pitch)] = o;
                     }
                 }
             }
@@ -544,6 +574,7 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
         }
         auto resident = [](size_t smem) { return int(std::min<size_t>(16, (227 * 1024) / (smem + 1024))); };
         launch_pdl(k_blur_units, 1, kBlock, 0, s, f);
+        // x sweeps planes -> planes_tmp, then y sweeps back; small radii keep their histories in registers
         launch_pdl(k_blur_stream<true>, kSMs * resident(row_bytes), kStreamThreads, row_bytes, s, f, f.planes, f.planes_tmp);
         launch_pdl(k_blur_stream<false>, kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s, f, f.planes_tmp, f.planes);
     }
