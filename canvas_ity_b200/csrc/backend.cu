@@ -679,18 +679,20 @@ int upload_frame(cb200_canvas *cv)
     f.n_opaque_jobs = 0;
     for (const job_rec &j : sf.jobs) f.n_opaque_jobs += j.opaque;
     f.general_compositor = 0;
-    bool needs_planes = false, needs_gradients = false, needs_everything = false;
+    bool needs_planes = false, needs_gradients = false, needs_patterns = false, needs_everything = false;
     for (const job_rec &j : sf.jobs) {
         const draw_rec &d = sf.draws[j.draw];
         const brush_rec &br = sf.brushes[d.brush];
         if (j.kind != JOB_MAIN || d.mask_src) needs_planes = true;
         if (j.kind == JOB_MAIN && br.type != CB200_BRUSH_COLOR) {
-            if (br.type == CB200_BRUSH_PATTERN || br.n_colors > 16) needs_everything = true;   // 16 = kStagedStops
+            if (br.type == CB200_BRUSH_PATTERN) needs_patterns = true;
+            else if (br.n_colors > 16) needs_everything = true;                                // 16 = kStagedStops
             else needs_gradients = true;
         }
     }
-    // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything
-    if (needs_everything || (needs_planes && needs_gradients)) f.general_compositor = 3;
+    // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything, 4 lean + patterns + small gradients
+    if (needs_everything || (needs_planes && (needs_gradients || needs_patterns))) f.general_compositor = 3;
+    else if (needs_patterns) f.general_compositor = 4;
     else if (needs_gradients) f.general_compositor = 2;
     else if (needs_planes) f.general_compositor = 1;
     f.shadow_jobs = reinterpret_cast<uint32_t *>(b + o_sjobs);

@@ -294,6 +294,80 @@ __device__ __noinline__ rgba paint_pattern(const float4 *texels, const staged_br
     return scale(1.0f / wsum, acc);
 }
 
+// The same sample for the common footprint of four taps per axis (no minification: scale clamps to 1),
+// with the work that is shared taken out of the pixel: the taps of one axis -- first index, Keys weights,
+// wrapped texel indices (one modulo, then increments) -- depend on one brush-space coordinate only, so an
+// axis-aligned brush matrix gives every row of a lane the same column taps and every lane of a row the same
+// row taps.  Same taps, weights (weight_x * weight_y) and summation order as hpp:2296-2328; the products are
+// fused into the sums.
+struct axis_taps { float w[4]; int i[4]; int n; };
+__device__ __forceinline__ axis_taps keys_taps(float q, float s, float rcp, int size, bool clamp_mode)
+{
+    axis_taps a;
+    const int first = int(ceilf(q - s * 2.0f)), last = int(ceilf(q + s * 2.0f));
+    a.n = last - first;
+    int at = 0;
+    if (!clamp_mode) {
+        at = first % size;
+        if (at < 0) at += size;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a.w[k] = keys_weight(fabsf(rcp * (float(first + k) - q)));
+        a.i[k] = clamp_mode ? min(max(first + k, 0), size - 1) : at;
+        at = at + 1 == size ? 0 : at + 1;
+    }
+    return a;
+}
+__device__ __forceinline__ rgba pattern_4x4(const float4 *tex, int width, const axis_taps &cx, const axis_taps &cy)
+{
+    float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f, wsum = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        const float4 *row = tex + cy.i[ky] * width;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+            const float wgt = cx.w[kx] * cy.w[ky];
+            const float4 c = __ldg(row + cx.i[kx]);
+            r = fmaf(wgt, c.x, r); g = fmaf(wgt, c.y, g); b = fmaf(wgt, c.z, b); a = fmaf(wgt, c.w, a);
+            wsum += wgt;
+        }
+    }
+    const float norm = 1.0f / wsum;
+    return mk(norm * r, norm * g, norm * b, norm * a);
+}
+
+// Any other footprint (minification, or a coordinate whose rounded ends give 3 or 5 taps), tap by tap as
+// hpp:2296-2328.  Inline on purpose: a call from the compositor's pixel loop would put the warp's 32 pixel
+// registers on the stack for the whole kernel.
+__device__ __forceinline__ rgba pattern_any(const float4 *tex, int width, int height, bool clamp_mode, float qx, float qy,
+                                            float sx, float sy, float rx, float ry)
+{
+    const int x0 = int(ceilf(qx - sx * 2.0f)), y0 = int(ceilf(qy - sy * 2.0f));
+    const int x1 = int(ceilf(qx + sx * 2.0f)), y1 = int(ceilf(qy + sy * 2.0f));
+    float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f, wsum = 0.0f;
+#pragma unroll 1
+    for (int ty = y0; ty < y1; ++ty) {
+        const float wy = keys_weight(fabsf(ry * (float(ty) - qy)));
+        int yy = ty % height;
+        if (yy < 0) yy += height;
+        if (clamp_mode) yy = min(max(ty, 0), height - 1);
+        const float4 *row = tex + yy * width;
+#pragma unroll 1
+        for (int tx = x0; tx < x1; ++tx) {
+            const float wgt = keys_weight(fabsf(rx * (float(tx) - qx))) * wy;
+            int xx = tx % width;
+            if (xx < 0) xx += width;
+            if (clamp_mode) xx = min(max(tx, 0), width - 1);
+            const float4 c = __ldg(row + xx);
+            r = fmaf(wgt, c.x, r); g = fmaf(wgt, c.y, g); b = fmaf(wgt, c.z, b); a = fmaf(wgt, c.w, a);
+            wsum += wgt;
+        }
+    }
+    const float norm = 1.0f / wsum;
+    return mk(norm * r, norm * g, norm * b, norm * a);
+}
+
 // Non-solid brushes: kept out of line so the solid path stays small.
 __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t draw, float x, float y)
 {
@@ -319,6 +393,7 @@ __device__ __noinline__ rgba paint_slow(paint_tables f, uint32_t brush, uint32_t
 //   kMode 1  + clip masks (in and out) and shadow planes, brushes still solid
 //   kMode 2  lean + unclipped gradient brushes with at most kStagedStops stops (full-canvas gradient fills)
 //   kMode 3  everything: masks, shadows, gradients, patterns
+//   kMode 4  lean + unclipped patterns / images and small gradients (draw_image and pattern fills without clips or shadows)
 // kLists: the job search walks the tile row's job list (frames with many jobs) instead of the
 // canvas' whole job range (a handful of jobs: the plain loop is leaner).
 #ifndef CB200_COMP_CTAS0
@@ -347,7 +422,7 @@ template <int kMode, bool kLists>
 __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5)
 k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager_load)
 {
-    constexpr bool kGeneral = kMode == 1 || kMode == 3, kPaint = kMode >= 2, kPattern = kMode == 3;
+    constexpr bool kGeneral = kMode == 1 || kMode == 3, kPaint = kMode >= 2, kPattern = kMode >= 3;
     grid_dependency_wait();
     __shared__ __align__(16) staged_brush staged_brushes[kPaint ? kTileWarps : 1];
     frame_header *h = f.hdr;
@@ -559,6 +634,63 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                     rgba paint = gradient_at(g, sbrush, float(x) + 0.5f, float(row0 + r) + 0.5f);
                     blend_program(px[r], scale(cov * alpha, paint), m);
                 }
+            } else if (kPattern && staged && brush_type == CB200_BRUSH_PATTERN && !mask && !mask_out) {
+                // unclipped pattern / image fill (hpp:2274-2330): axis set-ups hoisted where the brush matrix allows
+                const affine inv = sbrush.inv;
+                const int tex_w = sbrush.b.width, tex_h = sbrush.b.height;
+                const uint32_t repetition = sbrush.b.repetition;
+                const bool clamp_mode = (sbrush.b.flags & CB200_BRUSH_CLAMP) != 0;
+                const float4 *tex = f.texels + sbrush.b.texel_offset;
+                const float w = float(tex_w), hgt = float(tex_h);
+                const float sx = fmaxf(1.0f, fminf(fabsf(inv.a) + fabsf(inv.c), w * 0.25f));
+                const float sy = fmaxf(1.0f, fminf(fabsf(inv.b) + fabsf(inv.d), hgt * 0.25f));
+                const float rx = 1.0f / sx, ry = 1.0f / sy;
+                const mix_program m = decode_mix(op);
+                const bool cols_shared = inv.c == 0.0f, rows_shared = inv.b == 0.0f;      // warp-uniform
+                // a lane's column taps hold for all its rows when inv.c == 0; lane r < 8 prepares row r's taps when inv.b == 0
+                const vec2 p_col = apply(inv, v2(float(x) + 0.5f, float(row0) + 0.5f));
+                axis_taps cx = keys_taps(p_col.x - 0.5f, sx, rx, tex_w, clamp_mode);
+                bool x_out = (repetition & 2u) && (p_col.x < 0.0f || w <= p_col.x);
+                const vec2 p_row = apply(inv, v2(float(x) + 0.5f, float(row0 + (lane & 7)) + 0.5f));
+                const axis_taps cy_lane = keys_taps(p_row.y - 0.5f, sy, ry, tex_h, clamp_mode);
+                const bool y_out_lane = (repetition & 1u) && (p_row.y < 0.0f || hgt <= p_row.y);
+#pragma unroll
+                for (int r = 0; r < kWarpRows; ++r) {
+                    const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                    axis_taps cy;
+                    bool y_out;
+                    if (rows_shared) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            cy.w[k] = __shfl_sync(0xffffffffu, cy_lane.w[k], r);
+                            cy.i[k] = __shfl_sync(0xffffffffu, cy_lane.i[k], r);
+                        }
+                        cy.n = __shfl_sync(0xffffffffu, cy_lane.n, r);
+                        y_out = __shfl_sync(0xffffffffu, int(y_out_lane), r) != 0;
+                    }
+                    if (!(cov >= kThreshold || everywhere)) continue;
+                    ++painted;
+                    const float cy_px = float(row0 + r) + 0.5f;
+                    if (!rows_shared || !cols_shared) {
+                        const vec2 p = apply(inv, v2(float(x) + 0.5f, cy_px));
+                        if (!rows_shared) {
+                            cy = keys_taps(p.y - 0.5f, sy, ry, tex_h, clamp_mode);
+                            y_out = (repetition & 1u) && (p.y < 0.0f || hgt <= p.y);
+                        }
+                        if (!cols_shared) {
+                            cx = keys_taps(p.x - 0.5f, sx, rx, tex_w, clamp_mode);
+                            x_out = (repetition & 2u) && (p.x < 0.0f || w <= p.x);
+                        }
+                    }
+                    rgba paint;
+                    if (x_out || y_out) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (cx.n == 4 && cy.n == 4) paint = pattern_4x4(tex, tex_w, cx, cy);
+                    else {
+                        const vec2 q = apply(inv, v2(float(x) + 0.5f, cy_px)) - v2(0.5f, 0.5f);
+                        paint = pattern_any(tex, tex_w, tex_h, clamp_mode, q.x, q.y, sx, sy, rx, ry);
+                    }
+                    blend_program(px[r], scale(cov * alpha, paint), m);
+                }
             } else if (kGeneral) {
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
@@ -648,12 +780,14 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     }
     auto go = [&](auto kernel) { launch_pdl(kernel, tiles, kCompBlock, 0, s, f, t, tiles_x, ty0, eager); };
     if (f.row_jobs) {
-        if (f.general_compositor == 3) go(k_composite<3, true>);
+        if (f.general_compositor == 4) go(k_composite<4, true>);
+        else if (f.general_compositor == 3) go(k_composite<3, true>);
         else if (f.general_compositor == 2) go(k_composite<2, true>);
         else if (f.general_compositor == 1) go(k_composite<1, true>);
         else go(k_composite<0, true>);
     } else {
-        if (f.general_compositor == 3) go(k_composite<3, false>);
+        if (f.general_compositor == 4) go(k_composite<4, false>);
+        else if (f.general_compositor == 3) go(k_composite<3, false>);
         else if (f.general_compositor == 2) go(k_composite<2, false>);
         else if (f.general_compositor == 1) go(k_composite<1, false>);
         else go(k_composite<0, false>);

@@ -43,7 +43,7 @@ struct device_frame {
     // earlier job and the old pixels are irrelevant there (occlusion culling, k_tile_flags -> k_composite)
     uint32_t *tile_cover;  uint32_t n_target_tiles;
     uint32_t n_opaque_jobs;                            // occlusion-culling candidates in this frame
-    int general_compositor;                            // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything
+    int general_compositor;                            // 0 lean, 1 + masks / shadows / clips, 2 lean + small gradients, 3 everything, 4 lean + patterns
     float4 *texels;
     // geometry
     uint32_t *unit_count, *unit_offset;               // n_units + 1
