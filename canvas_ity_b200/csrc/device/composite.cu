@@ -161,14 +161,24 @@ struct staged_brush {
     brush_rec b;
     affine inv;
     float stops[kStagedStops];
+    float inv_span[kStagedStops];          // 1 / (stops[k] - stops[k-1]), k >= 1
     float4 colors[kStagedStops];
+    // pattern fills under an axis-aligned matrix: Keys weights, texel-row offsets and flags of the warp's 8 scanlines
+    float4 row_w[8];
+    int4 row_i[8];
+    int row_flags[8];
 };
 
 // Linear / radial gradient at a device-space pixel centre (hpp:2331-2376), from the staged copy.
-// Everything that does not depend on the pixel is gathered once per (job, warp).
+// Everything that does not depend on the pixel is gathered once per (job, warp): the axis, the radial
+// quadratic's leading coefficient and its reciprocal, and -- for the usual handful of stops -- the stop
+// positions themselves, so that the upper_bound search is four chained compares instead of a loop over
+// shared memory.  The offset inside a stop interval is multiplied by the interval's reciprocal (staged)
+// where the reference divides: at most 2 ulp of the interpolation factor, no decision depends on it.
 struct gradient_ctx {
     affine inv;
-    float sx, sy, ax, ay, axis2, r0, dr;
+    float sx, sy, ax, ay, axis2, r0, dr, qa, inv2a;
+    float s0, s1, s2, s3;
     uint32_t n;
     bool linear;
 };
@@ -183,8 +193,13 @@ __device__ __forceinline__ gradient_ctx make_gradient_ctx(const staged_brush &sb
     g.ax = axis.x; g.ay = axis.y;
     g.axis2 = dot(axis, axis);
     g.r0 = b.r0; g.dr = b.r1 - b.r0;
+    g.qa = g.axis2 - g.dr * g.dr;
+    g.inv2a = 1.0f / (2.0f * g.qa);
     g.n = b.n_colors;
     g.linear = b.type == CB200_BRUSH_LINEAR;
+    const float never = __int_as_float(0x7f800000);        // t < +inf: the search stops there
+    g.s0 = g.n > 0 ? sb.stops[0] : never; g.s1 = g.n > 1 ? sb.stops[1] : never;
+    g.s2 = g.n > 2 ? sb.stops[2] : never; g.s3 = g.n > 3 ? sb.stops[3] : never;
     return g;
 }
 
@@ -198,27 +213,31 @@ __device__ __forceinline__ rgba gradient_at(const gradient_ctx &g, const staged_
         if (g.axis2 == 0.0f) return mk(0.0f, 0.0f, 0.0f, 0.0f);
         t = along / g.axis2;
     } else {
-        float qa = g.axis2 - g.dr * g.dr;
         float qb = -2.0f * (along + g.r0 * g.dr);
         float qc = dot(rel, rel) - g.r0 * g.r0;
-        float disc = qb * qb - 4.0f * qa * qc;
+        float disc = qb * qb - 4.0f * g.qa * qc;
         if (disc < 0.0f || (g.axis2 == 0.0f && g.dr == 0.0f)) return mk(0.0f, 0.0f, 0.0f, 0.0f);
-        float root = sqrtf(disc), inv2a = 1.0f / (2.0f * qa);
-        float ta = (-qb - root) * inv2a, tb = (-qb + root) * inv2a;
+        float root = sqrtf(disc);
+        float ta = (-qb - root) * g.inv2a, tb = (-qb + root) * g.inv2a;
         if (g.r0 + g.dr * tb >= 0.0f) t = tb;
         else if (g.r0 + g.dr * ta >= 0.0f) t = ta;
         else return mk(0.0f, 0.0f, 0.0f, 0.0f);
     }
     uint32_t hi = 0;                                    // first stop strictly greater than t (NaN: none)
-    while (hi < g.n && !(t < sb.stops[hi])) ++hi;
+    if (g.n <= 4) {
+        const bool c0 = !(t < g.s0), c1 = c0 && !(t < g.s1), c2 = c1 && !(t < g.s2), c3 = c2 && !(t < g.s3);
+        hi = min(uint32_t(c0) + uint32_t(c1) + uint32_t(c2) + uint32_t(c3), g.n);
+    } else {
+        while (hi < g.n && !(t < sb.stops[hi])) ++hi;
+    }
     float4 c;
     if (hi == 0) c = sb.colors[0];
     else if (hi == g.n) c = sb.colors[g.n - 1];
     else {
-        float m = (t - sb.stops[hi - 1]) / (sb.stops[hi] - sb.stops[hi - 1]);
+        float m = (t - sb.stops[hi - 1]) * sb.inv_span[hi];
         float4 lo = sb.colors[hi - 1], up = sb.colors[hi];
-        c = make_float4(lo.x + m * (up.x - lo.x), lo.y + m * (up.y - lo.y), lo.z + m * (up.z - lo.z),
-                        lo.w + m * (up.w - lo.w));
+        c = make_float4(fmaf(m, up.x - lo.x, lo.x), fmaf(m, up.y - lo.y, lo.y), fmaf(m, up.z - lo.z, lo.z),
+                        fmaf(m, up.w - lo.w, lo.w));
     }
     return mk(c.x * c.w, c.y * c.w, c.z * c.w, c.w);
 }
@@ -419,7 +438,7 @@ __device__ __forceinline__ void blend_program(float4 &back, rgba fore, const mix
 }
 
 template <int kMode, bool kLists>
-__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : 5)
+__global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : kMode == 3 ? 5 : 4)
 k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager_load)
 {
     constexpr bool kGeneral = kMode == 1 || kMode == 3, kPaint = kMode >= 2, kPattern = kMode >= 3;
@@ -588,7 +607,9 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                     if (lane < 6)
                         reinterpret_cast<float *>(&sbrush.inv)[lane] = reinterpret_cast<const float *>(&f.draws[rec->draw].inverse)[lane];
                     if (uint32_t(lane) < n_stops) {
-                        sbrush.stops[lane] = f.stops[gb->first_color + lane];
+                        const float stop = f.stops[gb->first_color + lane];
+                        sbrush.stops[lane] = stop;
+                        sbrush.inv_span[lane] = lane ? 1.0f / (stop - f.stops[gb->first_color + lane - 1]) : 0.0f;
                         sbrush.colors[lane] = f.colors[gb->first_color + lane];
                     }
                 }
@@ -635,7 +656,7 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                     blend_program(px[r], scale(cov * alpha, paint), m);
                 }
             } else if (kPattern && staged && brush_type == CB200_BRUSH_PATTERN && !mask && !mask_out) {
-                // unclipped pattern / image fill (hpp:2274-2330): axis set-ups hoisted where the brush matrix allows
+                // unclipped pattern / image fill (hpp:2274-2330)
                 const affine inv = sbrush.inv;
                 const int tex_w = sbrush.b.width, tex_h = sbrush.b.height;
                 const uint32_t repetition = sbrush.b.repetition;
@@ -646,50 +667,102 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                 const float sy = fmaxf(1.0f, fminf(fabsf(inv.b) + fabsf(inv.d), hgt * 0.25f));
                 const float rx = 1.0f / sx, ry = 1.0f / sy;
                 const mix_program m = decode_mix(op);
-                const bool cols_shared = inv.c == 0.0f, rows_shared = inv.b == 0.0f;      // warp-uniform
-                // a lane's column taps hold for all its rows when inv.c == 0; lane r < 8 prepares row r's taps when inv.b == 0
-                const vec2 p_col = apply(inv, v2(float(x) + 0.5f, float(row0) + 0.5f));
-                axis_taps cx = keys_taps(p_col.x - 0.5f, sx, rx, tex_w, clamp_mode);
-                bool x_out = (repetition & 2u) && (p_col.x < 0.0f || w <= p_col.x);
-                const vec2 p_row = apply(inv, v2(float(x) + 0.5f, float(row0 + (lane & 7)) + 0.5f));
-                const axis_taps cy_lane = keys_taps(p_row.y - 0.5f, sy, ry, tex_h, clamp_mode);
-                const bool y_out_lane = (repetition & 1u) && (p_row.y < 0.0f || hgt <= p_row.y);
+                // Rows of this lane whose pixel goes tap by tap (pattern_any): all of them under a rotated or skewed
+                // brush matrix, otherwise only pixels whose footprint is not four taps wide.
+                uint32_t slow_rows = 0;
+                if (inv.b == 0.0f && inv.c == 0.0f) {
+                    // Axis-aligned matrix (every draw_image without rotation): the footprint is a product.  A lane's
+                    // column taps hold for all of its rows; lane r < 8 prepares the row taps of scanline r and leaves
+                    // them in shared memory; the four texel rows are filtered along x once per lane (row_filter) and
+                    // shared by all pixel rows that need them -- at 8x magnification a warp's 8 scanlines touch 4 or 5
+                    // texel rows, i.e. 16-20 texel loads per lane instead of 128.  Sum_y wy (Sum_x wx c) /
+                    // (Sum wx Sum wy): the reference's sum in another order (a few ulp; inside the promised 1e-4).
+                    const vec2 p_col = apply(inv, v2(float(x) + 0.5f, float(row0) + 0.5f));
+                    const axis_taps cx = keys_taps(p_col.x - 0.5f, sx, rx, tex_w, clamp_mode);
+                    const bool x_bad = cx.n != 4;
+                    const bool x_out = (repetition & 2u) && (p_col.x < 0.0f || w <= p_col.x);
+                    const float sum_wx = ((cx.w[0] + cx.w[1]) + cx.w[2]) + cx.w[3];
+                    __syncwarp();
+                    if (lane < kWarpRows) {
+                        const vec2 p_row = apply(inv, v2(float(x) + 0.5f, float(row0 + lane) + 0.5f));
+                        const axis_taps cy = keys_taps(p_row.y - 0.5f, sy, ry, tex_h, clamp_mode);
+                        const bool y_out = (repetition & 1u) && (p_row.y < 0.0f || hgt <= p_row.y);
+                        sbrush.row_w[lane] = make_float4(cy.w[0], cy.w[1], cy.w[2], cy.w[3]);
+                        sbrush.row_i[lane] = make_int4(cy.i[0] * tex_w, cy.i[1] * tex_w, cy.i[2] * tex_w, cy.i[3] * tex_w);
+                        sbrush.row_flags[lane] = (cy.n != 4 ? 1 : 0) | (y_out ? 2 : 0);
+                    }
+                    __syncwarp();
+                    rgba filtered[4];
+                    int4 filtered_at = make_int4(-1, -1, -1, -1);
+                    auto row_filter = [&](int texel_row_offset) -> rgba {
+                        const float4 *row = tex + texel_row_offset;
+                        float fr = 0.0f, fg = 0.0f, fb = 0.0f, fa = 0.0f;
 #pragma unroll
-                for (int r = 0; r < kWarpRows; ++r) {
-                    const float cov = fminf(fabsf(row_sum(r)), 1.0f);
-                    axis_taps cy;
-                    bool y_out;
-                    if (rows_shared) {
+                        for (int kx = 0; kx < 4; ++kx) {
+                            const float4 c = __ldg(row + cx.i[kx]);
+                            fr = fmaf(cx.w[kx], c.x, fr); fg = fmaf(cx.w[kx], c.y, fg);
+                            fb = fmaf(cx.w[kx], c.z, fb); fa = fmaf(cx.w[kx], c.w, fa);
+                        }
+                        return mk(fr, fg, fb, fa);
+                    };
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            cy.w[k] = __shfl_sync(0xffffffffu, cy_lane.w[k], r);
-                            cy.i[k] = __shfl_sync(0xffffffffu, cy_lane.i[k], r);
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                        if (!(cov >= kThreshold || everywhere)) continue;
+                        ++painted;
+                        const int flags = sbrush.row_flags[r];
+                        if (x_out || (flags & 2)) {
+                            blend_program(px[r], mk(0.0f, 0.0f, 0.0f, 0.0f), m);
+                            continue;
                         }
-                        cy.n = __shfl_sync(0xffffffffu, cy_lane.n, r);
-                        y_out = __shfl_sync(0xffffffffu, int(y_out_lane), r) != 0;
-                    }
-                    if (!(cov >= kThreshold || everywhere)) continue;
-                    ++painted;
-                    const float cy_px = float(row0 + r) + 0.5f;
-                    if (!rows_shared || !cols_shared) {
-                        const vec2 p = apply(inv, v2(float(x) + 0.5f, cy_px));
-                        if (!rows_shared) {
-                            cy = keys_taps(p.y - 0.5f, sy, ry, tex_h, clamp_mode);
-                            y_out = (repetition & 1u) && (p.y < 0.0f || hgt <= p.y);
+                        if (x_bad || (flags & 1)) {
+                            slow_rows |= 1u << r;
+                            continue;
                         }
-                        if (!cols_shared) {
-                            cx = keys_taps(p.x - 0.5f, sx, rx, tex_w, clamp_mode);
-                            x_out = (repetition & 2u) && (p.x < 0.0f || w <= p.x);
+                        const float4 wy = sbrush.row_w[r];
+                        const int4 at = sbrush.row_i[r];
+                        if (!(at.x == filtered_at.x && at.y == filtered_at.y && at.z == filtered_at.z && at.w == filtered_at.w)) {
+                            if (at.x == filtered_at.y && at.y == filtered_at.z && at.z == filtered_at.w) {
+                                filtered[0] = filtered[1]; filtered[1] = filtered[2]; filtered[2] = filtered[3];
+                            } else {
+                                filtered[0] = row_filter(at.x); filtered[1] = row_filter(at.y); filtered[2] = row_filter(at.z);
+                            }
+                            filtered[3] = row_filter(at.w);
+                            filtered_at = at;
                         }
+                        float pr = wy.x * filtered[0].r, pg = wy.x * filtered[0].g, pb = wy.x * filtered[0].b, pa = wy.x * filtered[0].a;
+                        pr = fmaf(wy.y, filtered[1].r, pr); pg = fmaf(wy.y, filtered[1].g, pg); pb = fmaf(wy.y, filtered[1].b, pb); pa = fmaf(wy.y, filtered[1].a, pa);
+                        pr = fmaf(wy.z, filtered[2].r, pr); pg = fmaf(wy.z, filtered[2].g, pg); pb = fmaf(wy.z, filtered[2].b, pb); pa = fmaf(wy.z, filtered[2].a, pa);
+                        pr = fmaf(wy.w, filtered[3].r, pr); pg = fmaf(wy.w, filtered[3].g, pg); pb = fmaf(wy.w, filtered[3].b, pb); pa = fmaf(wy.w, filtered[3].a, pa);
+                        // cov * alpha / total weight in one factor
+                        const float norm = (cov * alpha) * __frcp_rn(sum_wx * (((wy.x + wy.y) + wy.z) + wy.w));
+                        blend_program(px[r], mk(norm * pr, norm * pg, norm * pb, norm * pa), m);
                     }
-                    rgba paint;
-                    if (x_out || y_out) paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
-                    else if (cx.n == 4 && cy.n == 4) paint = pattern_4x4(tex, tex_w, cx, cy);
-                    else {
-                        const vec2 q = apply(inv, v2(float(x) + 0.5f, cy_px)) - v2(0.5f, 0.5f);
-                        paint = pattern_any(tex, tex_w, tex_h, clamp_mode, q.x, q.y, sx, sy, rx, ry);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                        if (cov >= kThreshold || everywhere) { slow_rows |= 1u << r; ++painted; }
                     }
-                    blend_program(px[r], scale(cov * alpha, paint), m);
+                }
+                if (__any_sync(0xffffffffu, slow_rows != 0)) {
+                    // one copy of the tap-by-tap code: the pixel registers rotate through px[0] instead of the loop
+                    // being unrolled eight times
+#pragma unroll 1
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        float4 cur = px[0];
+                        const float cov = fminf(fabsf(row_sum(r)), 1.0f);
+                        if (slow_rows >> r & 1u) {
+                            const vec2 p = apply(inv, v2(float(x) + 0.5f, float(row0 + r) + 0.5f));
+                            rgba paint = mk(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (!(((repetition & 2u) && (p.x < 0.0f || w <= p.x)) || ((repetition & 1u) && (p.y < 0.0f || hgt <= p.y))))
+                                paint = pattern_any(tex, tex_w, tex_h, clamp_mode, p.x - 0.5f, p.y - 0.5f, sx, sy, rx, ry);
+                            blend_program(cur, scale(cov * alpha, paint), m);
+                        }
+#pragma unroll
+                        for (int k = 0; k + 1 < kWarpRows; ++k) px[k] = px[k + 1];
+                        px[kWarpRows - 1] = cur;
+                    }
                 }
             } else if (kGeneral) {
 #pragma unroll
