@@ -437,7 +437,42 @@ __device__ __forceinline__ void blend_program(float4 &back, rgba fore, const mix
                        fminf(fmaf(mf, fore.a, mb * back.w), 1.0f));
 }
 
-template <int kMode, bool kLists>
+// ---- bulk asynchronous copies (the TMA engine's 1-D form: cp.async.bulk, no tensor map) ------------------------
+// Used by the kTma build of the compositor: a warp's 8 framebuffer rows (512 contiguous bytes each) travel between
+// global and shared memory as eight bulk copies issued by eight lanes, completion through an mbarrier (loads) or a
+// bulk group (stores), instead of eight 16-byte LDG/STG per lane.  An A/B against the plain build.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int kMode, bool kLists, bool kTma = false>
 __global__ void __launch_bounds__(kCompBlock, kMode == 0 ? CB200_COMP_CTAS0 : kMode == 1 ? 7 : kMode == 2 ? 6 : kMode == 3 ? 5 : 4)
 k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager_load)
 {
@@ -480,8 +515,31 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
     const uint32_t first_job = cover ? cover - 1u : job_range.x;
     float4 px[kWarpRows];
     const bool fetch_now = eager_load && !t.clear_first && !cover;
+    // kTma: the warp's rows wait in shared memory (bulk copies, one mbarrier per warp) until the first job needs them
+    __shared__ __align__(128) float4 tma_rows[kTma ? kTileWarps * kWarpRows * 32 : 1];
+    __shared__ __align__(8) unsigned long long tma_bar[kTma ? kTileWarps : 1];
+    float4 *const my_rows = tma_rows + (kTma ? warp * kWarpRows * 32 : 0);
+    const uint32_t my_bar = smem_u32(&tma_bar[kTma ? warp : 0]);
+    bool pending = false;
+    if (kTma) {
+        if (lane == 0) mbar_init(my_bar, 1);
+        __syncwarp();
+    }
+    auto settle = [&]() {                                      // the rows a bulk load brought: shared memory -> registers
+        if (kTma && pending) {
+            mbar_wait(my_bar, 0);
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r) px[r] = my_rows[r * 32 + lane];
+            pending = false;
+        }
+    };
     auto fetch = [&]() {
-        if (whole) {
+        if (kTma && whole) {
+            if (lane == 0) mbar_expect_tx(my_bar, kWarpRows * 512);
+            __syncwarp();
+            if (lane < kWarpRows) bulk_load(smem_u32(my_rows + lane * 32), fb_at - lane + size_t(lane) * pitch, 512, my_bar);
+            pending = true;
+        } else if (whole) {
 #pragma unroll
             for (int r = 0; r < kWarpRows; ++r) px[r] = __ldcs(fb_at + size_t(r) * pitch);
         } else {
@@ -490,7 +548,7 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                 if (live_mask >> r & 1u) px[r] = __ldcs(fb_at + size_t(r) * pitch);
         }
     };
-    if (!(fetch_now && whole)) {
+    if (!(fetch_now && whole) || kTma) {
 #pragma unroll
         for (int r = 0; r < kWarpRows; ++r) px[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
@@ -532,6 +590,7 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
             loaded = true;
         }
         touched = touched || votes != 0;
+        if (votes) settle();
         while (votes) {
             const int src = __ffs(int(votes)) - 1;
             votes &= votes - 1u;
@@ -787,8 +846,18 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
             }
         }
     }
+    settle();                                                // (a bulk load must land before its shared memory goes away)
     if (!touched && !t.clear_first) return;                  // no job reaches these pixels: leave them alone
-    if (whole) {
+    if (kTma && whole) {
+#pragma unroll
+        for (int r = 0; r < kWarpRows; ++r) my_rows[r * 32 + lane] = px[r];
+        fence_async_proxy();
+        __syncwarp();
+        if (lane < kWarpRows) {
+            bulk_store(fb_at - lane + size_t(lane) * pitch, smem_u32(my_rows + lane * 32), 512);
+            bulk_store_commit_and_wait_read();
+        }
+    } else if (whole) {
 #pragma unroll
         for (int r = 0; r < kWarpRows; ++r) fb_at[size_t(r) * pitch] = px[r];
     } else {
@@ -847,6 +916,8 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
     // are known up front (tile_cover) and never read.  CB200_EAGER_LOAD=0 loads on first use instead.
     int eager = 1;
     if (const char *e = getenv("CB200_EAGER_LOAD")) eager = atoi(e);
+    // CB200_TMA=1: lean build whose framebuffer rows move as bulk asynchronous copies (measured A/B)
+    static const bool tma = [] { const char *e = getenv("CB200_TMA"); return e && atoi(e) != 0; }();
     if (f.row_jobs) {
         const int n_rows = ty1 - ty0 + 1;
         launch_pdl(k_row_lists, (n_rows * 32 + kBlock - 1) / kBlock, kBlock, 0, s, f, t, ty0, n_rows);
@@ -857,12 +928,14 @@ void launch_composite(const device_frame &f, const canvas_target &t, int sorted_
         else if (f.general_compositor == 3) go(k_composite<3, true>);
         else if (f.general_compositor == 2) go(k_composite<2, true>);
         else if (f.general_compositor == 1) go(k_composite<1, true>);
+        else if (tma) go(k_composite<0, true, true>);
         else go(k_composite<0, true>);
     } else {
         if (f.general_compositor == 4) go(k_composite<4, false>);
         else if (f.general_compositor == 3) go(k_composite<3, false>);
         else if (f.general_compositor == 2) go(k_composite<2, false>);
         else if (f.general_compositor == 1) go(k_composite<1, false>);
+        else if (tma) go(k_composite<0, false, true>);
         else go(k_composite<0, false>);
     }
 }

@@ -99,6 +99,10 @@ __device__ float paint_alpha(const device_frame &f, const brush_rec &b, const af
     return lo + m * (up - lo);
 }
 
+constexpr int kStreamThreads = 128;        // lines in flight per CTA; every warp works on its own
+constexpr int kStreamMaxRadius = 30;       // history 3 x (2r+3) x 128 floats <= 95 KB
+constexpr int kStreamChunk = 1024;         // longer lines are swept in pieces (with a 3(r+1) run-in)
+
 // grid: (tile stride, shadow job)
 __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb)
 {
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
     const uint32_t j = f.shadow_jobs[blockIdx.y];
     const job_rec &jr = f.jobs[j];
     const uint32_t tiles = uint32_t(jr.tw) * uint32_t(jr.th);
+    if (jr.radius <= kStreamMaxRadius) return;                 // the x sweep rasters those itself (k_blur_x)
     if (blockIdx.x * (kBlock / 32) >= tiles) return;
     const draw_rec &d = f.draws[jr.draw];
     const brush_rec &br = f.brushes[d.brush];
@@ -169,9 +174,6 @@ __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb
 }
 
 // ---- streaming blur ---------------------------------------------------------------------------
-constexpr int kStreamThreads = 128;        // lines in flight per CTA; every warp works on its own
-constexpr int kStreamMaxRadius = 30;       // history 3 x (2r+3) x 128 floats <= 95 KB
-constexpr int kStreamChunk = 1024;         // longer lines are swept in pieces (with a 3(r+1) run-in)
 
 // Histories: ring[(slot * 3 + pass) * kStreamThreads + tid], slot in [0, 2r+3): the three passes of
 // one slot sit at constant offsets from one another, and the slot a step reads is the slot the next
@@ -214,9 +216,9 @@ __global__ void __launch_bounds__(kBlock) k_blur_units(device_frame f)
         if (i < n) {
             const job_rec &jr = f.jobs[f.shadow_jobs[i]];
             if (jr.radius <= kStreamMaxRadius && jr.need_r1 > jr.need_r0) {
-                // x sweep: the 32-row strips that hold rows [need_r0, need_r1), every chunk along the row;
+                // x sweep: the tile rows (of the padded raster space) that hold rows [need_r0, need_r1), every chunk along the row;
                 // y sweep: every 32-column strip, the chunks [chunk_lo, chunk_lo + chunk_n)
-                ux = uint32_t((jr.need_r1 - 1) / 32 - jr.need_r0 / 32 + 1) * uint32_t((jr.bw + kStreamChunk - 1) / kStreamChunk);
+                ux = uint32_t((jr.top + jr.need_r1 - 1) / 32 - (jr.top + jr.need_r0) / 32 + 1) * uint32_t((jr.bw + kStreamChunk - 1) / kStreamChunk);
                 uy = uint32_t((jr.pitch + 31) / 32) * uint32_t(jr.chunk_n);
             }
         }
@@ -292,85 +294,124 @@ struct cascade {
     }
 };
 
-// Persistent grid of independent warps; each takes the next unit off a ticket counter.
-template <bool kAlongRows>
-__global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, const float *src_base, float *dst_base)
+// The sweeps run as persistent grids of independent warps; each warp takes the next unit (32 adjacent lines x one
+// chunk of some plane) off a ticket counter.  Returns false when the units are used up.
+__device__ __forceinline__ bool next_unit(const device_frame &f, bool along_x, uint32_t &job_slot, int &unit)
+{
+    const uint32_t n_jobs = f.n_shadow_jobs;
+    const uint32_t *prefix = f.blur_units + (along_x ? 0u : n_jobs + 1u);
+    uint32_t *ticket = f.blur_units + 2 * (n_jobs + 1) + (along_x ? 0 : 1);
+    uint32_t global_unit = 0;
+    if ((threadIdx.x & 31) == 0) global_unit = atomicAdd(ticket, 1u);
+    global_unit = __shfl_sync(0xffffffffu, global_unit, 0);
+    if (global_unit >= prefix[n_jobs]) return false;
+    uint32_t lo = 0, hi = n_jobs;                               // last job whose prefix <= global_unit
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (prefix[mid] <= global_unit) lo = mid; else hi = mid;
+    }
+    job_slot = lo;
+    unit = int(global_unit - prefix[lo]);
+    return true;
+}
+
+// x sweep, fused with the shadow's alpha raster (hpp:2430-2452): the lines are plane rows, a warp owns one tile row
+// of the padded raster space (lane = scanline) and walks its 32x32 tiles left to right.  A tile's samples never
+// exist in global memory: most tiles of a shadow plane hold no edge at all (empty border, solid interior), so a
+// scanline's 32 samples are ONE value -- coverage carried in from the left times the paint's alpha -- that the lane
+// already holds; tiles with edges are rastered like the compositor does it (lane = column, tile_cov.cuh) into a
+// skewed shared tile and read back by row.  Outputs leave through the same tile, so global stores stay coalesced.
+// Saves the raster's 4 B/pixel write and the sweep's 4 B/pixel read.
+__global__ void __launch_bounds__(kStreamThreads, 5) k_blur_x(device_frame f, float *dst_base)
 {
     grid_dependency_wait();
     extern __shared__ float blur_smem[];
     if (f.hdr->overflow) return;
-    const uint32_t n_jobs = f.n_shadow_jobs;
-    const uint32_t *prefix = f.blur_units + (kAlongRows ? 0u : n_jobs + 1u);
-    uint32_t *ticket = f.blur_units + 2 * (n_jobs + 1) + (kAlongRows ? 0 : 1);
-    const uint32_t n_units = prefix[n_jobs];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // x sweep: one 32 x 32 staging tile per warp (skewed), then everybody's histories
     float *tile = blur_smem + warp * 32 * 33;
-    float *ring = blur_smem + (kAlongRows ? kStreamThreads * 33 : 0) + tid;
-    for (;;) {
-        uint32_t global_unit = 0;
-        if (lane == 0) global_unit = atomicAdd(ticket, 1u);
-        global_unit = __shfl_sync(0xffffffffu, global_unit, 0);
-        if (global_unit >= n_units) break;
-        uint32_t lo = 0, hi = n_jobs;                               // last job whose prefix <= global_unit
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) / 2;
-            if (prefix[mid] <= global_unit) lo = mid; else hi = mid;
-        }
-        const job_rec &jr = f.jobs[f.shadow_jobs[lo]];
-        const int r = jr.radius;
-        const int W = 2 * r + 3, p = r + 1;
-        // lines of the y sweep are storage columns, so that a warp always covers one aligned 128 B line
-        const int len = kAlongRows ? jr.bw : jr.bh, cross = kAlongRows ? jr.bh : jr.pitch;
-        const int pitch = jr.pitch, skew = jr.skew;
-        const float *src = src_base + jr.plane_offset;
+    float *mine = tile + lane * 33;
+    float *ring = blur_smem + kStreamThreads * 33 + tid;
+    uint32_t slot;
+    int unit;
+    while (next_unit(f, true, slot, unit)) {
+        const job_rec &jr = f.jobs[f.shadow_jobs[slot]];
+        const draw_rec &d = f.draws[jr.draw];
+        const brush_rec &br = f.brushes[d.brush];
+        const int r = jr.radius, W = 2 * r + 3, p = r + 1;
+        const int len = jr.bw, pitch = jr.pitch;
         float *dst = dst_base + jr.plane_offset;
-        // the strips / chunks this canvas needs (job_rec::need_r0 ..): see k_blur_units
-        const int strip_lo = kAlongRows ? jr.need_r0 / 32 : 0;
-        const int n_strips = kAlongRows ? (jr.need_r1 - 1) / 32 - strip_lo + 1 : (cross + 31) / 32;
-        const int unit = int(global_unit - prefix[lo]);
-        const int strip = strip_lo + unit % n_strips, chunk = (kAlongRows ? 0 : jr.chunk_lo) + unit / n_strips;
-        const int line = strip * 32 + lane;
-        const bool active = kAlongRows ? (line >= jr.need_r0 && line < jr.need_r1) : (line >= skew && line < skew + jr.bw);
-        constexpr int kChunk = kAlongRows ? kStreamChunk : kBlurChunkY;
-        // outputs [y0, y1) of the line; they leave the cascade at steps [t_store, t_last)
-        const int y0 = chunk * kChunk, y1 = min(len, y0 + kChunk);
-        const int t_begin = chunk ? y0 - 3 * p : 0, t_store = y0 + 3 * p, t_last = y1 + 3 * p;
-        // steps in [plain_lo, plain_hi): no pass is left of its first or right of its last output
-        const int plain_lo = 3 * p, plain_hi = len + p;
+        // a solid brush has one alpha for the whole plane (negative: evaluate the brush per pixel)
+        const float flat_alpha = br.type == CB200_BRUSH_COLOR ? (br.n_colors ? f.colors[br.first_color].w : 0.0f) : -1.0f;
+        // tile rows that hold plane rows [need_r0, need_r1) (job_rec: what this canvas / band needs)
+        const int ty_first = (jr.top + jr.need_r0) / 32;
+        const int n_strips = (jr.top + jr.need_r1 - 1) / 32 - ty_first + 1;
+        const int ty = ty_first + unit % n_strips, chunk = unit / n_strips;
+        const int row = ty * 32 + lane - jr.top;                   // this lane's plane row
+        const bool active = row >= jr.need_r0 && row < jr.need_r1;
+        const int q_lo = max(jr.need_r0 - (ty * 32 - jr.top), 0), q_hi = min(jr.need_r1 - (ty * 32 - jr.top), 32);
+        // outputs [y0, y1) of the line; they leave the cascade at steps [y0 + 3p, t_last)
+        const int y0 = chunk * kStreamChunk, y1 = min(len, y0 + kStreamChunk);
+        const int t_begin = chunk ? y0 - 3 * p : 0, t_last = y1 + 3 * p;
+        const int plain_lo = 3 * p, plain_hi = len + p;            // steps in between need no masks
         cascade c;
         c.reset(ring, W, r, len, jr.w1, jr.w2);
-        if (kAlongRows) {
-            // lines are plane rows: stage 32 columns of the warp's 32 rows through a skewed tile so
-            // that global accesses stay coalesced; the next block is fetched while this one is swept
-            float *mine = tile + lane * 33;
-            const float *in = src + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane);
-            const int rows_here = min(32, min(cross, jr.need_r1) - strip * 32);
-            float ahead[32];
-            // whole strips away from the line's ends load without predicates; addresses are one
-            // 32-bit multiply-add off a pointer that moves once per block
-            auto fetch = [&](int tb) {
-                const float *from = in + tb;
-                if (rows_here == 32 && tb >= 0 && tb + 32 <= len) {
+        // blocks are tiles of the padded raster space: sample t of a line is padded x = left + t
+        const int t_first = t_begin - ((t_begin + jr.left) & 31);
+        float *out_rows = dst + ptrdiff_t(ty * 32 - jr.top) * ptrdiff_t(pitch) + ptrdiff_t(jr.skew + lane - 3 * p);
+        // row info of a tile in three coalesced loads (lane = scanline), requested one tile ahead
+        float carried = 0.0f; uint32_t first = kNoRun, pixels = 0;
+        auto request = [&](int tb, float &cr, uint32_t &fi, uint32_t &pm) {
+            const int tx = (jr.left + tb) / 32;
+            cr = 0.0f; fi = kNoRun; pm = 0;
+            if (tb < len && tx >= jr.tx0 && tx < jr.tx0 + jr.tw && ty >= jr.ty0 && ty < jr.ty0 + jr.th) {
+                const uint32_t at = (jr.te_base + uint32_t(ty - jr.ty0) * uint32_t(jr.tw) + uint32_t(tx - jr.tx0)) * kTile + uint32_t(lane);
+                cr = f.te_backdrop[at]; fi = f.te_first[at]; pm = f.te_mask[at];
+            }
+        };
+        request(t_first, carried, first, pixels);
+        for (int tb = t_first; tb < t_last; tb += 32) {
+            const float cr = carried; const uint32_t fi = first, pm = pixels;
+            if (tb + 32 < t_last) request(tb + 32, carried, first, pixels);
+            const int x_tile = jr.left + tb;                        // padded x of the tile's first column
+            const bool inside = tb >= 0 && tb + 32 <= len;          // every column of the tile is a sample of the line
+            const bool edges = __ballot_sync(0xffffffffu, fi != kNoRun) != 0;
+            const bool plain = tb >= plain_lo && tb + 32 <= plain_hi;
+            // (warp-uniform: the other branch shuffles)
+            if (flat_alpha >= 0.0f && !edges && (inside || __all_sync(0xffffffffu, cr == 0.0f))) {
+                // one value per scanline (a tile that sticks out of the line qualifies only when it is empty)
+                const float cov = fminf(fabsf(cr), 1.0f);
+                const float v = cov >= kThreshold ? cov * flat_alpha : 0.0f;
+                if (active) {
+                    if (plain) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) ahead[q] = from[q * pitch];
-                } else {
-                    const int col = tb + lane;
-                    const bool col_in = col >= 0 && col < len;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) ahead[q] = (col_in && q < rows_here) ? from[q * pitch] : 0.0f;
+                        for (int u = 0; u < 32; ++u) mine[u] = c.push<false>(v, 0);
+                    } else {
+#pragma unroll 8
+                        for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(unsigned(tb + u) < unsigned(len) ? v : 0.0f, tb + u);
+                    }
                 }
-            };
-            const int t_first = t_begin - ((t_begin + skew) & 31);      // blocks start on 128 B lines
-            float *out_rows = dst + size_t(strip * 32) * size_t(pitch) + size_t(skew + lane - 3 * p);
-            fetch(t_first);
-            for (int tb = t_first; tb < t_last; tb += 32) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) tile[q * 33 + lane] = ahead[q];
-                if (tb + 32 < t_last) fetch(tb + 32);
+            } else {
+                // raster the tile: lane = column, scanline by scanline
+                const int x = x_tile + lane;
+                const bool x_in = tb + lane >= 0 && tb + lane < len;
+#pragma unroll 1
+                for (int ly = 0; ly < 32; ++ly) {
+                    const float sum = pixel_sum<true>(f.cumulative, __shfl_sync(0xffffffffu, cr, ly), __shfl_sync(0xffffffffu, fi, ly),
+                                                      __shfl_sync(0xffffffffu, pm, ly));
+                    const float cov = fminf(fabsf(sum), 1.0f);
+                    float v = 0.0f;
+                    if (x_in && cov >= kThreshold && ly >= q_lo && ly < q_hi) {
+                        if (flat_alpha >= 0.0f) v = cov * flat_alpha;
+                        else {
+                            const vec2 centre = v2(float(x) + 0.5f, float(ty * 32 + ly) + 0.5f) - v2(jr.off_x, jr.off_y);
+                            v = cov * paint_alpha(f, br, d.inverse, centre);
+                        }
+                    }
+                    tile[ly * 33 + lane] = v;
+                }
                 __syncwarp();
                 if (active) {
-                    if (tb >= plain_lo && tb + 32 <= plain_hi) {
+                    if (plain) {
 #pragma unroll
                         for (int u = 0; u < 32; ++u) mine[u] = c.push<false>(mine[u], 0);
                     } else {
@@ -378,58 +419,86 @@ __global__ void __launch_bounds__(kStreamThreads) k_blur_stream(device_frame f, 
                         for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(mine[u], tb + u);
                     }
                 }
-                __syncwarp();
-                const int col = tb + lane - 3 * p;
-                if (col >= y0 && col < y1) {
-                    float *out = out_rows + tb;
-                    if (rows_here == 32) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) out[q * pitch] = tile[q * 33 + lane];
-                    } else {
-                        for (int q = 0; q < rows_here; ++q) out[q * pitch] = tile[q * 33 + lane];
-                    }
-                }
-                __syncwarp();
             }
-        } else {
-            if (!active) continue;
-            constexpr int kAhead = 8;
-            const float *in = src + size_t(line);
-            float *out = dst + size_t(line);
-            float ahead[kAhead];
-            auto fetch = [&](int tb) {
-                const float *from = in + ptrdiff_t(tb) * ptrdiff_t(pitch);
-                if (tb >= 0 && tb + kAhead <= len) {
+            __syncwarp();
+            const int col = tb + lane - 3 * p;
+            if (col >= y0 && col < y1) {
+                float *out = out_rows + tb;
+                if (q_lo == 0 && q_hi == 32) {
 #pragma unroll
-                    for (int u = 0; u < kAhead; ++u) ahead[u] = from[u * pitch];
+                    for (int q = 0; q < 32; ++q) out[q * pitch] = tile[q * 33 + lane];
                 } else {
-#pragma unroll
-                    for (int u = 0; u < kAhead; ++u) ahead[u] = unsigned(tb + u) < unsigned(len) ? from[u * pitch] : 0.0f;
+                    for (int q = q_lo; q < q_hi; ++q) out[q * pitch] = tile[q * 33 + lane];
                 }
-            };
-            // blocks of kAhead steps, laid out so that none straddles the first stored output
-            const int t_first = t_store - ((t_store - t_begin + kAhead - 1) & ~(kAhead - 1));
-            fetch(t_first);
-            for (int tb = t_first; tb < t_last; tb += kAhead) {
-                float v[kAhead];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// y sweep: the lines are storage columns, so that a warp always covers one aligned 128 B line of every row
+__global__ void __launch_bounds__(kStreamThreads, 8) k_blur_y(device_frame f, const float *src_base, float *dst_base)
+{
+    grid_dependency_wait();
+    extern __shared__ float blur_smem[];
+    if (f.hdr->overflow) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    float *ring = blur_smem + tid;
+    uint32_t slot;
+    int unit;
+    while (next_unit(f, false, slot, unit)) {
+        const job_rec &jr = f.jobs[f.shadow_jobs[slot]];
+        const int r = jr.radius, W = 2 * r + 3, p = r + 1;
+        const int len = jr.bh, pitch = jr.pitch;
+        const float *src = src_base + jr.plane_offset;
+        float *dst = dst_base + jr.plane_offset;
+        // every 32-column strip of the storage, the chunks [chunk_lo, chunk_lo + chunk_n) this canvas needs
+        const int n_strips = (pitch + 31) / 32;
+        const int strip = unit % n_strips, chunk = jr.chunk_lo + unit / n_strips;
+        const int line = strip * 32 + lane;
+        if (!(line >= jr.skew && line < jr.skew + jr.bw)) continue;
+        // outputs [y0, y1) of the line; they leave the cascade at steps [t_store, t_last)
+        const int y0 = chunk * kBlurChunkY, y1 = min(len, y0 + kBlurChunkY);
+        const int t_begin = chunk ? y0 - 3 * p : 0, t_store = y0 + 3 * p, t_last = y1 + 3 * p;
+        const int plain_lo = 3 * p, plain_hi = len + p;            // steps in between need no masks
+        cascade c;
+        c.reset(ring, W, r, len, jr.w1, jr.w2);
+        constexpr int kAhead = 8;
+        const float *in = src + size_t(line);
+        float *out = dst + size_t(line);
+        float ahead[kAhead];
+        auto fetch = [&](int tb) {
+            const float *from = in + ptrdiff_t(tb) * ptrdiff_t(pitch);
+            if (tb >= 0 && tb + kAhead <= len) {
 #pragma unroll
-                for (int u = 0; u < kAhead; ++u) v[u] = ahead[u];
-                if (tb + kAhead < t_last) fetch(tb + kAhead);
-                const bool plain = tb >= plain_lo && tb + kAhead <= plain_hi;
-                if (plain && tb < t_store) {
+                for (int u = 0; u < kAhead; ++u) ahead[u] = from[u * pitch];
+            } else {
 #pragma unroll
-                    for (int u = 0; u < kAhead; ++u) c.push<false>(v[u], 0);
-                } else if (plain && tb + kAhead <= t_last) {
-                    float *o = out + ptrdiff_t(tb - 3 * p) * ptrdiff_t(pitch);
+                for (int u = 0; u < kAhead; ++u) ahead[u] = unsigned(tb + u) < unsigned(len) ? from[u * pitch] : 0.0f;
+            }
+        };
+        // blocks of kAhead steps, laid out so that none straddles the first stored output
+        const int t_first = t_store - ((t_store - t_begin + kAhead - 1) & ~(kAhead - 1));
+        fetch(t_first);
+        for (int tb = t_first; tb < t_last; tb += kAhead) {
+            float v[kAhead];
 #pragma unroll
-                    for (int u = 0; u < kAhead; ++u) o[u * pitch] = c.push<false>(v[u], 0);
-                } else {
+            for (int u = 0; u < kAhead; ++u) v[u] = ahead[u];
+            if (tb + kAhead < t_last) fetch(tb + kAhead);
+            const bool plain = tb >= plain_lo && tb + kAhead <= plain_hi;
+            if (plain && tb < t_store) {
 #pragma unroll
-                    for (int u = 0; u < kAhead; ++u) {
-                        const float o = c.push<true>(v[u], tb + u);
-                        const int i3 = tb + u - 3 * p;
-                        if (i3 >= y0 && i3 < y1) out[size_t(i3) * size_t(pitch)] = o;
-                    }
+                for (int u = 0; u < kAhead; ++u) c.push<false>(v[u], 0);
+            } else if (plain && tb + kAhead <= t_last) {
+                float *o = out + ptrdiff_t(tb - 3 * p) * ptrdiff_t(pitch);
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) o[u * pitch] = c.push<false>(v[u], 0);
+            } else {
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) {
+                    const float o = c.push<true>(v[u], tb + u);
+                    const int i3 = tb + u - 3 * p;
+                    if (i3 >= y0 && i3 < y1) out[size_t(i3) * size_t(pitch)] = o;
                 }
             }
         }
@@ -559,8 +628,11 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
                    cudaEvent_t after_raster)
 {
     if (!f.n_shadow_jobs) { if (after_raster) cudaEventRecord(after_raster, s); return; }
-    dim3 grid(64, f.n_shadow_jobs);
-    launch_pdl(k_shadow_raster, grid, kBlock, 0, s, f, sorted_buffer);
+    // planes wider than the streaming sweeps take (r > kStreamMaxRadius) are rastered into memory first
+    if (f.max_shadow_radius > kStreamMaxRadius) {
+        dim3 grid(64, f.n_shadow_jobs);
+        launch_pdl(k_shadow_raster, grid, kBlock, 0, s, f, sorted_buffer);
+    }
     if (after_raster) cudaEventRecord(after_raster, s);
     const int longest = std::max(t.width, t.height) + f.max_shadow_pad;
     if (f.min_shadow_radius <= kStreamMaxRadius) {
@@ -569,14 +641,14 @@ void launch_shadow(const device_frame &f, const canvas_target &t, int sorted_buf
         const size_t ring_bytes = size_t(3 * w * kStreamThreads) * sizeof(float);
         const size_t row_bytes = ring_bytes + size_t(kStreamThreads * 33) * sizeof(float);
         if (row_bytes > 48 * 1024) {                             // per device, so not cached in a static
-            cudaFuncSetAttribute(k_blur_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
-            cudaFuncSetAttribute(k_blur_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
+            cudaFuncSetAttribute(k_blur_x, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
+            cudaFuncSetAttribute(k_blur_y, cudaFuncAttributeMaxDynamicSharedMemorySize, int(row_bytes));
         }
         auto resident = [](size_t smem) { return int(std::min<size_t>(16, (227 * 1024) / (smem + 1024))); };
         launch_pdl(k_blur_units, 1, kBlock, 0, s, f);
-        // x sweeps planes -> planes_tmp, then y sweeps back; small radii keep their histories in registers
-        launch_pdl(k_blur_stream<true>, kSMs * resident(row_bytes), kStreamThreads, row_bytes, s, f, f.planes, f.planes_tmp);
-        launch_pdl(k_blur_stream<false>, kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s, f, f.planes_tmp, f.planes);
+        // x sweep (rasters as it goes) -> planes_tmp, then the y sweep back into planes
+        launch_pdl(k_blur_x, kSMs * resident(row_bytes), kStreamThreads, row_bytes, s, f, f.planes_tmp);
+        launch_pdl(k_blur_y, kSMs * resident(ring_bytes), kStreamThreads, ring_bytes, s, f, f.planes_tmp, f.planes);
     }
     if (f.max_shadow_radius > kStreamMaxRadius) {
         // rows -> transpose -> rows (= columns) -> transpose back; the result ends up in f.planes
