@@ -101,7 +101,7 @@ __device__ float paint_alpha(const device_frame &f, const brush_rec &b, const af
 
 constexpr int kStreamThreads = 128;        // lines in flight per CTA; every warp works on its own
 constexpr int kStreamMaxRadius = 30;       // history 3 x (2r+3) x 128 floats <= 95 KB
-constexpr int kStreamChunk = 1024;         // longer lines are swept in pieces (with a 3(r+1) run-in)
+constexpr int kStreamChunk = 256;          // longer lines are swept in pieces (with a 3(r+1) run-in)
 
 // grid: (tile stride, shadow job)
 __global__ void __launch_bounds__(kBlock) k_shadow_raster(device_frame f, int sb)
@@ -358,40 +358,84 @@ __global__ void __launch_bounds__(kStreamThreads, 5) k_blur_x(device_frame f, fl
         // blocks are tiles of the padded raster space: sample t of a line is padded x = left + t
         const int t_first = t_begin - ((t_begin + jr.left) & 31);
         float *out_rows = dst + ptrdiff_t(ty * 32 - jr.top) * ptrdiff_t(pitch) + ptrdiff_t(jr.skew + lane - 3 * p);
-        // row info of a tile in three coalesced loads (lane = scanline), requested one tile ahead
-        float carried = 0.0f; uint32_t first = kNoRun, pixels = 0;
-        auto request = [&](int tb, float &cr, uint32_t &fi, uint32_t &pm) {
+        // A tile's row info in three coalesced loads (lane = scanline), requested two tiles ahead; the running sums
+        // after the scanline's first four runs inside the tile (tile_cov.cuh: `cumulative`, compacted per scanline)
+        // one tile ahead, once the info that says where they are has arrived.
+        struct tile_rows { float carried; uint32_t first, pixels; };
+        struct tile_sums { float s0, s1, s2, s3; };
+        auto request = [&](int tb) -> tile_rows {
             const int tx = (jr.left + tb) / 32;
-            cr = 0.0f; fi = kNoRun; pm = 0;
+            tile_rows ti = { 0.0f, kNoRun, 0u };
             if (tb < len && tx >= jr.tx0 && tx < jr.tx0 + jr.tw && ty >= jr.ty0 && ty < jr.ty0 + jr.th) {
                 const uint32_t at = (jr.te_base + uint32_t(ty - jr.ty0) * uint32_t(jr.tw) + uint32_t(tx - jr.tx0)) * kTile + uint32_t(lane);
-                cr = f.te_backdrop[at]; fi = f.te_first[at]; pm = f.te_mask[at];
+                ti.carried = f.te_backdrop[at]; ti.first = f.te_first[at];
+                ti.pixels = ti.first != kNoRun ? f.te_mask[at] : 0u;
             }
+            return ti;
         };
-        request(t_first, carried, first, pixels);
+        auto request_sums = [&](const tile_rows &ti) -> tile_sums {
+            tile_sums ts = { 0.0f, 0.0f, 0.0f, 0.0f };
+            if (ti.first != kNoRun) {
+                const float *at = f.cumulative + (ti.first & ~kRowEnds);
+                const int n = __popc(ti.pixels);
+                ts.s0 = at[0];                                     // first != kNoRun: at least one run
+                if (n > 1) ts.s1 = at[1];
+                if (n > 2) ts.s2 = at[2];
+                if (n > 3) ts.s3 = at[3];
+            }
+            return ts;
+        };
+        tile_rows next_rows = request(t_first), after_rows = request(t_first + 32);
+        tile_sums next_sums = request_sums(next_rows);
         for (int tb = t_first; tb < t_last; tb += 32) {
-            const float cr = carried; const uint32_t fi = first, pm = pixels;
-            if (tb + 32 < t_last) request(tb + 32, carried, first, pixels);
+            const tile_rows rows = next_rows;
+            tile_sums sums = next_sums;
+            next_rows = after_rows;
+            if (tb + 32 < t_last) next_sums = request_sums(next_rows);
+            if (tb + 64 < t_last) after_rows = request(tb + 64);
+            const float cr = rows.carried; const uint32_t fi = rows.first, pm = rows.pixels;
             const int x_tile = jr.left + tb;                        // padded x of the tile's first column
             const bool inside = tb >= 0 && tb + 32 <= len;          // every column of the tile is a sample of the line
             const bool edges = __ballot_sync(0xffffffffu, fi != kNoRun) != 0;
             const bool plain = tb >= plain_lo && tb + 32 <= plain_hi;
-            // (warp-uniform: the other branch shuffles)
+            // (warp-uniform: the last branch shuffles)
             if (flat_alpha >= 0.0f && !edges && (inside || __all_sync(0xffffffffu, cr == 0.0f))) {
                 // one value per scanline (a tile that sticks out of the line qualifies only when it is empty)
                 const float cov = fminf(fabsf(cr), 1.0f);
                 const float v = cov >= kThreshold ? cov * flat_alpha : 0.0f;
                 if (active) {
                     if (plain) {
-#pragma unroll
+#pragma unroll 8
                         for (int u = 0; u < 32; ++u) mine[u] = c.push<false>(v, 0);
                     } else {
 #pragma unroll 8
                         for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(unsigned(tb + u) < unsigned(len) ? v : 0.0f, tb + u);
                     }
                 }
+            } else if (flat_alpha >= 0.0f) {
+                // edges: a lane walks ITS scanline's runs left to right -- the sum changes at the pixels of `pm`,
+                // and after the scanline's last run nothing carries on (render_shadow walks the runs alone,
+                // hpp:2430-2452; pixel_sum<true> says the same per pixel)
+                if (active) {
+                    const float *more = f.cumulative + (fi & ~kRowEnds);
+                    const int last_pixel = (fi != kNoRun && (fi & kRowEnds)) ? 31 - __clz(int(pm)) : 32;
+                    float sum = cr;
+                    int taken = 0;
+#pragma unroll 8
+                    for (int u = 0; u < 32; ++u) {
+                        if (pm >> u & 1u) {
+                            if (taken < 4) { sum = sums.s0; sums.s0 = sums.s1; sums.s1 = sums.s2; sums.s2 = sums.s3; }
+                            else sum = more[taken];
+                            ++taken;
+                        }
+                        const float cov = u > last_pixel ? 0.0f : fminf(fabsf(sum), 1.0f);
+                        float v = cov >= kThreshold ? cov * flat_alpha : 0.0f;
+                        if (unsigned(tb + u) >= unsigned(len)) v = 0.0f;
+                        mine[u] = c.push<true>(v, tb + u);
+                    }
+                }
             } else {
-                // raster the tile: lane = column, scanline by scanline
+                // a brush that varies per pixel: raster the tile (lane = column, scanline by scanline), sweep it by row
                 const int x = x_tile + lane;
                 const bool x_in = tb + lane >= 0 && tb + lane < len;
 #pragma unroll 1
@@ -401,23 +445,15 @@ __global__ void __launch_bounds__(kStreamThreads, 5) k_blur_x(device_frame f, fl
                     const float cov = fminf(fabsf(sum), 1.0f);
                     float v = 0.0f;
                     if (x_in && cov >= kThreshold && ly >= q_lo && ly < q_hi) {
-                        if (flat_alpha >= 0.0f) v = cov * flat_alpha;
-                        else {
-                            const vec2 centre = v2(float(x) + 0.5f, float(ty * 32 + ly) + 0.5f) - v2(jr.off_x, jr.off_y);
-                            v = cov * paint_alpha(f, br, d.inverse, centre);
-                        }
+                        const vec2 centre = v2(float(x) + 0.5f, float(ty * 32 + ly) + 0.5f) - v2(jr.off_x, jr.off_y);
+                        v = cov * paint_alpha(f, br, d.inverse, centre);
                     }
                     tile[ly * 33 + lane] = v;
                 }
                 __syncwarp();
                 if (active) {
-                    if (plain) {
-#pragma unroll
-                        for (int u = 0; u < 32; ++u) mine[u] = c.push<false>(mine[u], 0);
-                    } else {
 #pragma unroll 8
-                        for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(mine[u], tb + u);
-                    }
+                    for (int u = 0; u < 32; ++u) mine[u] = c.push<true>(mine[u], tb + u);
                 }
             }
             __syncwarp();
