@@ -637,15 +637,35 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                 const uint2 off = __ldg(reinterpret_cast<const uint2 *>(rec) + 10);    // plane offset
                 const float *plane = f.planes + (uint64_t(off.y) << 32 | off.x);
                 const rgba tint = mk(colour.x, colour.y, colour.z, colour.w);
+                // the eight rows' plane samples are requested together (one dependent load per row, consumed right
+                // away, left 59 % of this build's stall samples on that load: config 3)
+                const bool x_ok = x >= box.x && x < box.z;
+                const float *column = plane + ptrdiff_t(row0 + place.x - place.z) * ptrdiff_t(place.w) + ptrdiff_t(x + place.x - place.y);
+                float s[kWarpRows];
+                uint32_t rows_in = 0;
 #pragma unroll
                 for (int r = 0; r < kWarpRows; ++r) {
                     const int y = row0 + r;
-                    if (!(live_mask >> r & 1u) || x < box.x || x >= box.z || y < box.y || y >= box.w) continue;
-                    float vis = mask ? fminf(fabsf(mask[size_t(y - t.band_y0) * pitch + size_t(x)]), 1.0f) : 1.0f;
-                    if (vis < kThreshold) continue;
-                    float s = plane[size_t(y + place.x - place.z) * size_t(place.w) + size_t(x + place.x - place.y)];
-                    blend(px[r], scale(alpha * s, tint), op, vis);
-                    ++painted;
+                    const bool in = (live_mask >> r & 1u) && x_ok && y >= box.y && y < box.w;
+                    s[r] = in ? __ldg(column + r * place.w) : 0.0f;
+                    rows_in |= uint32_t(in) << r;
+                }
+                if (!mask) {
+#pragma unroll
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        if (!(rows_in >> r & 1u)) continue;
+                        blend_unclipped(px[r], scale(alpha * s[r], tint), op);
+                        ++painted;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kWarpRows; ++r) {
+                        if (!(rows_in >> r & 1u)) continue;
+                        const float vis = fminf(fabsf(mask[size_t(row0 + r - t.band_y0) * pitch + size_t(x)]), 1.0f);
+                        if (vis < kThreshold) continue;
+                        blend(px[r], scale(alpha * s[r], tint), op, vis);
+                        ++painted;
+                    }
                 }
                 continue;
             }
