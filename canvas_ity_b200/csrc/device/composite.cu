@@ -441,6 +441,7 @@ __device__ __forceinline__ void blend_program(float4 &back, rgba fore, const mix
 // Used by the kTma build of the compositor: a warp's 8 framebuffer rows (512 contiguous bytes each) travel between
 // global and shared memory as eight bulk copies issued by eight lanes, completion through an mbarrier (loads) or a
 // bulk group (stores), instead of eight 16-byte LDG/STG per lane.  An A/B against the plain build.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -582,6 +583,15 @@ k_composite(device_frame f, canvas_target t, int tiles_x, int tile_y0, int eager
                     hit = true;
                     te = kNoRun;
                 }
+            }
+        }
+        if (hit) {
+            // the hits of this step are replayed one after the other; ask for what each replay starts with -- the job's
+            // record and this warp's rows of its tile entry -- now, so that those loads find their lines in L1
+            prefetch_l1(f.comp + j);
+            if (te != kNoRun && (f.job_box[j].y >> 12 & 3u) != JOB_SHADOW) {
+                const uint32_t slot = te * kTile + uint32_t(warp * kWarpRows);
+                prefetch_l1(f.te_backdrop + slot); prefetch_l1(f.te_first + slot); prefetch_l1(f.te_mask + slot);
             }
         }
         uint32_t votes = __ballot_sync(0xffffffffu, hit);
