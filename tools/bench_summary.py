@@ -8,7 +8,7 @@ p = b.get("passes", {})
 for k in ("readback", "coverage", "sort"):
     if k in p: print(k, p[k])
 c3 = p.get("config3_tiger_alpha0.9_shadow_blur16")
-if c3: print("config3 frame", c3["frame_ms"], "blur", c3["blur"]["ms"], "raster", c3["shadow_raster"]["ms"], "composite", c3["composite"]["ms"], "frac of ceiling", c3["frac_of_per_pass_hbm_ceiling"])
+if c3: print("config3 frame", c3["frame_ms"], "blur + raster", c3["blur_and_shadow_raster"]["ms"], "composite", c3["composite"]["ms"], "frac of ceiling", c3["frac_of_per_pass_hbm_ceiling"])
 c4 = p.get("config4_full_canvas_fills")
 if c4 and "fills" in c4: print("config4", {k: round(v["composite_ms"], 3) for k, v in c4["fills"].items()})
 if "config5_batch_of_256x256_canvases" in p: print("config5", p["config5_batch_of_256x256_canvases"])

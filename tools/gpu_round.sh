@@ -17,6 +17,6 @@ for k in k_png_rows k_hit_test k_glyph_instances; do      # launched a handful o
   cmd="bench.py --steps 2 --warmup 3 --lanes 1 --no-cpu-baseline"; [ $k = k_glyph_instances ] && cmd="tools/text_bench.py 2000"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $O/prof_$k python $cmd > $O/prof_$k.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_blur_stream|k_shadow_raster" -s 6 -c 3 -f -o $O/prof_shadow python tools/shadow_bench.py > $O/prof_shadow.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_blur_x|k_blur_y" -s 6 -c 2 -f -o $O/prof_shadow python tools/shadow_bench.py > $O/prof_shadow.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:k_composite -s 2 -c 1 -f -o $O/prof_fill python tools/fill_bench.py > $O/prof_fill.log 2>&1
 ls -la $O
