@@ -25,7 +25,11 @@ namespace {
 
 // ------------------------------------------------------------- job items ----
 
-__global__ void __launch_bounds__(kBlock) k_job_items(device_frame f)
+// The two per-job bookkeeping kernels run as ONE CTA (their prefix sums carry from job to job): 1024 threads, so a
+// batch of 18 K jobs takes 18 rounds of it, not 72.
+constexpr int kOneCta = 1024;
+
+__global__ void __launch_bounds__(kOneCta) k_job_items(device_frame f)
 {
     grid_dependency_wait();
     __shared__ uint32_t sm[33];
@@ -308,26 +312,49 @@ __global__ void __launch_bounds__(kBlock) k_row_emit(device_frame f)
         uint32_t total;
         uint32_t at = carry + block_exclusive_scan(valid ? f.row_runs[it] : 0u, sm, total);
         carry += total;
-        if (!valid) continue;
-        const uint32_t slot = f.row_piece[it];
-        const uint32_t tagged = f.piece_job[slot];
-        const uint32_t j = tagged & 0x7fffffffu;
-        const bool projected = (tagged >> 31) != 0;              // an excursion outside the canvas, flattened onto its boundary
-        edge_walk e = edge_setup(f.pieces[slot]);
-        row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
-        run_sink sink = { keys + at, vals + at, ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx, 0x7fffffff, -1 };
-        walk_row_runs(e, w, sink);
-        if (f.jobs[j].kind == JOB_SHADOW) {
-            // exact bounds of the runs the reference keeps (non-zero deltas) plus the
+        // (no early exit for the lanes past the end: the bounds below are combined across the warp)
+        uint32_t j = 0;
+        bool projected = false, shadow = false;
+        int lo_x = 0x7fffffff, hi_x = -1, row_y = 0;
+        uint32_t first_key = 0xffffffffu;
+        if (valid) {
+            const uint32_t slot = f.row_piece[it];
+            const uint32_t tagged = f.piece_job[slot];
+            j = tagged & 0x7fffffffu;
+            projected = (tagged >> 31) != 0;                     // an excursion outside the canvas, flattened onto its boundary
+            edge_walk e = edge_setup(f.pieces[slot]);
+            row_walk w = row_setup(e, int(f.piece_rlo[slot] + (it - f.piece_row_off[slot])));
+            run_sink sink = { keys + at, vals + at, ((uint64_t(j) << by) | uint64_t(uint32_t(w.py))) << bx, 0x7fffffff, -1 };
+            walk_row_runs(e, w, sink);
+            shadow = f.jobs[j].kind == JOB_SHADOW;
+            lo_x = sink.lo_x; hi_x = sink.hi_x; row_y = int(w.py);
+            first_key = (uint32_t(w.py) << 16) | uint32_t(w.px);
+        }
+        if (f.n_shadow_jobs) {
+            // Shadow jobs: exact bounds of the runs the reference keeps (non-zero deltas) plus the
             // smallest (y,x) run of all, which it keeps unconditionally (hpp:2244-2252).  A projected
             // piece enters nothing: its runs only cancel one another, and the boundary segment the
-            // reference's clip puts in its place is accounted for by k_shadow_boxes.
-            job_rec &jr = f.jobs[j];
-            if (sink.hi_x >= 0 && !projected) {
-                atomicMin(&jr.run_min_x, sink.lo_x); atomicMax(&jr.run_max_x, sink.hi_x);
-                atomicMin(&jr.run_min_y, int(w.py)); atomicMax(&jr.run_max_y, int(w.py));
+            // reference's clip puts in its place is accounted for by k_shadow_boxes.  Neighbouring row
+            // items nearly always belong to one job, so the lanes of a job combine their bounds first and
+            // one of them issues the atomics (one set per row item kept 1.1 M row items queueing on 305
+            // words: k_row_emit 147 us on config 3).
+            const int lane = threadIdx.x & 31;
+            const bool counts = shadow && !projected;
+            const uint32_t peers = __match_any_sync(0xffffffffu, counts ? j : 0x80000000u | uint32_t(lane));
+            const bool has_runs = counts && hi_x >= 0;
+            const int g_lo_x = __reduce_min_sync(peers, has_runs ? lo_x : 0x7fffffff);
+            const int g_hi_x = __reduce_max_sync(peers, has_runs ? hi_x : -1);
+            const int g_lo_y = __reduce_min_sync(peers, has_runs ? row_y : 0x7fffffff);
+            const int g_hi_y = __reduce_max_sync(peers, has_runs ? row_y : -1);
+            const uint32_t g_first = __reduce_min_sync(peers, counts ? first_key : 0xffffffffu);
+            if (counts && lane == __ffs(int(peers)) - 1) {
+                job_rec &jr = f.jobs[j];
+                if (g_hi_x >= 0) {
+                    atomicMin(&jr.run_min_x, g_lo_x); atomicMax(&jr.run_max_x, g_hi_x);
+                    atomicMin(&jr.run_min_y, g_lo_y); atomicMax(&jr.run_max_y, g_hi_y);
+                }
+                atomicMin(&jr.first_key, g_first);
             }
-            if (!projected) atomicMin(&jr.first_key, (uint32_t(w.py) << 16) | uint32_t(w.px));
         }
     }
 }
@@ -388,7 +415,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_boxes(device_frame f, canvas_
 
 // ------------------------------------------------------------- job tiles ----
 
-__global__ void __launch_bounds__(kBlock) k_job_tiles(device_frame f, canvas_target t)
+__global__ void __launch_bounds__(kOneCta) k_job_tiles(device_frame f, canvas_target t)
 {
     grid_dependency_wait();
     __shared__ uint32_t sm[33];
@@ -532,13 +559,13 @@ __global__ void k_clear_tiles(device_frame f)
 
 void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s)
 {
-    launch_pdl(k_job_items, 1, kBlock, 0, s, f);
+    launch_pdl(k_job_items, 1, kOneCta, 0, s, f);
     launch_pdl(k_edges, kGrid, kBlock, 0, s, f, t);
     launch_pdl(k_scan_rows, kGrid, kBlock, 0, s, f);
     launch_pdl(k_row_count, kGrid, kBlock, 0, s, f);
     launch_pdl(k_row_emit, kGrid, kBlock, 0, s, f);
     if (f.n_shadow_jobs) launch_pdl(k_shadow_boxes, kGrid, kBlock, 0, s, f, t);
-    launch_pdl(k_job_tiles, 1, kBlock, 0, s, f, t);
+    launch_pdl(k_job_tiles, 1, kOneCta, 0, s, f, t);
     launch_pdl(k_clear_tiles, kGrid, kBlock, 0, s, f);
 }
 
