@@ -123,7 +123,7 @@ struct cb200_canvas {
     dev_buf<float4> pieces, texels;
     dev_buf<comp_rec> comp;
     dev_buf<uint2> job_box;
-    dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count, loop_mark;
+    dev_buf<uint32_t> job_te, blur_units, row_jobs, row_job_count, loop_mark, job_run_begin;
     dev_buf<uint2> box_loops;
     dev_buf<leak_rec> leaks;  uint32_t cap_leaks = 0;
     dev_buf<uint32_t> tile_cover;
@@ -511,6 +511,7 @@ int ensure_capacity(cb200_canvas *cv, const staged_frame &sf, const frame_header
     CK(cv->comp.reserve(sf.jobs.size() + 1));
     CK(cv->job_box.reserve(sf.jobs.size() + 1));
     CK(cv->job_te.reserve(sf.jobs.size() + 1));
+    CK(cv->job_run_begin.reserve(sf.jobs.size() + 2));
     CK(cv->blur_units.reserve(2 * (sf.shadow_jobs.size() + 1) + 2));
     {   // tile-row job lists: rows of the target x the largest job count of a canvas (skipped when huge)
         uint32_t most = 0;
@@ -727,6 +728,8 @@ int upload_frame(cb200_canvas *cv)
     f.cap_tiles = cv->cap_tiles;
     f.planes = cv->planes.p; f.planes_tmp = cv->planes_tmp.p; f.cap_planes = cv->cap_planes;
     f.partials = cv->partials.p; f.sort_hist = cv->sort_hist.p;
+    // many small jobs (batches): every job's runs are sorted inside one CTA instead of by the global passes (sort.cu)
+    f.job_run_begin = segmented_sort_passes(sf.key_bits, sf.bits_x, sf.bits_y, sf.jobs.size()) ? cv->job_run_begin.p : nullptr;
 
     canvas_target &t = cv->target;
     t.fb = cv->fb; t.width = cv->width; t.height = cv->height;
@@ -749,8 +752,8 @@ int frame_launch_count(const cb200_canvas *cv)
     const staged_frame &sf = cv->staged;
     const device_frame &f = cv->df;
     return (sf.glyph_insts.empty() ? 0 : 1) + (sf.units.empty() ? 0 : 3) + (sf.dash_items.empty() ? 0 : 2) +
-           ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + 3 +
-           (sf.shadow_jobs.empty() ? 0 : 2 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 4 : 0)) + 1 + (f.row_jobs ? 1 : 0);
+           ((sf.sources.empty() && sf.dash_items.empty()) ? 0 : 9) + 7 + 3 * sort_passes(sf.key_bits) + (f.job_run_begin ? 2 : 0) + 3 +
+           (sf.shadow_jobs.empty() ? 0 : 1 + (f.min_shadow_radius <= 30 ? 3 : 0) + (f.max_shadow_radius > 30 ? 5 : 0)) + 1 + (f.row_jobs ? 1 : 0);
 }
 
 // The fixed launch sequence of one frame, issued into the canvas stream -- or, with `in_graph`, into a
@@ -777,7 +780,8 @@ int enqueue_frame(cb200_canvas *cv, bool in_graph)
     launch_raster(f, cv->target, s);
     if (stages) CK(cudaEventRecord(cv->ev[2], s));
     int sorted = 0;
-    launch_sort(f, s, sf.key_bits, &sorted);
+    launch_sort(f, s, sf.key_bits, &sorted, segmented_sort_passes(sf.key_bits, sf.bits_x, sf.bits_y, sf.jobs.size()),
+                sf.bits_x + sf.bits_y, uint32_t(sf.jobs.size()));
     if (stages) CK(cudaEventRecord(cv->ev[3], s));
     launch_rows(f, cv->target, sorted, s);
     if (stages) CK(cudaEventRecord(cv->ev[8], s));
@@ -1176,7 +1180,7 @@ void cb200_canvas_destroy(cb200_canvas *cv)
     cv->piece_rows.release(); cv->piece_rlo.release(); cv->piece_row_off.release();
     cv->row_runs.release(); cv->row_piece.release(); cv->te_flags.release(); cv->te_job.release(); cv->te_first.release(); cv->te_mask.release(); cv->partials.release();
     cv->sort_hist.release(); cv->pts.release(); cv->loops.release(); cv->sources.release();
-    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
+    cv->pieces.release(); cv->texels.release(); cv->comp.release(); cv->job_box.release(); cv->job_te.release(); cv->job_run_begin.release(); cv->blur_units.release(); cv->row_jobs.release(); cv->row_job_count.release(); cv->keys0.release(); cv->keys1.release();
     cv->vals0.release(); cv->vals1.release(); cv->cumulative.release(); cv->long_rows.release(); cv->te_backdrop.release();
     cv->planes.release(); cv->planes_tmp.release(); cv->rgba8.release(); cv->loop_mark.release(); cv->box_loops.release(); cv->leaks.release(); cv->tile_cover.release();
     drop_replay_graphs(cv);

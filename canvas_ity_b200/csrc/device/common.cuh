@@ -164,6 +164,7 @@ struct frame_header {
     uint32_t n_long_rows;                  // scanline segments handed to k_rows_long
     uint32_t n_leaks;                      // scanlines of source_over-like draws whose coverage does not return to 0 (leak_rec)
     uint32_t n_box_loops;                  // loops of shadow jobs that cross a side or the top of the padded canvas
+    uint32_t max_job_runs;                 // runs of the frame's largest job (k_job_runs; 0: not measured -- sort.cu)
     uint64_t plane_floats;               // storage (pitched)
     uint64_t shadow_working_pixels;      // sum of bw * bh: what the reference blurs (hpp:2426)
     uint32_t overflow;                     // bit set: which capacity was exceeded

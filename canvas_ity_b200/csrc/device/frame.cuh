@@ -76,6 +76,7 @@ struct device_frame {
     // scratch
     uint32_t *partials;                                // several kGrid-sized slices
     uint32_t *sort_hist;
+    uint32_t *job_run_begin;                           // [n_jobs + 1] first run of every job in emission order (sort.cu); null: no segmented sort
 };
 
 struct canvas_target {
@@ -101,7 +102,8 @@ void launch_join_math(const float *x, uint32_t n, float *acos_out, float *tan_ou
 // raster.cu
 void launch_raster(const device_frame &f, const canvas_target &t, cudaStream_t s);
 // sort.cu
-void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer);
+void launch_sort(const device_frame &f, cudaStream_t s, int key_bits, int *result_buffer, int seg_passes, int bits_yx, uint32_t n_jobs);
+int segmented_sort_passes(int key_bits, int bits_x, int bits_y, size_t n_jobs);
 int sort_passes(int key_bits);
 // coverage.cu
 void launch_rows(const device_frame &f, const canvas_target &t, int sorted_buffer, cudaStream_t s);
