@@ -193,12 +193,21 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
         double carry = 0.0;
         uint32_t distinct = head;                     // compacted index of the next distinct pixel (see walk_row)
         uint32_t last_slot = kNoRun;                  // (te, row) slot of the tile that holds the latest run
+        // the next 32 runs are requested while these are processed (the walk waited for memory once per step: a
+        // third of the kernel's stall samples on a batch, where nearly every scanline is a long one)
+        uint64_t key_ahead = head + uint32_t(lane) < n ? keys[head + uint32_t(lane)] : ~0ull;
+        float delta_ahead = head + uint32_t(lane) < n ? delta[head + uint32_t(lane)] : 0.0f;
         for (uint32_t base = head;; base += 32) {
             uint32_t idx = base + uint32_t(lane);
-            uint64_t key = idx < n ? keys[idx] : ~0ull;
+            const uint64_t key = key_ahead;
+            const float dv = delta_ahead;
+            key_ahead = idx + 32 < n ? keys[idx + 32] : ~0ull;
+            delta_ahead = idx + 32 < n ? delta[idx + 32] : 0.0f;
             bool valid = (key >> bx) == row;
-            uint64_t nkey = idx + 1 < n ? keys[idx + 1] : ~0ull;
-            double v = valid ? double(delta[idx]) : 0.0;
+            // the key that follows mine: my neighbour's, or the first of the next step
+            const uint64_t key_right = __shfl_down_sync(0xffffffffu, key, 1), key_next_step = __shfl_sync(0xffffffffu, key_ahead, 0);
+            const uint64_t nkey = lane == 31 ? key_next_step : key_right;
+            double v = valid ? double(dv) : 0.0;
             double incl = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(kBlock) k_rows_long(device_frame f, int sb)
             // k_clear_tiles; this warp is the only writer of the row)
             const uint32_t peers = __match_any_sync(0xffffffffu, slot);
             const uint32_t bits = __reduce_or_sync(peers, final_of_pixel ? 1u << (x % kTile) : 0u);
-            if (slot != kNoRun && lane == __ffs(int(peers)) - 1 && bits) f.te_mask[slot] |= bits;
+            if (slot != kNoRun && lane == __ffs(int(peers)) - 1 && bits) atomicOr(&f.te_mask[slot], bits);   // fire and forget (a load-or-store waited for the load)
             uint32_t vm = __ballot_sync(0xffffffffu, valid);
             int last_lane = 31 - __clz(int(vm));
             carry += __shfl_sync(0xffffffffu, incl, last_lane);
