@@ -22,7 +22,7 @@ namespace cb200 {
 
 namespace {
 
-constexpr uint32_t kShortRow = 16;      // longer scanline segments go to the warp-cooperative kernel (48 -> 16: the CTA no longer waits at its barrier behind one long walk; coverage 0.141 -> 0.124 ms on the tiger)
+constexpr uint32_t kShortRow = 24;      // longer scanline segments go to the warp-cooperative kernel (48 made the CTA wait at its barrier behind single long walks; 16 sent too many 17-24-run rows to a warp once k_rows_long prefetched: tiger coverage 0.127 -> 0.120 ms, batch of 2048 canvases 27.4 -> 26.9 ms)
 
 // What is left over after the last run of a scanline.  render_main and clip (hpp:2551-2605, 3057-3099) walk the
 // runs merged with the clip mask's, whose last run of a row sits at the right canvas edge: the residue carries on
