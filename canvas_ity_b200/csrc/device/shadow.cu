@@ -1,22 +1,21 @@
 // shadow.cu -- K9: drop shadows (reference render_shadow, hpp:2395-2539).
 //
-//   k_shadow_raster  per 32x32 tile of a shadow job's working rectangle (padded
-//                    canvas space): coverage * paint.alpha -> float plane
-//                    (hpp:2430-2452), coverage rebuilt from the sorted runs exactly
-//                    like the compositor does (tile_cov.cuh)
-//   k_blur_stream    the three extended-box passes (Gwosdek et al.) of one axis, zero outside the
-//                    working rectangle (hpp:2453-2503), as ONE streaming sweep: a thread owns one
-//                    line (a plane row for the x axis, a plane column for the y axis) and pushes
-//                    every sample through three cascaded running sums whose 2r+3-deep histories
-//                    live in shared memory.  A step is the reference's four-term update of the
-//                    window sum (hpp:2463-2479) written as two differences and two fused
-//                    multiply-adds; sweeps restart every chunk, so the result stays within ~1e-7 of
-//                    the reference's own running sum (the plane is only ever a factor of the
-//                    composite, hpp:2519-2523).  One global read + one write per pixel and axis
-//                    (16 B per working pixel for the whole blur = the algorithmic figure).
-//   k_blur_rows      fallback for radii whose history does not fit (r > kStreamMaxRadius): the
-//   k_transpose      three passes per row in shared memory, each output a windowed sum, with
-//                    32x32 tiled transposes around the column passes.
+//   k_blur_x         x sweep FUSED with the shadow's alpha raster (hpp:2430-2452): a warp owns one tile row
+//   k_blur_y         of the padded raster space and produces its samples as it sweeps -- one value per
+//                    scanline in tiles without edges, the scanline's own runs otherwise -- so the alpha
+//                    plane is never written or read.  Both sweeps run the three extended-box passes
+//                    (Gwosdek et al.) of their axis, zero outside the working rectangle (hpp:2453-2503),
+//                    as ONE streaming pass: a thread owns one line (a plane row for x, a storage column
+//                    for y) and pushes every sample through three cascaded running sums whose 2r+3-deep
+//                    histories live in shared memory.  A step is the reference's four-term update of the
+//                    window sum (hpp:2463-2479) written as two differences and two fused multiply-adds;
+//                    sweeps restart every chunk, so the result stays within ~1e-7 of the reference's own
+//                    running sum (the plane is only ever a factor of the composite, hpp:2519-2523).
+//   k_blur_units     prefix sums of the sweeps' work units (32 lines x one chunk) over all planes
+//   k_shadow_raster  only for radii whose history does not fit (r > kStreamMaxRadius): coverage *
+//   k_blur_rows      paint.alpha -> float plane per 32x32 tile (tile_cov.cuh), then the three passes per
+//   k_transpose      row in shared memory, each output a windowed sum, with 32x32 tiled transposes
+//                    around the column passes.
 // The blurred plane is consumed by the tile compositor (composite.cu).
 #include "frame.cuh"
 #include "tile_cov.cuh"
