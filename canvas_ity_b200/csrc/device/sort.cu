@@ -10,6 +10,8 @@
 //   k_sort_scatter  each CTA re-reads its slice in order, 2048 keys (8 per thread) per step;
 //                   ranks are made stable with warp match + per-warp digit counts; the step is
 //                   regrouped by digit in shared memory before it is stored
+// Frames of many small jobs (batches of small canvases) are sorted job by job instead, each job's range inside one
+// CTA and by its (y, x) bits only: k_job_runs + k_sort_jobs (see segmented_sort_applies below).
 #include "frame.cuh"
 
 namespace cb200 {
