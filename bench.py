@@ -629,9 +629,66 @@ def config5_pass(lib, H, _native, n, rank, world, local, barrier, torch, dist):
     ms = torch.tensor([float(np.median(frames_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return {"canvases": n * world, "canvases_per_gpu": n, "frame_ms": float(ms[0]), "canvases_per_s": n * world / (float(ms[0]) * 1e-3),
-            "canvases_per_s_per_gpu": n / (float(ms[0]) * 1e-3), "draws": draws, "raw_runs": runs, "stages_ms_rank0": stage,
-            "sort_gkeys_per_s": runs / stage["sort"] / 1e6 if stage and stage["sort"] else None}
+    out = {"canvases": n * world, "canvases_per_gpu": n, "frame_ms": float(ms[0]), "canvases_per_s": n * world / (float(ms[0]) * 1e-3),
+           "canvases_per_s_per_gpu": n / (float(ms[0]) * 1e-3), "draws": draws, "raw_runs": runs, "stages_ms_rank0": stage,
+           "sort_gkeys_per_s": runs / stage["sort"] / 1e6 if stage and stage["sort"] else None}
+    out["in_flight"] = config5_in_flight(lib, scripts, n, world, local, barrier, torch, dist)
+    return out
+
+
+def config5_in_flight(lib, scripts, n, world, local, barrier, torch, dist, parts=4, steps=3, regions=3):
+    """The same canvases of this rank as `parts` batches on `parts` streams, replayed concurrently from their resident
+    frames (cb200_frame_keep + cb200_frame_replay, like the tiger's lanes): most kernels of a batch frame are latency-
+    or occupancy-bound, so frames in flight fill one another's idle issue slots.  Span from the earliest begin to the
+    latest end event, one untimed frame queued first; canvases/s = canvases x steps / median span (max over ranks)."""
+    batches, devs = [], []
+    ms = C.c_float()
+    try:
+        for k in range(parts):
+            mine = scripts[k::parts]
+            b = lib.cv_batch_create(len(mine), 256, 256, local)
+            if not b:
+                return {"error": lib.cv_last_error().decode()}
+            batches.append(b)
+            for i, s in enumerate(mine):
+                lib.cv_run_script(lib.cv_batch_canvas(b, i), s, len(s), None, 0, None)
+            assert lib.cv_batch_flush(b) == 0, lib.cv_last_error()
+            dev = lib.cv_batch_device(b)
+            assert lib.cb200_frame_keep(dev) == 0, lib.cb200_last_error()
+            assert lib.cb200_set_stage_timing(dev, 0) == 0
+            devs.append(dev)
+        for d in devs:                                          # first replay verifies the frame, later ones are graph launches
+            assert lib.cb200_frame_replay(d, 1) == 0, lib.cb200_last_error()
+        for d in devs:
+            assert lib.cb200_sync(d) == 0
+        spans = []
+        for _ in range(regions):
+            for d in devs:
+                assert lib.cb200_frame_replay(d, 1) == 0
+            barrier()
+            for d in devs:
+                assert lib.cb200_timer_begin(d) == 0
+            for _ in range(steps):
+                for d in devs:
+                    assert lib.cb200_frame_replay(d, 1) == 0
+            for d in devs:
+                assert lib.cb200_timer_stop(d) == 0
+            span = 0.0
+            for d in devs:
+                assert lib.cb200_timer_end(d, C.byref(ms), None, None) == 0
+            for a in devs:
+                for b in devs:
+                    assert lib.cb200_timer_between(a, b, C.byref(ms)) == 0
+                    span = max(span, ms.value)
+            spans.append(span)
+    finally:
+        for b in batches:
+            lib.cv_batch_destroy(b)
+    span = torch.tensor([float(np.median(spans))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(span, op=dist.ReduceOp.MAX)
+    return {"batches_in_flight": parts, "steps": steps, "span_ms": float(span[0]), "frame_ms": float(span[0]) / steps,
+            "canvases_per_s": n * world * steps / (float(span[0]) * 1e-3), "canvases_per_s_per_gpu": n * steps / (float(span[0]) * 1e-3)}
 
 
 def config3_bands_pass(lib, H, _native, sharding, size, shadow_kw, rank, world, local, barrier, torch, dist):

@@ -79,6 +79,7 @@ SIGNATURES = {
     "cb200_submit": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_upload": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "cb200_frame_replay": (C.c_int, [C.c_void_p, C.c_int]),
+    "cb200_frame_keep": (C.c_int, [C.c_void_p]),
     "cb200_set_graph_replay": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_sync": (C.c_int, [C.c_void_p]),
     "cb200_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5),

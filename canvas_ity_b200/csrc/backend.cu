@@ -1230,6 +1230,18 @@ int cb200_frame_upload(cb200_canvas *cv, const cb200_frame *frame)
     return CB200_OK;
 }
 
+int cb200_frame_keep(cb200_canvas *cv)
+{
+    if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(cv->device));
+    int rc = finish_pending(cv);                 // completed (and re-run with larger buffers if it had to be)
+    if (rc != CB200_OK) return rc;
+    if (!cv->staged.valid || cv->staged.draws.empty()) return fail(CB200_ERR_BAD_ARG, "no frame submitted");
+    cv->resident = true;
+    cv->replay_verified = false;
+    return CB200_OK;
+}
+
 int cb200_frame_replay(cb200_canvas *cv, int clear)
 {
     if (!cv) return fail(CB200_ERR_BAD_ARG, "null argument");

@@ -209,6 +209,10 @@ int cb200_submit(cb200_canvas *canvas, const cb200_frame *frame);
  * (device-resident timing; the framebuffer is cleared first when `clear`). */
 int cb200_frame_upload(cb200_canvas *canvas, const cb200_frame *frame);
 int cb200_frame_replay(cb200_canvas *canvas, int clear);
+/* Keep the frame that was submitted last (cb200_submit or cb200_batch_submit) as the resident frame: waits for it to
+ * complete, then cb200_frame_replay re-runs it.  This is how a whole batch is replayed (its frame is assembled from the
+ * members' frames at submission, there is no single cb200_frame to upload). */
+int cb200_frame_keep(cb200_canvas *canvas);
 
 /* Replays of a resident frame that has completed once are issued as ONE CUDA graph launch (the frame's
  * ~36 kernels with their programmatic-dependent-launch edges, header restore and readback) instead

@@ -316,6 +316,38 @@ def test_batch_equals_individual_canvases(lib):
         lib.cv_batch_destroy(batch)
 
 
+def test_a_batch_frame_can_be_kept_and_replayed(lib):
+    """cb200_frame_keep makes the batch's last frame resident; cb200_frame_replay then re-renders all members (also
+    as a CUDA graph, also several times back to back) with exactly the bits of the first render -- and a frame of 1200
+    jobs takes the job-segmented sort (>= 1024 jobs), whose order must equal the global sort's that the solo renders use."""
+    n, size = 140, 256                                      # 140 canvases x ~9 jobs: above the segmented sort's threshold
+    scripts = [H.config5_script(i) for i in range(n)]
+    batch = lib.cv_batch_create(n, size, size, 0)
+    assert batch, lib.cv_last_error()
+    try:
+        for i, s in enumerate(scripts):
+            H._run(lib, lib.cv_batch_canvas(batch, i), s)
+        assert lib.cv_batch_flush(batch) == 0, lib.cv_last_error()
+        picks = [0, 1, 57, n - 1]
+        first = {}
+        for i in picks:
+            first[i] = np.zeros((size, size, 4), np.float32)
+            assert lib.cv_batch_read_f32(batch, i, first[i].ctypes.data) == 0
+            alone = H.render_script(lib, scripts[i], size, size)
+            assert np.array_equal(first[i].view(np.uint32), alone["f32"].view(np.uint32)), "canvas %d differs from solo render" % i
+        dev = lib.cv_batch_device(batch)
+        assert lib.cb200_frame_keep(dev) == 0, lib.cb200_last_error()
+        for _ in range(3):
+            assert lib.cb200_frame_replay(dev, 1) == 0, lib.cb200_last_error()
+        assert lib.cb200_sync(dev) == 0
+        for i in picks:
+            again = np.zeros((size, size, 4), np.float32)
+            assert lib.cv_batch_read_f32(batch, i, again.ctypes.data) == 0
+            assert np.array_equal(again.view(np.uint32), first[i].view(np.uint32)), "canvas %d changed under replay" % i
+    finally:
+        lib.cv_batch_destroy(batch)
+
+
 def test_batch_with_clip_masks_and_odd_size(lib):
     """Batch canvases whose height is not a multiple of the tile size, with clips and shadows."""
     n, w, h = 5, 100, 77
